@@ -1,0 +1,271 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (via the thin Python mirror),
+against the CPU oracle on identical seeded inputs.  Tolerance (BASELINE.json north_star):
+rel-RMS <= 1e-5 and max-abs <= 1e-4 per output sample, f32 -- see tests/parity.py.
+"""
+import numpy as np
+import pytest
+
+import closed_forms as cf
+import golden_vectors as gv
+import stimulus
+from oracle import pyoracle as po
+from parity import assert_parity, errors
+
+pytestmark = pytest.mark.gpu
+
+import yagi_b200 as yb  # noqa: E402
+
+A, S = yb.ANALYZER, yb.SYNTHESIZER
+
+
+def _rand_c(rng, n):
+    return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+
+
+def _oracle_analysis(M, m, x, h=None, as_=60.0):
+    q = po.FirPfbCh2.new(po.ANALYZER, M, m, h) if h is not None else po.FirPfbCh2.new_kaiser(po.ANALYZER, M, m, as_)
+    return q.execute_block(x)
+
+
+# ------------------------------------------------------------------ firpfbch2 analysis
+def test_config1_M16_m5_65536_samples():
+    """BASELINE config #1: firpfbch2 analysis M=16 m=5 on 65536 cf32 samples vs the CPU path."""
+    M, m, N = 16, 5, 65536
+    x = stimulus.noise_plus_tones(0, N, M)
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    np.testing.assert_array_equal(q.get_taps(), po.FirPfbCh2.new_kaiser(po.ANALYZER, M, m, 60.0).taps())
+    y = q.execute_block(x)
+    assert y.size == 2 * N
+    assert_parity(y, _oracle_analysis(M, m, x), "config #1")
+
+
+def test_config3_geometry_M256_m7_prefix():
+    """BASELINE config #3 geometry (M=256, m=7) on a 2^20-sample prefix vs the oracle."""
+    M, m, N = 256, 7, 1 << 20
+    x = stimulus.noise_plus_tones(0, N, M)
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    y = q.execute_block(x)
+    rel, mx = assert_parity(y, _oracle_analysis(M, m, x), "config #3 prefix")
+    # attribute: both vs the f64 closed form on the first 64 frames
+    ref64 = cf.firpfbch2_analysis(q.get_taps(), M, m, x[: 64 * M // 2]).reshape(-1)
+    r_gpu, _ = errors(y[: 64 * M], ref64)
+    assert r_gpu < 5e-6
+
+
+@pytest.mark.parametrize("M,m", [(2, 1), (4, 3), (6, 2), (8, 5), (12, 4), (32, 5), (64, 3), (100, 2), (128, 4),
+                                 (512, 3), (1024, 4), (2048, 2)])
+def test_analysis_geometries_random_prototype(M, m):
+    """Edge geometries incl. non-power-of-two M, arbitrary (non-Kaiser) prototypes, odd frame counts."""
+    rng = np.random.default_rng(M * 31 + m)
+    h = rng.standard_normal(2 * M * m + 1).astype(np.float32)        # one spare tap: must be ignored
+    K = 8 * m + 3
+    x = _rand_c(rng, K * M // 2)
+    q = yb.FirPfbCh2.new(A, M, m, h)
+    y = q.execute_block(x)
+    ref = _oracle_analysis(M, m, x, h=h)
+    scale = max(1.0, np.abs(ref).max())
+    assert_parity(y / scale, ref / scale, "M=%d m=%d" % (M, m))
+
+
+@pytest.mark.parametrize("M,m", [(16, 5), (256, 7), (6, 2)])
+def test_state_continuity_uneven_blocks_reset_clone(M, m):
+    """Archetypes 4/5: block-vs-sample, uneven block sizes with odd counts
+    (parity flag), reset, and clone-mid-stream producing bit-identical continuations."""
+    K = 300 if M <= 16 else 96
+    x = stimulus.noise_plus_tones(0, K * M // 2, M)
+    ref = _oracle_analysis(M, m, x)
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    cuts = [0, 1, 2, 5, 6, 37, 38, 71, K]
+    ys = [q.execute_block(x[a * M // 2: b * M // 2]) for a, b in zip(cuts, cuts[1:])]
+    y = np.concatenate(ys)
+    assert_parity(y, ref, "uneven blocks")
+    one = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0).execute_block(x)
+    assert_parity(one, ref, "one block")
+    # frame-at-a-time `execute`
+    q.reset()
+    y1 = np.concatenate([q.execute(x[k * M // 2:(k + 1) * M // 2]) for k in range(9)])
+    assert_parity(y1, ref[: 9 * M], "execute()")
+    # reset after an odd number of frames clears the flag
+    q.reset()
+    assert_parity(q.execute_block(x), ref, "after reset")
+    # clone mid-stream at an odd frame count
+    q.reset()
+    q.execute_block(x[: 7 * M // 2])
+    c = q.clone()
+    a = q.execute_block(x[7 * M // 2: 40 * M // 2])
+    b = c.execute_block(x[7 * M // 2: 40 * M // 2])
+    np.testing.assert_array_equal(a, b)
+    assert_parity(a, ref[7 * M: 40 * M], "clone continuation")
+
+
+def test_state_get_set_and_time_shards():
+    """Shard hand-off: shards primed with set_state(halo) reproduce the single pass,
+    including a cut +-2 frames around each boundary."""
+    M, m, K = 256, 7, 512
+    x = stimulus.noise_plus_tones(0, K * M // 2, M)
+    whole = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0).execute_block(x).reshape(K, M)
+    ref = _oracle_analysis(M, m, x).reshape(K, M)
+    assert_parity(whole, ref, "whole")
+    for ws in (2, 3, 8):
+        shards = yb.firpfbch2_time_shards(K, M, m, ws)
+        parts = []
+        for sh in shards:
+            q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+            assert q.state_len() == sh.halo_len
+            q.set_state(stimulus.noise_plus_tones(sh.halo_begin, sh.halo_len, M), 0)
+            parts.append(q.execute_block(x[sh.sample_begin: sh.sample_end]))
+        y = np.concatenate(parts).reshape(K, M)
+        assert_parity(y, ref, "ws=%d" % ws)
+        for sh in shards[1:]:
+            b = sh.frame_begin
+            np.testing.assert_allclose(y[b - 2: b + 2], whole[b - 2: b + 2], atol=2e-6)
+    # get_state returns exactly the last (4m-1) M/2 inputs and the parity
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    q.execute_block(x[: 33 * M // 2])
+    hist, flag = q.get_state()
+    assert flag == 1
+    np.testing.assert_array_equal(hist, x[33 * M // 2 - q.state_len(): 33 * M // 2])
+
+
+@pytest.mark.parametrize("n", [2, 4, 6, 8, 10, 16, 20, 22, 24, 26, 30, 32, 36, 48, 64, 92, 96, 120, 130, 192])
+def test_fft_stage_against_reference_golden_vectors(n):
+    """Pins the CUDA IFFT stage on the reference's own Fft golden pairs (src/fft/test_data.rs),
+    oracle-free: with the prototype h[0..M) = 1 (else 0) the analyser is a pure backward DFT:
+    frame 1 gives y = (1/M) IDFT_unnorm(roll(V, M/2)), V[b] = s[M-1-b].  Feed s so that the rolled
+    V equals the golden Y; the output must be the golden X (tolerance 2e-4, src/fft/mod.rs:125-151)."""
+    G = gv.load()
+    X, Y = G["FFT_TEST_X%d" % n], G["FFT_TEST_Y%d" % n]
+    M = n
+    h = np.zeros(2 * M, dtype=np.float32)
+    h[:M] = 1.0
+    V = np.roll(Y, -M // 2)                 # roll(V, +M/2) == Y
+    s = V[::-1].astype(np.complex64)        # V[b] = s[M-1-b]
+    q = yb.FirPfbCh2.new(A, M, 1, h)
+    y = q.execute_block(s).reshape(2, M)[1]
+    assert np.abs(y - X).max() < 2e-4
+
+
+def test_device_pointer_api_matches_host_api():
+    import torch
+    M, m, K = 256, 7, 256
+    x = stimulus.noise_plus_tones(0, K * M // 2, M)
+    yh = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0).execute_block(x)
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    xd = torch.from_numpy(x).cuda()
+    y1 = q.execute_block(xd[: 100 * M // 2])
+    y2 = q.execute_block(xd[100 * M // 2:])
+    torch.cuda.synchronize()
+    yd = torch.cat([y1, y2]).cpu().numpy()
+    np.testing.assert_array_equal(yd, yh)
+    assert q.last_path() in (1, 2)
+    assert q.last_kernel_ms() > 0.0
+
+
+# ------------------------------------------------------------------ firpfbch2 synthesis
+@pytest.mark.parametrize("M,m", [(2, 1), (6, 2), (16, 5), (64, 3), (256, 7), (1024, 4)])
+def test_synthesis_vs_oracle(M, m):
+    rng = np.random.default_rng(M + m)
+    K = 12 * m + 5
+    X = _rand_c(rng, K * M)
+    q = yb.FirPfbCh2.new_kaiser(S, M, m, 60.0)
+    cuts = [0, 1, 4, 5, K]
+    y = np.concatenate([q.execute_block(X[a * M: b * M]) for a, b in zip(cuts, cuts[1:])])
+    ref = po.FirPfbCh2.new_kaiser(po.SYNTHESIZER, M, m, 60.0).execute_block(X)
+    scale = max(1.0, np.abs(ref).max())
+    assert_parity(y / scale, ref / scale, "synthesis M=%d" % M)
+    c = q.clone()
+    v = _rand_c(rng, 6 * M)
+    np.testing.assert_array_equal(q.execute_block(v), c.execute_block(v))
+
+
+@pytest.mark.parametrize("M", [8, 16, 32, 64])
+def test_firpfbch2_crcf_reconstruction(M):
+    """autotest firpfbch2_crcf_n8..n64 on the CUDA path: analysis -> synthesis, delay 2Mm - M/2 + 1, tol 1e-3."""
+    m = 5
+    nb = 8 * m * 2
+    n = nb * M // 2
+    s = 1
+    x = np.empty(n, dtype=np.complex64)
+    for i in range(n):
+        s = (s * 524287) % 1031
+        x[i] = np.exp(2j * np.pi * s / 1031.0)
+    qa = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    qs = yb.FirPfbCh2.new_kaiser(S, M, m, 60.0)
+    y = qs.execute_block(qa.execute_block(x))
+    D = 2 * M * m - M // 2 + 1
+    assert np.abs(y[:D]).max() < 1e-3
+    assert np.abs(y[D:] - x[: n - D]).max() < 1e-3
+
+
+def test_config4_roundtrip_M1024_m4():
+    """BASELINE config #4 (reduced length): analysis -> synthesis round trip, M=1024 m=4,
+    channel matrix and reconstruction vs the CPU path."""
+    M, m, N = 1024, 4, 1 << 19
+    x = stimulus.noise_plus_tones(0, N, M)
+    qa = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    qs = yb.FirPfbCh2.new_kaiser(S, M, m, 60.0)
+    Y = qa.execute_block(x)
+    y = qs.execute_block(Y)
+    oa = po.FirPfbCh2.new_kaiser(po.ANALYZER, M, m, 60.0)
+    os_ = po.FirPfbCh2.new_kaiser(po.SYNTHESIZER, M, m, 60.0)
+    Yr = oa.execute_block(x)
+    yr = os_.execute_block(Yr)
+    assert_parity(Y, Yr, "channel matrix")
+    assert_parity(y, yr, "reconstruction")
+    D = 2 * M * m - M // 2 + 1
+    assert np.abs(y[D:] - x[: N - D]).max() < 2e-3
+
+
+# ------------------------------------------------------------------ firpfbch
+@pytest.mark.parametrize("M,p,S_", [(1, 3, 1), (4, 5, 3), (5, 4, 2), (64, 14, 8), (16, 6, 5)])
+def test_firpfbch_streams_vs_oracle(M, p, S_):
+    rng = np.random.default_rng(M * 7 + p)
+    h = rng.standard_normal(M * p).astype(np.float32)
+    Q = 3 * p + 2
+    x = _rand_c(rng, S_ * Q * M).reshape(S_, Q * M)
+    for type_, otype in ((A, po.ANALYZER), (S, po.SYNTHESIZER)):
+        q = yb.FirPfbCh.new(type_, M, p, h, n_streams=S_)
+        cut = (Q // 2) * M
+        y = np.concatenate([q.execute_block(np.ascontiguousarray(x[:, :cut])).reshape(S_, -1),
+                            q.execute_block(np.ascontiguousarray(x[:, cut:])).reshape(S_, -1)], axis=1)
+        ref = np.stack([po.FirPfbCh.new(otype, M, p, h).execute_block(x[s]) for s in range(S_)])
+        scale = max(1.0, np.abs(ref).max())
+        assert_parity(y / scale, ref / scale, "firpfbch type=%d" % int(type_))
+
+
+def test_config5_geometry_firpfbch_M64_m7():
+    """BASELINE config #5 geometry (M=64, m=7 Kaiser), 16 streams x 2^12 samples."""
+    M, m, S_, N = 64, 7, 16, 1 << 12
+    x = np.stack([stimulus.noise_plus_tones(0, N, M, stream=s) for s in range(S_)])
+    q = yb.FirPfbCh.new_kaiser(A, M, m, 60.0, n_streams=S_)
+    y = q.execute_block(x).reshape(S_, -1)
+    ref = np.stack([po.FirPfbCh.new_kaiser(po.ANALYZER, M, m, 60.0).execute_block(x[s]) for s in range(S_)])
+    scale = max(1.0, np.abs(ref).max())
+    assert_parity(y / scale, ref / scale, "config #5 geometry")
+
+
+# ------------------------------------------------------------------ firfilt
+@pytest.mark.parametrize("case", gv.FIRFILT_CASES)
+def test_firfilt_reference_golden_vectors(case):
+    G = gv.load()
+    h, x, yr = (G["FIRFILT_CRCF_DATA_%s_%s" % (case, k)] for k in "HXY")
+    y = yb.FirFilt.new(h).execute_block(x.astype(np.complex64))
+    np.testing.assert_allclose(y, yr, atol=1e-3, rtol=1e-3)          # firfilt.rs:851-919 tolerance
+
+
+def test_config2_geometry_firfilt_63_taps():
+    """BASELINE config #2 geometry: 63-tap Kaiser firfilt over many streams, with state continuity."""
+    S_, N = 64, 1 << 13
+    h = yb.fir_design_kaiser(63, 0.25, 60.0, 0.0)
+    np.testing.assert_array_equal(h, po.fir_design_kaiser(63, 0.25, 60.0, 0.0))
+    x = np.stack([stimulus.noise_plus_tones(0, N, 256, stream=s) for s in range(S_)])
+    q = yb.FirFilt.new(h, n_streams=S_)
+    q.set_scale(0.5)
+    cuts = [0, 1, 63, 64, 1000, N]
+    y = np.concatenate([q.execute_block(np.ascontiguousarray(x[:, a:b])).reshape(S_, -1) for a, b in zip(cuts, cuts[1:])], axis=1)
+    ref = np.stack([po.firfilt_crcf(h, x[s], scale=0.5) for s in range(S_)])
+    assert_parity(y, ref, "config #2 geometry")
+    assert q.get_scale() == 0.5
+    q.reset()
+    y2 = q.execute_block(x).reshape(S_, -1)
+    assert_parity(y2, ref, "after reset")

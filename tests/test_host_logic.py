@@ -1,0 +1,126 @@
+"""CPU-side tests of the product's host logic: C ABI surface, constructor validation, sharding.
+
+No compute calls are made here (there is no GPU in the build container); validation runs
+before any device is touched, so Config errors are observable on CPU.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import yagi_b200 as yb
+from yagi_b200 import _lib
+from yagi_b200.sharding import firpfbch2_time_shards, stream_shards
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "yagi_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(yg_[A-Za-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 45
+    L = C.CDLL(_lib.path()) if os.path.exists(_lib.path()) else _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), "missing export: " + name
+    assert sorted(_lib.SYMBOLS) == declared          # the ctypes binding covers the whole header
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (yg_\w+)", out))
+    assert exported == set(declared)
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_version_and_error_string():
+    L = _lib.lib()
+    assert L.yg_version() == 0x000100
+    n = C.c_int32(-1)
+    assert L.yg_device_count(C.byref(n)) == 0 and n.value >= 0
+
+
+def test_fir_design_kaiser_matches_formula_and_validates():
+    h = yb.fir_design_kaiser(3585, 1.0 / 256, 60.0, 0.0)
+    n = 3585
+    beta = 0.1102 * (60.0 - 8.7)
+    t = np.arange(n) - (n - 1) / 2.0
+    r = 2 * t / (n - 1)
+    ref = np.sinc(2 * t / 256) * np.i0(beta * np.sqrt(1 - r * r)) / np.i0(beta)
+    assert np.abs(h - ref).max() < 5e-6
+    for bad in [(0, 0.1, 60, 0), (10, 0.0, 60, 0), (10, 0.6, 60, 0), (10, 0.1, 0, 0), (10, 0.1, 60, -0.5), (10, 0.1, 60, 0.6)]:
+        with pytest.raises(yb.ConfigError):
+            yb.fir_design_kaiser(*bad)
+
+
+def test_firpfbch2_crcf_config():
+    """autotest firpfbch2_crcf_config through the product ABI (validation precedes device use)."""
+    for bad in [(77, 76, 12), (yb.ANALYZER, 0, 12), (yb.ANALYZER, 17, 12), (yb.ANALYZER, 76, 0)]:
+        with pytest.raises(yb.ConfigError):
+            yb.FirPfbCh2.new_kaiser(bad[0], bad[1], bad[2], 60.0)
+    with pytest.raises(yb.ConfigError):
+        yb.FirPfbCh2.new(yb.ANALYZER, 8, 3, np.zeros(47, dtype=np.float32))
+    with pytest.raises(yb.ConfigError):
+        yb.FirPfbCh2.new_kaiser(yb.SYNTHESIZER, 8, 3, 0.0)        # As must be > 0 (kaiser.rs:27-29)
+
+
+def test_firpfbch_and_firfilt_config():
+    for bad in [(77, 8, 4), (yb.ANALYZER, 0, 4), (yb.ANALYZER, 8, 0)]:
+        with pytest.raises(yb.ConfigError):
+            yb.FirPfbCh.new(bad[0], bad[1], bad[2], np.zeros(64, dtype=np.float32))
+    with pytest.raises(yb.ConfigError):
+        yb.FirPfbCh.new_kaiser(yb.ANALYZER, 8, 0, 60.0)
+    with pytest.raises(yb.ConfigError):
+        yb.FirPfbCh.new(yb.ANALYZER, 8, 4, np.zeros(31, dtype=np.float32))
+    with pytest.raises(yb.ConfigError):
+        yb.FirPfbCh.new(yb.ANALYZER, 8, 4, np.zeros(32, dtype=np.float32), n_streams=0)
+    with pytest.raises(yb.ConfigError):
+        yb.FirFilt.new(np.zeros(0, dtype=np.float32))                 # firfilt.rs:65-67
+    with pytest.raises(yb.ConfigError):
+        yb.FirFilt.new_kaiser(0, 0.25)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(yb.InternalError, match="no CPU fallback"):
+        yb.FirPfbCh2.new_kaiser(yb.ANALYZER, 16, 5, 60.0)
+    with pytest.raises(yb.InternalError):
+        yb.FirFilt.new(np.ones(4, dtype=np.float32))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "yagi_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("n_frames,M,m,ws", [(2 ** 21, 256, 7, 8), (2 ** 21, 256, 7, 3), (1001, 16, 5, 4), (7, 8, 2, 8), (64, 1024, 4, 2)])
+def test_time_shards_cover_and_align(n_frames, M, m, ws):
+    sh = firpfbch2_time_shards(n_frames, M, m, ws)
+    assert len(sh) == ws
+    assert sh[0].frame_begin == 0 and sh[-1].frame_end == n_frames
+    for a, b in zip(sh, sh[1:]):
+        assert a.frame_end == b.frame_begin
+    for s in sh:
+        assert s.frame_begin % 2 == 0                      # local parity == global parity
+        assert s.sample_begin == s.frame_begin * M // 2
+        assert s.halo_len == (4 * m - 1) * M // 2 == 2 * M * m - M // 2
+        assert s.halo_begin == s.sample_begin - s.halo_len
+    sizes = [s.n_frames for s in sh]
+    assert max(sizes) - min(sizes) <= 3
+
+
+def test_stream_shards():
+    sh = stream_shards(4096, 8)
+    assert [len(r) for r in sh] == [512] * 8
+    sh = stream_shards(10, 4)
+    assert sum(len(r) for r in sh) == 10 and sh[0].start == 0 and sh[-1].stop == 10

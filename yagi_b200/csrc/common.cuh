@@ -1,0 +1,174 @@
+// common.cuh -- shared host/device helpers for libyagi_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/yagi_b200.h"
+
+namespace yg {
+
+// ---------------------------------------------------------------- errors
+std::string& last_error_ref();
+int32_t fail(int32_t code, const char* fmt, ...);
+
+#define YG_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return ::yg::fail(YG_EINTERNAL, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), \
+                              __FILE__, __LINE__, #expr);                                      \
+    } while (0)
+
+#define YG_TRY(expr)                 \
+    do {                             \
+        int32_t _rc = (expr);        \
+        if (_rc != YG_OK) return _rc;\
+    } while (0)
+
+// Binds the calling thread to a handle's device for the duration of a call.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        cur = dev;
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != cur) cudaSetDevice(prev); }
+    int cur = -1;
+};
+
+int32_t require_device(int* dev_out);
+
+// ---------------------------------------------------------------- design (host)
+int32_t fir_design_kaiser(uint32_t n, float fc, float as, float mu, float* h);
+// twiddle table tw[k] = exp(+j 2 pi k / M), computed in f64 and rounded once
+void make_twiddles(uint32_t M, std::vector<float2>& tw);
+
+// ---------------------------------------------------------------- device buffers
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int32_t reserve(size_t want) {
+        if (want <= n) return YG_OK;
+        if (p) { cudaFree(p); p = nullptr; n = 0; }
+        YG_CUDA(cudaMalloc(&p, want * sizeof(T)));
+        n = want;
+        return YG_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// Three-stream chunked host<->device pipeline used by the host-pointer entry points:
+// H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c.
+struct HostPipe {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    DevBuf<yg_cf32> dx[2], dy[2];
+    bool inited = false;
+    int32_t init();
+    void destroy();
+};
+
+// launch(d_x, frames, d_y, stream) must enqueue everything for `frames` frames on `stream`.
+template <typename Launch>
+int32_t run_host_pipe(HostPipe& hp, cudaStream_t s_comp, const yg_cf32* x, yg_cf32* y, size_t n_frames,
+                      size_t in_per_frame, size_t out_per_frame, size_t frames_per_chunk, Launch&& launch)
+{
+    YG_TRY(hp.init());
+    if (n_frames == 0) return YG_OK;
+    if (frames_per_chunk == 0) frames_per_chunk = 1;
+    if (frames_per_chunk > n_frames) frames_per_chunk = n_frames;
+    const int nbuf = (n_frames > frames_per_chunk) ? 2 : 1;
+    for (int b = 0; b < nbuf; b++) {
+        YG_TRY(hp.dx[b].reserve(frames_per_chunk * in_per_frame));
+        YG_TRY(hp.dy[b].reserve(frames_per_chunk * out_per_frame));
+    }
+    size_t done = 0;
+    for (size_t c = 0; done < n_frames; c++) {
+        const int b = (int)(c & 1);
+        const size_t f = (n_frames - done < frames_per_chunk) ? (n_frames - done) : frames_per_chunk;
+        if (c >= 2) YG_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_comp[b], 0));      // dx[b] free
+        YG_CUDA(cudaMemcpyAsync(hp.dx[b].p, x + done * in_per_frame, f * in_per_frame * sizeof(yg_cf32),
+                                cudaMemcpyHostToDevice, hp.s_in));
+        YG_CUDA(cudaEventRecord(hp.ev_in[b], hp.s_in));
+        YG_CUDA(cudaStreamWaitEvent(s_comp, hp.ev_in[b], 0));
+        if (c >= 2) YG_CUDA(cudaStreamWaitEvent(s_comp, hp.ev_out[b], 0));       // dy[b] free
+        YG_TRY(launch(hp.dx[b].p, f, hp.dy[b].p, s_comp));
+        YG_CUDA(cudaEventRecord(hp.ev_comp[b], s_comp));
+        YG_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_comp[b], 0));
+        YG_CUDA(cudaMemcpyAsync(y + done * out_per_frame, hp.dy[b].p, f * out_per_frame * sizeof(yg_cf32),
+                                cudaMemcpyDeviceToHost, hp.s_out));
+        YG_CUDA(cudaEventRecord(hp.ev_out[b], hp.s_out));
+        done += f;
+    }
+    YG_CUDA(cudaStreamSynchronize(hp.s_out));
+    YG_CUDA(cudaStreamSynchronize(s_comp));
+    return YG_OK;
+}
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// Unnormalised M-point DFT of X (shared memory) by one thread block.
+//   backward != 0 : e^{+j 2 pi n k / M}   (Fft Direction::Backward, src/fft/mod.rs:13-26)
+//   backward == 0 : e^{-j 2 pi n k / M}
+// tw[k] = e^{+j 2 pi k / M} (global, read-only).  `Y` is a second M-entry shared scratch.
+// Returns the shared buffer holding the result.  All threads of the block must call it;
+// on return the result is visible to all threads (ends with __syncthreads()).
+__device__ inline float2* block_dft(float2* X, float2* Y, uint32_t M, const float2* __restrict__ tw, int backward)
+{
+    __syncthreads();
+    if ((M & (M - 1)) == 0) {
+        // Stockham autosort radix-2
+        uint32_t l = M >> 1, s = 1;
+        float2* x = X;
+        float2* y = Y;
+        for (; l >= 1; l >>= 1, s <<= 1) {
+            for (uint32_t idx = threadIdx.x; idx < (M >> 1); idx += blockDim.x) {
+                const uint32_t j = idx / s, k = idx - j * s;
+                float2 w = __ldg(&tw[j * s]);
+                if (!backward) w.y = -w.y;
+                const float2 a = x[k + s * j];
+                const float2 b = x[k + s * (j + l)];
+                y[k + s * (2 * j)] = cadd(a, b);
+                y[k + s * (2 * j + 1)] = cmul(csub(a, b), w);
+            }
+            __syncthreads();
+            float2* t = x; x = y; y = t;
+        }
+        return x;
+    }
+    // direct DFT, twiddle index reduced mod M exactly in integers
+    for (uint32_t c = threadIdx.x; c < M; c += blockDim.x) {
+        float2 acc = make_float2(0.f, 0.f);
+        uint32_t idx = 0;
+        for (uint32_t b = 0; b < M; b++) {
+            float2 w = __ldg(&tw[idx]);
+            if (!backward) w.y = -w.y;
+            acc = cadd(acc, cmul(X[b], w));
+            idx += c;
+            if (idx >= M) idx -= M;
+        }
+        Y[c] = acc;
+    }
+    __syncthreads();
+    return Y;
+}
+#endif  // __CUDACC__
+
+}  // namespace yg

@@ -1,0 +1,481 @@
+// firpfbch2.cu -- firpfbch2_crcf handle, state management, generic kernels (any even M, any m)
+// and dispatch to the fused fast path (firpfbch2_fast.cu).
+//
+// Closed forms computed here (frame k since reset, s[t<0] = 0):
+//   analysis : V_k[b] = sum_n h[b+nM] s[t_k - b - nM],  t_k = (k+1) M/2 - 1
+//              y_k    = (1/M) IDFT_unnorm( roll(V_k, (k&1) M/2) )
+//   synthesis: u_k = 1/2 IDFT_unnorm(X_k)
+//              y[k M/2 + i] = sum_{l<4m} h[i + l M/2] u_{k-l}[(i + (k&1) M/2) mod M]
+#include "common.cuh"
+#include "firpfbch2_fast.cuh"
+
+#include <algorithm>
+
+using namespace yg;
+
+struct yg_firpfbch2_crcf_s {
+    int32_t type = 0;
+    uint32_t M = 0, M2 = 0, m = 0;
+    size_t L = 0;                 // taps used = 2*M*m
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<float> h;         // prototype (L)
+    DevBuf<float> d_h;
+    DevBuf<float2> d_tw;
+    size_t state_len = 0;         // cf32 entries of history
+    DevBuf<yg_cf32> d_hist[2];
+    int cur = 0;
+    int32_t flag = 0;
+    DevBuf<yg_cf32> d_U;          // synthesiser: [4m-1 history frames + n frames][M]
+    HostPipe pipe;
+    int32_t last_path = 0;
+    // ring of event pairs around the dominant kernel of each execute_block_dev call
+    static constexpr int kRing = 64;
+    cudaEvent_t ev0s[kRing] = {}, ev1s[kRing] = {};
+    unsigned long long n_timed = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // the pair being recorded by the current call
+    bool timed = false;
+    void next_events() { ev0 = ev0s[n_timed % kRing]; ev1 = ev1s[n_timed % kRing]; n_timed++; }
+    Firpfbch2FastPlan fast;       // fused fast path (may be unsupported for this M/m)
+};
+
+namespace {
+
+// ------------------------------------------------------------------ generic kernels
+// One block per frame (grid-stride).  Shared: 2*M float2.
+__global__ void k_analysis_generic(const float* __restrict__ h, const float2* __restrict__ tw,
+                                   const float2* __restrict__ hist, long long Hlen,
+                                   const float2* __restrict__ x, float2* __restrict__ y,
+                                   uint32_t M, uint32_t P /*2m*/, long long f_begin, long long f_end, int flag0)
+{
+    extern __shared__ float2 sm[];
+    float2* X = sm;
+    float2* Y = sm + M;
+    const uint32_t M2 = M >> 1;
+    // frames are numbered from the start of this call; flag0 is the parity of frame 0
+    for (long long f = f_begin + blockIdx.x; f < f_end; f += gridDim.x) {
+        const int par = (flag0 + (int)(f & 1)) & 1;
+        const long long tk = (f + 1) * (long long)M2 - 1;        // relative to x[0]
+        for (uint32_t b = threadIdx.x; b < M; b += blockDim.x) {
+            float2 acc = make_float2(0.f, 0.f);
+            // oldest sample first, like window.read() . h_sub (src/dotprod/mod.rs:36-39)
+            for (int n = (int)P - 1; n >= 0; n--) {
+                const long long t = tk - b - (long long)n * M;
+                const float2 s = (t >= 0) ? __ldg(&x[t]) : __ldg(&hist[Hlen + t]);
+                const float c = __ldg(&h[b + (size_t)n * M]);
+                acc.x = fmaf(c, s.x, acc.x);
+                acc.y = fmaf(c, s.y, acc.y);
+            }
+            uint32_t dst = b + (par ? M2 : 0);
+            if (dst >= M) dst -= M;
+            X[dst] = acc;
+        }
+        const float2* r = block_dft(X, Y, M, tw, 1);
+        const float Mf = (float)M;
+        for (uint32_t c = threadIdx.x; c < M; c += blockDim.x) {
+            const float2 v = r[c];
+            y[f * (long long)M + c] = make_float2(v.x / Mf, v.y / Mf);
+        }
+        __syncthreads();
+    }
+}
+
+// new_hist[i] = stream[n_new - Hlen + i], stream = concat(old_hist, x[0..n_new))
+__global__ void k_update_hist(float2* __restrict__ hist_new, const float2* __restrict__ hist_old, long long Hlen,
+                              const float2* __restrict__ x, long long n_new)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < Hlen;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long t = n_new - Hlen + i;
+        hist_new[i] = (t >= 0) ? x[t] : hist_old[Hlen + t];
+    }
+}
+
+// Synthesiser stage 1: U[k] = IDFT_unnorm(X_k) * (1/M) * (M/2)   (two f32 multiplies, as upstream)
+__global__ void k_synth_ifft(const float2* __restrict__ tw, const float2* __restrict__ x, float2* __restrict__ U,
+                             uint32_t M, long long n_frames)
+{
+    extern __shared__ float2 sm[];
+    float2* X = sm;
+    float2* Y = sm + M;
+    const float s0 = 1.0f / (float)M;
+    const float s1 = (float)(M >> 1);
+    for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        for (uint32_t c = threadIdx.x; c < M; c += blockDim.x) X[c] = __ldg(&x[f * (long long)M + c]);
+        const float2* r = block_dft(X, Y, M, tw, 1);
+        for (uint32_t c = threadIdx.x; c < M; c += blockDim.x) {
+            float2 v = r[c];
+            v.x *= s0; v.y *= s0;
+            v.x *= s1; v.y *= s1;
+            U[f * (long long)M + c] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// Synthesiser stage 2: weighted overlap-add.  U points at frame 0 of this call; frames -1..-(4m-1)
+// (history) precede it in memory.  One thread per output sample.
+__global__ void k_synth_wola(const float* __restrict__ h, const float2* __restrict__ U, float2* __restrict__ y,
+                             uint32_t M, uint32_t m, long long n_frames, int flag0)
+{
+    const uint32_t M2 = M >> 1;
+    const long long total = n_frames * (long long)M2;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total;
+         o += (long long)gridDim.x * blockDim.x) {
+        const long long f = o / M2;
+        const uint32_t i = (uint32_t)(o - f * M2);
+        const int par = (flag0 + (int)(f & 1)) & 1;
+        uint32_t col = i + (par ? M2 : 0);
+        // two banks (even / odd l), each summed oldest first, then added (upstream y0 + y1)
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+        for (int n = (int)(2 * m) - 1; n >= 0; n--) {
+            const int l0 = 2 * n, l1 = 2 * n + 1;
+            const float c0 = __ldg(&h[i + (size_t)l0 * M2]);
+            const float c1 = __ldg(&h[i + (size_t)l1 * M2]);
+            const float2 u0 = __ldg(&U[(f - l0) * (long long)M + col]);
+            const float2 u1 = __ldg(&U[(f - l1) * (long long)M + col]);
+            a0.x = fmaf(c0, u0.x, a0.x); a0.y = fmaf(c0, u0.y, a0.y);
+            a1.x = fmaf(c1, u1.x, a1.x); a1.y = fmaf(c1, u1.y, a1.y);
+        }
+        y[o] = make_float2(a0.x + a1.x, a0.y + a1.y);
+    }
+}
+
+int32_t check(yg_firpfbch2_crcf q)
+{
+    if (!q) return fail(YG_EVALUE, "null firpfbch2 handle");
+    return YG_OK;
+}
+
+int32_t validate(int32_t type, uint32_t M, uint32_t m)
+{
+    if (type != YG_ANALYZER && type != YG_SYNTHESIZER) return fail(YG_ECONFIG, "invalid type %d", type);
+    if (M < 2) return fail(YG_ECONFIG, "number of channels must be at least 2");
+    if (M % 2) return fail(YG_ECONFIG, "number of channels must be even");
+    if (m < 1) return fail(YG_ECONFIG, "filter semi-length must be at least 1");
+    return YG_OK;
+}
+
+size_t smem_dft(uint32_t M) { return 2 * (size_t)M * sizeof(float2); }
+
+int32_t set_smem(const void* fn, size_t bytes)
+{
+    if (bytes > 48 * 1024) {
+        if (bytes > 227 * 1024) return fail(YG_ECONFIG, "M too large for the generic kernel (needs %zu B shared memory)", bytes);
+        YG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+    return YG_OK;
+}
+
+int32_t launch_generic_analysis(yg_firpfbch2_crcf q, const float2* hist, const float2* x, float2* y,
+                                size_t f_begin, size_t f_end, cudaStream_t st)
+{
+    if (f_end <= f_begin) return YG_OK;
+    const size_t smem = smem_dft(q->M);
+    YG_TRY(set_smem((const void*)k_analysis_generic, smem));
+    const int block = (int)std::min<uint32_t>(256, (q->M + 31) / 32 * 32);
+    const int grid = (int)std::min<size_t>(f_end - f_begin, 148 * 16);
+    k_analysis_generic<<<grid, block, smem, st>>>(q->d_h.p, q->d_tw.p, hist, (long long)q->state_len, x, y, q->M,
+                                                  2 * q->m, (long long)f_begin, (long long)f_end, q->flag);
+    YG_CUDA(cudaGetLastError());
+    return YG_OK;
+}
+
+int32_t launch_analysis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
+{
+    const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
+    const float2* x = reinterpret_cast<const float2*>(d_x);
+    float2* y = reinterpret_cast<float2*>(d_y);
+
+    // The fused kernel handles an even-parity start and an even number of frames; what is
+    // left over (a leading odd-parity frame, a trailing single frame) and calls too small to
+    // fill the machine go to the generic kernel.
+    q->next_events();
+    if (q->fast.supported && n_frames >= q->fast.min_frames) {
+        const size_t lead = (q->flag & 1) ? 1 : 0;
+        const size_t body = (n_frames - lead) & ~(size_t)1;
+        YG_CUDA(cudaEventRecord(q->ev0, st));
+        YG_TRY(firpfbch2_fast_launch(q->fast, hist, (long long)q->state_len, x, y, lead, body, st));
+        YG_CUDA(cudaEventRecord(q->ev1, st));
+        q->timed = true;
+        q->last_path = 2;
+        YG_TRY(launch_generic_analysis(q, hist, x, y, 0, lead, st));
+        YG_TRY(launch_generic_analysis(q, hist, x, y, lead + body, n_frames, st));
+        return YG_OK;
+    }
+    YG_CUDA(cudaEventRecord(q->ev0, st));
+    YG_TRY(launch_generic_analysis(q, hist, x, y, 0, n_frames, st));
+    YG_CUDA(cudaEventRecord(q->ev1, st));
+    q->timed = true;
+    q->last_path = 1;
+    return YG_OK;
+}
+
+int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
+{
+    const uint32_t M = q->M;
+    const size_t nh = 4 * (size_t)q->m - 1;
+    YG_TRY(q->d_U.reserve((nh + n_frames) * M));
+    float2* U = reinterpret_cast<float2*>(q->d_U.p);
+    YG_CUDA(cudaMemcpyAsync(U, q->d_hist[q->cur].p, nh * M * sizeof(yg_cf32), cudaMemcpyDeviceToDevice, st));
+    const size_t smem = smem_dft(M);
+    YG_TRY(set_smem((const void*)k_synth_ifft, smem));
+    const int block = (int)std::min<uint32_t>(256, (M + 31) / 32 * 32);
+    const int grid = (int)std::min<size_t>(n_frames, 148 * 16);
+    q->next_events();
+    YG_CUDA(cudaEventRecord(q->ev0, st));
+    k_synth_ifft<<<grid, block, smem, st>>>(q->d_tw.p, reinterpret_cast<const float2*>(d_x), U + nh * M, M,
+                                            (long long)n_frames);
+    YG_CUDA(cudaGetLastError());
+    const long long total = (long long)n_frames * q->M2;
+    const int grid2 = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+    k_synth_wola<<<grid2, 256, 0, st>>>(q->d_h.p, U + nh * M, reinterpret_cast<float2*>(d_y), M, q->m,
+                                        (long long)n_frames, q->flag);
+    YG_CUDA(cudaGetLastError());
+    YG_CUDA(cudaEventRecord(q->ev1, st));
+    q->timed = true;
+    q->last_path = 1;
+    // new history = last nh frames of U
+    YG_CUDA(cudaMemcpyAsync(q->d_hist[q->cur].p, U + n_frames * M, nh * M * sizeof(yg_cf32),
+                            cudaMemcpyDeviceToDevice, st));
+    return YG_OK;
+}
+
+int32_t execute_dev(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
+{
+    if (n_frames == 0) return YG_OK;
+    if (q->type == YG_ANALYZER) {
+        YG_TRY(launch_analysis(q, d_x, n_frames, d_y, st));
+        const long long n_new = (long long)n_frames * q->M2;
+        const long long Hlen = (long long)q->state_len;
+        const int nxt = q->cur ^ 1;
+        const int grid = (int)std::min<long long>((Hlen + 255) / 256, 1024);
+        k_update_hist<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(q->d_hist[nxt].p),
+                                            reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
+                                            reinterpret_cast<const float2*>(d_x), n_new);
+        YG_CUDA(cudaGetLastError());
+        q->cur = nxt;
+    } else {
+        YG_TRY(launch_synthesis(q, d_x, n_frames, d_y, st));
+    }
+    q->flag = (q->flag + (int)(n_frames & 1)) & 1;
+    return YG_OK;
+}
+
+int32_t build(int32_t type, uint32_t M, uint32_t m, const float* h, size_t h_len, yg_firpfbch2_crcf* out)
+{
+    if (!out) return fail(YG_EVALUE, "null output pointer");
+    *out = nullptr;
+    YG_TRY(validate(type, M, m));
+    const size_t L = 2 * (size_t)M * m;
+    if (!h) return fail(YG_EVALUE, "null prototype filter");
+    if (h_len < L) return fail(YG_ECONFIG, "prototype filter length (%zu) must be at least 2*M*m (%zu)", h_len, L);
+    int dev = 0;
+    YG_TRY(require_device(&dev));
+
+    auto* q = new yg_firpfbch2_crcf_s();
+    q->type = type; q->M = M; q->M2 = M / 2; q->m = m; q->L = L; q->dev = dev;
+    q->h.assign(h, h + L);
+    auto cleanup = [&](int32_t rc) { yg_firpfbch2_crcf_destroy(q); return rc; };
+#define TRYQ(expr) do { int32_t _rc = (expr); if (_rc != YG_OK) return cleanup(_rc); } while (0)
+#define CUDAQ(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return cleanup(fail(YG_EINTERNAL, "CUDA error %s (%s)", cudaGetErrorString(_e), #expr)); } while (0)
+    CUDAQ(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < yg_firpfbch2_crcf_s::kRing; i++) {
+        CUDAQ(cudaEventCreate(&q->ev0s[i]));
+        CUDAQ(cudaEventCreate(&q->ev1s[i]));
+    }
+    TRYQ(q->d_h.reserve(L));
+    CUDAQ(cudaMemcpy(q->d_h.p, q->h.data(), L * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float2> tw;
+    make_twiddles(M, tw);
+    TRYQ(q->d_tw.reserve(M));
+    CUDAQ(cudaMemcpy(q->d_tw.p, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
+    const size_t nh = 4 * (size_t)m - 1;
+    q->state_len = (type == YG_ANALYZER) ? nh * q->M2 : nh * M;
+    for (int b = 0; b < 2; b++) {
+        TRYQ(q->d_hist[b].reserve(q->state_len));
+        CUDAQ(cudaMemset(q->d_hist[b].p, 0, q->state_len * sizeof(yg_cf32)));
+    }
+    if (type == YG_ANALYZER) TRYQ(firpfbch2_fast_plan(q->fast, M, m, q->h.data()));
+#undef TRYQ
+#undef CUDAQ
+    *out = q;
+    return YG_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+int32_t yg_firpfbch2_crcf_create(int32_t type, uint32_t M, uint32_t m, const float* h, size_t h_len,
+                                 yg_firpfbch2_crcf* out)
+{
+    return build(type, M, m, h, h_len, out);
+}
+
+int32_t yg_firpfbch2_crcf_create_kaiser(int32_t type, uint32_t M, uint32_t m, float as, yg_firpfbch2_crcf* out)
+{
+    if (!out) return fail(YG_EVALUE, "null output pointer");
+    *out = nullptr;
+    YG_TRY(validate(type, M, m));
+    const uint32_t n = 2 * M * m + 1;
+    std::vector<float> hf(n);
+    const float fc = (type == YG_ANALYZER) ? 1.0f / (float)M : 0.5f / (float)M;
+    YG_TRY(fir_design_kaiser(n, fc, as, 0.0f, hf.data()));
+    float sum = 0.0f;
+    for (uint32_t i = 0; i < n; i++) sum += hf[i];
+    for (uint32_t i = 0; i < n; i++) hf[i] = hf[i] * (float)M / sum;      // resamp.rs:49-51 idiom
+    return build(type, M, m, hf.data(), n, out);
+}
+
+int32_t yg_firpfbch2_crcf_clone(yg_firpfbch2_crcf q, yg_firpfbch2_crcf* out)
+{
+    YG_TRY(check(q));
+    DeviceGuard g(q->dev);
+    YG_CUDA(cudaStreamSynchronize(q->stream));
+    yg_firpfbch2_crcf c = nullptr;
+    YG_TRY(build(q->type, q->M, q->m, q->h.data(), q->h.size(), &c));
+    cudaError_t e = cudaMemcpy(c->d_hist[c->cur].p, q->d_hist[q->cur].p, q->state_len * sizeof(yg_cf32),
+                               cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) { yg_firpfbch2_crcf_destroy(c); return fail(YG_EINTERNAL, "CUDA error %s", cudaGetErrorString(e)); }
+    c->flag = q->flag;
+    *out = c;
+    return YG_OK;
+}
+
+int32_t yg_firpfbch2_crcf_destroy(yg_firpfbch2_crcf q)
+{
+    if (!q) return YG_OK;
+    DeviceGuard g(q->dev);
+    if (q->stream) cudaStreamSynchronize(q->stream);
+    firpfbch2_fast_release(q->fast);
+    q->pipe.destroy();
+    q->d_h.release(); q->d_tw.release(); q->d_hist[0].release(); q->d_hist[1].release(); q->d_U.release();
+    for (int i = 0; i < yg_firpfbch2_crcf_s::kRing; i++) {
+        if (q->ev0s[i]) cudaEventDestroy(q->ev0s[i]);
+        if (q->ev1s[i]) cudaEventDestroy(q->ev1s[i]);
+    }
+    if (q->stream) cudaStreamDestroy(q->stream);
+    delete q;
+    return YG_OK;
+}
+
+int32_t yg_firpfbch2_crcf_reset(yg_firpfbch2_crcf q)
+{
+    YG_TRY(check(q));
+    DeviceGuard g(q->dev);
+    YG_CUDA(cudaMemsetAsync(q->d_hist[q->cur].p, 0, q->state_len * sizeof(yg_cf32), q->stream));
+    YG_CUDA(cudaStreamSynchronize(q->stream));
+    q->flag = 0;
+    return YG_OK;
+}
+
+int32_t yg_firpfbch2_crcf_execute_block_dev(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y,
+                                            void* cuda_stream)
+{
+    YG_TRY(check(q));
+    if (n_frames && (!d_x || !d_y)) return fail(YG_EVALUE, "null buffer");
+    DeviceGuard g(q->dev);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : q->stream;
+    return execute_dev(q, d_x, n_frames, d_y, st);
+}
+
+int32_t yg_firpfbch2_crcf_execute_block(yg_firpfbch2_crcf q, const yg_cf32* x, size_t n_frames, yg_cf32* y)
+{
+    YG_TRY(check(q));
+    if (n_frames && (!x || !y)) return fail(YG_EVALUE, "null buffer");
+    DeviceGuard g(q->dev);
+    const size_t nin = (q->type == YG_ANALYZER) ? q->M2 : q->M;
+    const size_t nout = (q->type == YG_ANALYZER) ? q->M : q->M2;
+    // ~32 MiB of input per chunk, an even number of frames so chunk starts keep the fast path
+    size_t fpc = ((size_t)32 << 20) / (nin * sizeof(yg_cf32));
+    fpc = std::max<size_t>(2, fpc & ~(size_t)1);
+    return run_host_pipe(q->pipe, q->stream, x, y, n_frames, nin, nout, fpc,
+                         [&](const yg_cf32* dx, size_t f, yg_cf32* dy, cudaStream_t st) {
+                             return execute_dev(q, dx, f, dy, st);
+                         });
+}
+
+int32_t yg_firpfbch2_crcf_execute(yg_firpfbch2_crcf q, const yg_cf32* x, yg_cf32* y)
+{
+    return yg_firpfbch2_crcf_execute_block(q, x, 1, y);
+}
+
+int32_t yg_firpfbch2_crcf_sync(yg_firpfbch2_crcf q)
+{
+    YG_TRY(check(q));
+    DeviceGuard g(q->dev);
+    YG_CUDA(cudaStreamSynchronize(q->stream));
+    return YG_OK;
+}
+
+int32_t yg_firpfbch2_crcf_get_type(yg_firpfbch2_crcf q, int32_t* type) { YG_TRY(check(q)); *type = q->type; return YG_OK; }
+int32_t yg_firpfbch2_crcf_get_M(yg_firpfbch2_crcf q, uint32_t* M) { YG_TRY(check(q)); *M = q->M; return YG_OK; }
+int32_t yg_firpfbch2_crcf_get_m(yg_firpfbch2_crcf q, uint32_t* m) { YG_TRY(check(q)); *m = q->m; return YG_OK; }
+
+int32_t yg_firpfbch2_crcf_get_taps(yg_firpfbch2_crcf q, float* h)
+{
+    YG_TRY(check(q));
+    if (!h) return fail(YG_EVALUE, "null pointer");
+    memcpy(h, q->h.data(), q->L * sizeof(float));
+    return YG_OK;
+}
+
+int32_t yg_firpfbch2_crcf_state_len(yg_firpfbch2_crcf q, size_t* n)
+{
+    YG_TRY(check(q));
+    *n = q->state_len;
+    return YG_OK;
+}
+
+int32_t yg_firpfbch2_crcf_get_state(yg_firpfbch2_crcf q, yg_cf32* hist, int32_t* flag)
+{
+    YG_TRY(check(q));
+    DeviceGuard g(q->dev);
+    YG_CUDA(cudaStreamSynchronize(q->stream));
+    if (hist) YG_CUDA(cudaMemcpy(hist, q->d_hist[q->cur].p, q->state_len * sizeof(yg_cf32), cudaMemcpyDeviceToHost));
+    if (flag) *flag = q->flag;
+    return YG_OK;
+}
+
+int32_t yg_firpfbch2_crcf_set_state(yg_firpfbch2_crcf q, const yg_cf32* hist, int32_t flag)
+{
+    YG_TRY(check(q));
+    if (flag != 0 && flag != 1) return fail(YG_EVALUE, "flag must be 0 or 1");
+    DeviceGuard g(q->dev);
+    YG_CUDA(cudaStreamSynchronize(q->stream));
+    if (hist) YG_CUDA(cudaMemcpy(q->d_hist[q->cur].p, hist, q->state_len * sizeof(yg_cf32), cudaMemcpyHostToDevice));
+    q->flag = flag;
+    return YG_OK;
+}
+
+int32_t yg_firpfbch2_crcf_last_path(yg_firpfbch2_crcf q, int32_t* path) { YG_TRY(check(q)); *path = q->last_path; return YG_OK; }
+
+int32_t yg_firpfbch2_crcf_last_kernel_ms(yg_firpfbch2_crcf q, float* ms)
+{
+    YG_TRY(check(q));
+    if (!q->timed) return fail(YG_EMODE, "no timed launch yet");
+    DeviceGuard g(q->dev);
+    YG_CUDA(cudaEventSynchronize(q->ev1));
+    YG_CUDA(cudaEventElapsedTime(ms, q->ev0, q->ev1));
+    return YG_OK;
+}
+
+int32_t yg_firpfbch2_crcf_kernel_times(yg_firpfbch2_crcf q, float* ms, size_t cap, size_t* n)
+{
+    YG_TRY(check(q));
+    if (!ms || !n) return fail(YG_EVALUE, "null pointer");
+    DeviceGuard g(q->dev);
+    const unsigned long long have = std::min<unsigned long long>(q->n_timed, yg_firpfbch2_crcf_s::kRing);
+    const size_t take = (size_t)std::min<unsigned long long>(have, cap);
+    for (size_t i = 0; i < take; i++) {
+        const unsigned long long idx = (q->n_timed - take + i) % yg_firpfbch2_crcf_s::kRing;   // oldest first
+        YG_CUDA(cudaEventSynchronize(q->ev1s[idx]));
+        YG_CUDA(cudaEventElapsedTime(&ms[i], q->ev0s[idx], q->ev1s[idx]));
+    }
+    *n = take;
+    return YG_OK;
+}
+
+}  // extern "C"

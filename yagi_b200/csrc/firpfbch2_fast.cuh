@@ -1,0 +1,25 @@
+// firpfbch2_fast.cuh -- interface of the fused firpfbch2 analysis kernel (sm_100a).
+#pragma once
+#include "common.cuh"
+
+namespace yg {
+
+struct Firpfbch2FastPlan {
+    bool supported = false;
+    uint32_t M = 0, m = 0;
+    size_t min_frames = 0;        // below this the generic kernel is used
+    void* d_taps = nullptr;       // kernel-specific tap layout (device)
+    void* d_twid = nullptr;       // kernel-specific twiddle layout (device)
+    int variant = 0;
+};
+
+// Decide whether (M, m) has a fused kernel and upload its tap / twiddle tables.
+int32_t firpfbch2_fast_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const float* h);
+void firpfbch2_fast_release(Firpfbch2FastPlan& p);
+
+// Frames [f0, f0 + n_frames) of the call (f0 even-parity in the global frame count, n_frames
+// even).  `x` points at the first sample of the call, `hist` holds the Hlen samples before it.
+int32_t firpfbch2_fast_launch(const Firpfbch2FastPlan& p, const float2* hist, long long Hlen, const float2* x,
+                              float2* y, size_t f0, size_t n_frames, cudaStream_t st);
+
+}  // namespace yg
