@@ -20,8 +20,9 @@
  *     buffers and one stream, is NOT thread-safe (reference methods take `&mut self`),
  *     and distinct handles are independent;
  *   - `*_dev` entry points take DEVICE pointers and are asynchronous on the given
- *     cudaStream_t (passed as void*; NULL = the handle's own stream, see *_sync);
- *     the others take HOST pointers and return when the result is in `y`;
+ *     cudaStream_t (passed as void*; NULL = the CUDA default stream, as everywhere in CUDA);
+ *     the others take HOST pointers, run on the handle's own stream and return when the
+ *     result is in `y`; state updates stay ordered when consecutive calls use different streams;
  *   - samples are interleaved (re, im) f32 pairs == num_complex::Complex<f32>.
  *   - there is no CPU fallback: without a CUDA device every constructor fails with
  *     Internal.
@@ -82,7 +83,7 @@ int32_t yg_firpfbch2_crcf_execute(yg_firpfbch2_crcf q, const yg_cf32* x, yg_cf32
 int32_t yg_firpfbch2_crcf_execute_block(yg_firpfbch2_crcf q, const yg_cf32* x, size_t n_frames, yg_cf32* y);
 int32_t yg_firpfbch2_crcf_execute_block_dev(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames,
                                             yg_cf32* d_y, void* cuda_stream);
-int32_t yg_firpfbch2_crcf_sync(yg_firpfbch2_crcf q);                        /* wait for the handle's stream */
+int32_t yg_firpfbch2_crcf_sync(yg_firpfbch2_crcf q);                        /* wait for all work queued on this handle */
 int32_t yg_firpfbch2_crcf_get_type(yg_firpfbch2_crcf q, int32_t* type);
 int32_t yg_firpfbch2_crcf_get_M(yg_firpfbch2_crcf q, uint32_t* M);
 int32_t yg_firpfbch2_crcf_get_m(yg_firpfbch2_crcf q, uint32_t* m);

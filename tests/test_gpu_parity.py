@@ -269,3 +269,87 @@ def test_config2_geometry_firfilt_63_taps():
     q.reset()
     y2 = q.execute_block(x).reshape(S_, -1)
     assert_parity(y2, ref, "after reset")
+
+
+# ------------------------------------------------------------------ fused fast path (M=256, m=7)
+def test_fused_path_state_continuity_and_edges():
+    """The fused kernel (last_path == 2) across calls of uneven sizes: odd-parity starts (a leading
+    frame goes to the generic kernel), odd lengths (trailing frame), partial 16-pair batches,
+    single-batch and multi-batch slabs, history taken from the previous call's tail."""
+    M, m = 256, 7
+    K = 6000
+    x = stimulus.noise_plus_tones(0, K * M // 2, M)
+    ref = _oracle_analysis(M, m, x).reshape(K, M)
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    cuts = [0, 64, 129, 130, 331, 1000, 1067, 1131, 3000, 3001 + 64, 5999, K]
+    outs = []
+    for a, b in zip(cuts, cuts[1:]):
+        outs.append(q.execute_block(x[a * M // 2: b * M // 2]))
+        if b - a >= 64:
+            assert q.last_path() == 2, (a, b)
+    y = np.concatenate(outs).reshape(K, M)
+    assert_parity(y, ref, "fused, uneven calls")
+    # per-frame worst case, to catch a single bad frame hidden by the global RMS
+    per_frame = np.abs(y - ref).max(axis=1)
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+
+
+def test_fused_path_matches_generic_kernel_closely():
+    """Same input through the fused kernel (one big call) and the generic kernel (calls < 64 frames)."""
+    M, m, K = 256, 7, 640
+    x = stimulus.noise_plus_tones(0, K * M // 2, M)
+    qf = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    yf = qf.execute_block(x)
+    assert qf.last_path() == 2
+    qg = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    yg_ = np.concatenate([qg.execute_block(x[a * M // 2:(a + 32) * M // 2]) for a in range(0, K, 32)])
+    assert qg.last_path() == 1
+    assert_parity(yf, yg_, "fused vs generic", rel_tol=2e-6, abs_tol=2e-6)
+
+
+def test_fused_path_full_size_properties():
+    """BASELINE config #3 at full size (2^28 samples) through size-independent properties:
+    (a) channel-sum checksum: sum_c y_k[c] = X_k[0] = the single polyphase partial sum
+        V_k[b0], b0 = (k odd ? M/2 : 0)  => one 14-tap dot product per frame, checked for every frame;
+    (b) sampled frames (start, slab boundaries, end) against the oracle on the same input window."""
+    import torch
+    M, m = 256, 7
+    N = 1 << 28
+    K = N // (M // 2)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234)
+    xr = torch.empty(N, 2, dtype=torch.float32, device="cuda")
+    xr.normal_(0.0, 1.0, generator=g)
+    x = torch.view_as_complex(xr)
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    y = q.execute_block(x).view(K, M)
+    torch.cuda.synchronize()
+    assert q.last_path() == 2
+    h = torch.from_numpy(q.get_taps()).cuda()
+    # (a) checksum over every frame with k >= 4m (full history inside x)
+    k = torch.arange(4 * m, K, device="cuda", dtype=torch.int64)
+    b0 = (k & 1) * (M // 2)
+    tk = (k + 1) * (M // 2) - 1
+    acc = torch.zeros(k.numel(), dtype=torch.complex128, device="cuda")
+    for n in range(2 * m):
+        acc += h[b0 + n * M].to(torch.float64) * x[tk - b0 - n * M].to(torch.complex128)
+    chk = y[4 * m:].to(torch.complex128).sum(dim=1)
+    err = (chk - acc).abs().max().item()
+    assert err < 2e-4, err            # sum of 256 outputs each within ~1e-6
+    del acc, chk
+    # (b) sampled windows against the oracle
+    halo = (4 * m - 1) * M // 2
+    for f0 in (0, 2 * 7084, 2 * 7085 * 16, K // 2 - 64, K - 128):
+        f0 -= f0 % 2
+        nf = 128
+        s0 = f0 * M // 2
+        lo = max(0, s0 - halo - M // 2)
+        pre = x[lo:s0].cpu().numpy()
+        seg = x[s0: s0 + nf * M // 2].cpu().numpy()
+        o = po.FirPfbCh2.new_kaiser(po.ANALYZER, M, m, 60.0)
+        if pre.size:
+            pad = (-pre.size) % M                      # keep the priming an even number of frames
+            o.execute_block(np.concatenate([np.zeros(pad, dtype=np.complex64), pre]))
+        ref = o.execute_block(seg)
+        got = y[f0: f0 + nf].reshape(-1).cpu().numpy()
+        assert_parity(got, ref, "full-size window at frame %d" % f0)

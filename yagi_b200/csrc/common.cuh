@@ -67,6 +67,33 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// Keeps a handle's state updates ordered when consecutive calls use different streams
+// (e.g. a device-pointer call on the caller's stream followed by a host-pointer call).
+struct StreamOrder {
+    cudaEvent_t ev = nullptr;
+    cudaStream_t last = nullptr;
+    bool armed = false;
+    int32_t enter(cudaStream_t st)
+    {
+        if (armed && st != last) YG_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        return YG_OK;
+    }
+    int32_t leave(cudaStream_t st)
+    {
+        if (!ev) YG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        YG_CUDA(cudaEventRecord(ev, st));
+        last = st;
+        armed = true;
+        return YG_OK;
+    }
+    int32_t wait_host()
+    {
+        if (armed) YG_CUDA(cudaEventSynchronize(ev));
+        return YG_OK;
+    }
+    void destroy() { if (ev) cudaEventDestroy(ev); ev = nullptr; armed = false; }
+};
+
 // Three-stream chunked host<->device pipeline used by the host-pointer entry points:
 // H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c.
 struct HostPipe {

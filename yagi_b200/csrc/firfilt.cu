@@ -12,6 +12,7 @@ struct yg_firfilt_crcf_s {
     float scale = 1.0f;
     int dev = 0;
     cudaStream_t stream = nullptr;
+    StreamOrder order;
     std::vector<float> h;
     DevBuf<float> d_h;
     size_t state_len = 0;          // h_len - 1 samples per stream
@@ -86,7 +87,16 @@ int32_t check(yg_firfilt_crcf q)
     return YG_OK;
 }
 
+int32_t execute_dev_impl(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf32* d_y, cudaStream_t st);
+
 int32_t execute_dev(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf32* d_y, cudaStream_t st)
+{
+    YG_TRY(q->order.enter(st));
+    YG_TRY(execute_dev_impl(q, d_x, n, d_y, st));
+    return q->order.leave(st);
+}
+
+int32_t execute_dev_impl(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf32* d_y, cudaStream_t st)
 {
     if (n == 0) return YG_OK;
     const long long S = q->n_streams;
@@ -166,6 +176,7 @@ int32_t yg_firfilt_crcf_clone(yg_firfilt_crcf q, yg_firfilt_crcf* out)
     YG_TRY(check(q));
     DeviceGuard g(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     yg_firfilt_crcf c = nullptr;
     YG_TRY(build(q->h.data(), q->h_len, q->n_streams, &c));
     c->scale = q->scale;
@@ -183,6 +194,8 @@ int32_t yg_firfilt_crcf_destroy(yg_firfilt_crcf q)
     if (!q) return YG_OK;
     DeviceGuard g(q->dev);
     if (q->stream) cudaStreamSynchronize(q->stream);
+    q->order.wait_host();
+    q->order.destroy();
     q->d_h.release(); q->d_hist[0].release(); q->d_hist[1].release();
     q->d_stage_x.release(); q->d_stage_y.release();
     if (q->stream) cudaStreamDestroy(q->stream);
@@ -194,9 +207,11 @@ int32_t yg_firfilt_crcf_reset(yg_firfilt_crcf q)
 {
     YG_TRY(check(q));
     DeviceGuard g(q->dev);
+    YG_TRY(q->order.wait_host());
     if (q->state_len)
         YG_CUDA(cudaMemsetAsync(q->d_hist[q->cur].p, 0, q->state_len * q->n_streams * sizeof(yg_cf32), q->stream));
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     return YG_OK;
 }
 
@@ -209,7 +224,7 @@ int32_t yg_firfilt_crcf_execute_block_dev(yg_firfilt_crcf q, const yg_cf32* d_x,
     YG_TRY(check(q));
     if (n && (!d_x || !d_y)) return fail(YG_EVALUE, "null buffer");
     DeviceGuard g(q->dev);
-    return execute_dev(q, d_x, n, d_y, cuda_stream ? (cudaStream_t)cuda_stream : q->stream);
+    return execute_dev(q, d_x, n, d_y, (cudaStream_t)cuda_stream);
 }
 
 int32_t yg_firfilt_crcf_execute_block(yg_firfilt_crcf q, const yg_cf32* x, size_t n, yg_cf32* y)
@@ -225,6 +240,7 @@ int32_t yg_firfilt_crcf_execute_block(yg_firfilt_crcf q, const yg_cf32* x, size_
     YG_TRY(execute_dev(q, q->d_stage_x.p, n, q->d_stage_y.p, q->stream));
     YG_CUDA(cudaMemcpyAsync(y, q->d_stage_y.p, tot * sizeof(yg_cf32), cudaMemcpyDeviceToHost, q->stream));
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     return YG_OK;
 }
 
@@ -233,6 +249,7 @@ int32_t yg_firfilt_crcf_sync(yg_firfilt_crcf q)
     YG_TRY(check(q));
     DeviceGuard g(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     return YG_OK;
 }
 

@@ -15,6 +15,7 @@ struct yg_firpfbch_crcf_s {
     size_t L = 0;                  // M*p
     int dev = 0;
     cudaStream_t stream = nullptr;
+    StreamOrder order;
     std::vector<float> h;
     DevBuf<float> d_h;
     DevBuf<float2> d_tw;
@@ -159,7 +160,16 @@ int32_t set_smem(const void* fn, size_t bytes)
     return YG_OK;
 }
 
+int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st);
+
 int32_t execute_dev(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
+{
+    YG_TRY(q->order.enter(st));
+    YG_TRY(execute_dev_impl(q, d_x, n_frames, d_y, st));
+    return q->order.leave(st);
+}
+
+int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
 {
     if (n_frames == 0) return YG_OK;
     const uint32_t M = q->M, p = q->p;
@@ -273,6 +283,7 @@ int32_t yg_firpfbch_crcf_clone(yg_firpfbch_crcf q, yg_firpfbch_crcf* out)
     YG_TRY(check(q));
     DeviceGuard g(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     yg_firpfbch_crcf c = nullptr;
     YG_TRY(build(q->type, q->M, q->p, q->h.data(), q->h.size(), q->n_streams, &c));
     if (q->state_len) {
@@ -289,6 +300,8 @@ int32_t yg_firpfbch_crcf_destroy(yg_firpfbch_crcf q)
     if (!q) return YG_OK;
     DeviceGuard g(q->dev);
     if (q->stream) cudaStreamSynchronize(q->stream);
+    q->order.wait_host();
+    q->order.destroy();
     q->d_h.release(); q->d_tw.release(); q->d_hist[0].release(); q->d_hist[1].release(); q->d_U.release();
     q->d_stage_x.release(); q->d_stage_y.release();
     if (q->stream) cudaStreamDestroy(q->stream);
@@ -300,9 +313,11 @@ int32_t yg_firpfbch_crcf_reset(yg_firpfbch_crcf q)
 {
     YG_TRY(check(q));
     DeviceGuard g(q->dev);
+    YG_TRY(q->order.wait_host());
     if (q->state_len)
         YG_CUDA(cudaMemsetAsync(q->d_hist[q->cur].p, 0, q->state_len * q->n_streams * sizeof(yg_cf32), q->stream));
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     return YG_OK;
 }
 
@@ -312,7 +327,7 @@ int32_t yg_firpfbch_crcf_execute_block_dev(yg_firpfbch_crcf q, const yg_cf32* d_
     YG_TRY(check(q));
     if (n_frames && (!d_x || !d_y)) return fail(YG_EVALUE, "null buffer");
     DeviceGuard g(q->dev);
-    return execute_dev(q, d_x, n_frames, d_y, cuda_stream ? (cudaStream_t)cuda_stream : q->stream);
+    return execute_dev(q, d_x, n_frames, d_y, (cudaStream_t)cuda_stream);
 }
 
 int32_t yg_firpfbch_crcf_execute_block(yg_firpfbch_crcf q, const yg_cf32* x, size_t n_frames, yg_cf32* y)
@@ -329,6 +344,7 @@ int32_t yg_firpfbch_crcf_execute_block(yg_firpfbch_crcf q, const yg_cf32* x, siz
     YG_TRY(execute_dev(q, q->d_stage_x.p, n_frames, q->d_stage_y.p, q->stream));
     YG_CUDA(cudaMemcpyAsync(y, q->d_stage_y.p, n * sizeof(yg_cf32), cudaMemcpyDeviceToHost, q->stream));
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     return YG_OK;
 }
 
@@ -342,6 +358,7 @@ int32_t yg_firpfbch_crcf_sync(yg_firpfbch_crcf q)
     YG_TRY(check(q));
     DeviceGuard g(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     return YG_OK;
 }
 

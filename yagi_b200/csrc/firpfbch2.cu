@@ -19,6 +19,7 @@ struct yg_firpfbch2_crcf_s {
     size_t L = 0;                 // taps used = 2*M*m
     int dev = 0;
     cudaStream_t stream = nullptr;
+    StreamOrder order;
     std::vector<float> h;         // prototype (L)
     DevBuf<float> d_h;
     DevBuf<float2> d_tw;
@@ -241,7 +242,16 @@ int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frame
     return YG_OK;
 }
 
+int32_t execute_dev_impl(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st);
+
 int32_t execute_dev(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
+{
+    YG_TRY(q->order.enter(st));
+    YG_TRY(execute_dev_impl(q, d_x, n_frames, d_y, st));
+    return q->order.leave(st);
+}
+
+int32_t execute_dev_impl(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
 {
     if (n_frames == 0) return YG_OK;
     if (q->type == YG_ANALYZER) {
@@ -334,6 +344,7 @@ int32_t yg_firpfbch2_crcf_clone(yg_firpfbch2_crcf q, yg_firpfbch2_crcf* out)
     YG_TRY(check(q));
     DeviceGuard g(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     yg_firpfbch2_crcf c = nullptr;
     YG_TRY(build(q->type, q->M, q->m, q->h.data(), q->h.size(), &c));
     cudaError_t e = cudaMemcpy(c->d_hist[c->cur].p, q->d_hist[q->cur].p, q->state_len * sizeof(yg_cf32),
@@ -349,6 +360,8 @@ int32_t yg_firpfbch2_crcf_destroy(yg_firpfbch2_crcf q)
     if (!q) return YG_OK;
     DeviceGuard g(q->dev);
     if (q->stream) cudaStreamSynchronize(q->stream);
+    q->order.wait_host();
+    q->order.destroy();
     firpfbch2_fast_release(q->fast);
     q->pipe.destroy();
     q->d_h.release(); q->d_tw.release(); q->d_hist[0].release(); q->d_hist[1].release(); q->d_U.release();
@@ -365,8 +378,10 @@ int32_t yg_firpfbch2_crcf_reset(yg_firpfbch2_crcf q)
 {
     YG_TRY(check(q));
     DeviceGuard g(q->dev);
+    YG_TRY(q->order.wait_host());
     YG_CUDA(cudaMemsetAsync(q->d_hist[q->cur].p, 0, q->state_len * sizeof(yg_cf32), q->stream));
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     q->flag = 0;
     return YG_OK;
 }
@@ -377,7 +392,7 @@ int32_t yg_firpfbch2_crcf_execute_block_dev(yg_firpfbch2_crcf q, const yg_cf32* 
     YG_TRY(check(q));
     if (n_frames && (!d_x || !d_y)) return fail(YG_EVALUE, "null buffer");
     DeviceGuard g(q->dev);
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : q->stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
     return execute_dev(q, d_x, n_frames, d_y, st);
 }
 
@@ -407,6 +422,7 @@ int32_t yg_firpfbch2_crcf_sync(yg_firpfbch2_crcf q)
     YG_TRY(check(q));
     DeviceGuard g(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     return YG_OK;
 }
 
@@ -434,6 +450,7 @@ int32_t yg_firpfbch2_crcf_get_state(yg_firpfbch2_crcf q, yg_cf32* hist, int32_t*
     YG_TRY(check(q));
     DeviceGuard g(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     if (hist) YG_CUDA(cudaMemcpy(hist, q->d_hist[q->cur].p, q->state_len * sizeof(yg_cf32), cudaMemcpyDeviceToHost));
     if (flag) *flag = q->flag;
     return YG_OK;
@@ -445,6 +462,7 @@ int32_t yg_firpfbch2_crcf_set_state(yg_firpfbch2_crcf q, const yg_cf32* hist, in
     if (flag != 0 && flag != 1) return fail(YG_EVALUE, "flag must be 0 or 1");
     DeviceGuard g(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
+    YG_TRY(q->order.wait_host());
     if (hist) YG_CUDA(cudaMemcpy(q->d_hist[q->cur].p, hist, q->state_len * sizeof(yg_cf32), cudaMemcpyHostToDevice));
     q->flag = flag;
     return YG_OK;

@@ -11,6 +11,7 @@ struct Firpfbch2FastPlan {
     void* d_taps = nullptr;       // kernel-specific tap layout (device)
     void* d_twid = nullptr;       // kernel-specific twiddle layout (device)
     int variant = 0;
+    int n_sm = 0;
 };
 
 // Decide whether (M, m) has a fused kernel and upload its tap / twiddle tables.
