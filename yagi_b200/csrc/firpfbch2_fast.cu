@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <type_traits>
 #include <vector>
 
@@ -40,7 +41,12 @@ constexpr int kThreads = kFirThreads + kFftThreads;
 constexpr int kInStageBytes = kPairsPerBatch * kM * 8;            // 32 KB of input per batch
 constexpr int kRegionBytes = 16 * 17 * 16;                        // 4352: padded 16x16 exchange, 16 B units
 constexpr int kVBufBytes = kPairsPerBatch * kRegionBytes;         // 69632
-constexpr int kSmemBytes = 2 * kInStageBytes + 2 * kVBufBytes + 64;
+constexpr int kSmemBytes = 2 * kInStageBytes + 2 * kVBufBytes + 128;
+// mbarrier slots (8 B each) after the data buffers
+constexpr int kMbInFull = 0;     // [2]    TMA transaction barriers, one per input stage
+constexpr int kMbInFree = 2;     // [2]    8 FIR warps have drained the stage          (pipeline v2)
+constexpr int kMbVFull = 4;      // [2][4] 8 FIR warps have written regions 4g..4g+3   (pipeline v2)
+constexpr int kMbVFree = 12;     // [2]    8 FFT warps have drained the buffer         (pipeline v2)
 
 // named barriers (0 is __syncthreads)
 constexpr int kBarFull0 = 1, kBarEmpty0 = 3, kBarFir = 5;
@@ -57,6 +63,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
@@ -172,7 +182,7 @@ struct FastParams {
     const float2* twid;       // [16][16] e^{+j 2 pi n2 k1 / 256}
 };
 
-template <int kTaps>                     // 2m + 1
+template <int kTaps, bool kV2>          // kTaps = 2m + 1; kV2: mbarrier pipeline with staggered FFT start
 __device__ __forceinline__ void fir_role(const FastParams& p, uint32_t smem, uint32_t mbar,
                                          long long batch_begin, long long batch_end)
 {
@@ -232,9 +242,15 @@ __device__ __forceinline__ void fir_role(const FastParams& p, uint32_t smem, uin
         const uint32_t in = in_stage0 + st * kInStageBytes + pos * 8;
 #pragma unroll
         for (int r = 0; r < kPairsPerBatch; r++) W[16 * PAR + r] = lds64(in + r * (kM * 8));
-        bar_sync(kBarFir, kFirThreads);                                 // everyone has drained this stage
-        if (j == 0 && batch + 2 < batch_end) issue_load(batch + 2);
-        if (lb >= 2) bar_sync(kBarEmpty0 + PAR, kThreads);              // FFT role released V[PAR]
+        if (kV2) {
+            __syncwarp();
+            if ((j & 31) == 0) mbar_arrive(mbar + 8 * (kMbInFree + st));  // this warp has drained the stage
+            if (lb >= 2) mbar_wait(mbar + 8 * (kMbVFree + PAR), (uint32_t)(((lb >> 1) - 1) & 1));
+        } else {
+            bar_sync(kBarFir, kFirThreads);                             // everyone has drained this stage
+            if (j == 0 && batch + 2 < batch_end) issue_load(batch + 2);
+            if (lb >= 2) bar_sync(kBarEmpty0 + PAR, kThreads);          // FFT role released V[PAR]
+        }
         const uint32_t vout = vbuf0 + PAR * kVBufBytes + j * 16;
 #pragma unroll
         for (int r = 0; r < kPairsPerBatch; r++) {
@@ -246,8 +262,19 @@ __device__ __forceinline__ void fir_role(const FastParams& p, uint32_t smem, uin
                 aim = fma2(T[i], f2(w.y), aim);
             }
             sts128(vout + r * kRegionBytes, make_float4(are.x, are.y, aim.x, aim.y));
+            if (kV2 && (r & 3) == 3) {
+                __syncwarp();
+                if ((j & 31) == 0) mbar_arrive(mbar + 8 * (kMbVFull + 4 * PAR + (r >> 2)));
+            }
         }
-        bar_arrive(kBarFull0 + PAR, kThreads);
+        if (kV2) {
+            if (j == 0 && batch + 2 < batch_end) {
+                mbar_wait(mbar + 8 * (kMbInFree + st), (uint32_t)((lb >> 1) & 1));
+                issue_load(batch + 2);
+            }
+        } else {
+            bar_arrive(kBarFull0 + PAR, kThreads);
+        }
     };
 
     for (long long batch = batch_begin; batch < batch_end; batch += 2) {
@@ -256,7 +283,8 @@ __device__ __forceinline__ void fir_role(const FastParams& p, uint32_t smem, uin
     }
 }
 
-__device__ __forceinline__ void fft_role(const FastParams& p, uint32_t smem, long long batch_begin, long long batch_end)
+template <bool kV2>
+__device__ __forceinline__ void fft_role(const FastParams& p, uint32_t smem, uint32_t mbar, long long batch_begin, long long batch_end)
 {
     const int tid = threadIdx.x - kFirThreads;
     const int g = tid >> 4;              // frame pair within the batch
@@ -275,7 +303,8 @@ __device__ __forceinline__ void fft_role(const FastParams& p, uint32_t smem, lon
         const int b = (int)((batch - batch_begin) & 1);
         const uint32_t region = vbuf0 + b * kVBufBytes + g * kRegionBytes;
         const long long pair = batch * kPairsPerBatch + g;
-        bar_sync(kBarFull0 + b, kThreads);
+        if (kV2) mbar_wait(mbar + 8 * (kMbVFull + 4 * b + (tid >> 6)), (uint32_t)(((batch - batch_begin) >> 1) & 1));
+        else bar_sync(kBarFull0 + b, kThreads);
 
         C2 v[16];
         // pass 1: thread n2 = t gathers X[16 n1 + n2], n1 = 0..15
@@ -303,7 +332,11 @@ __device__ __forceinline__ void fft_role(const FastParams& p, uint32_t smem, lon
             v[n2].im = make_float2(q.z, q.w);
         }
         __syncwarp();
-        bar_arrive(kBarEmpty0 + b, kThreads);       // V[b] may be overwritten by the FIR role
+        if (kV2) {
+            if ((tid & 31) == 0) mbar_arrive(mbar + 8 * (kMbVFree + b));
+        } else {
+            bar_arrive(kBarEmpty0 + b, kThreads);   // V[b] may be overwritten by the FIR role
+        }
         dft16(v);
         if (pair < p.n_pairs) {
             float2* ye = p.y + (p.f0 + 2 * pair) * (long long)kM + t;     // even frame of the pair
@@ -318,7 +351,7 @@ __device__ __forceinline__ void fft_role(const FastParams& p, uint32_t smem, lon
     }
 }
 
-template <int kTaps>
+template <int kTaps, bool kV2>
 __global__ void __launch_bounds__(kThreads, 1) k_firpfbch2_analysis_fused(const FastParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -330,31 +363,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_firpfbch2_analysis_fused(const 
     const long long batch_end = (n_batches * (blockIdx.x + 1)) / gridDim.x;
 
     if (threadIdx.x == 0) {
-        mbar_init(mbar, 1);
-        mbar_init(mbar + 8, 1);
+        mbar_init(mbar + 8 * (kMbInFull + 0), 1);
+        mbar_init(mbar + 8 * (kMbInFull + 1), 1);
+        for (int i = 0; i < 2; i++) mbar_init(mbar + 8 * (kMbInFree + i), 8);
+        for (int i = 0; i < 8; i++) mbar_init(mbar + 8 * (kMbVFull + i), 8);
+        for (int i = 0; i < 2; i++) mbar_init(mbar + 8 * (kMbVFree + i), 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     if (batch_begin >= batch_end) return;
 
-    if (threadIdx.x < kFirThreads) fir_role<kTaps>(p, smem, mbar, batch_begin, batch_end);
-    else fft_role(p, smem, batch_begin, batch_end);
+    if (threadIdx.x < kFirThreads) fir_role<kTaps, kV2>(p, smem, mbar, batch_begin, batch_end);
+    else fft_role<kV2>(p, smem, mbar, batch_begin, batch_end);
 }
 
-template <int kTaps>
+template <int kTaps, bool kV2>
 int32_t launch_t(const Firpfbch2FastPlan& plan, const FastParams& p, cudaStream_t st)
 {
     static bool attr_done[64] = {};
     int dev = 0;
     YG_CUDA(cudaGetDevice(&dev));
     if (!attr_done[dev & 63]) {
-        YG_CUDA(cudaFuncSetAttribute(k_firpfbch2_analysis_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        YG_CUDA(cudaFuncSetAttribute(k_firpfbch2_analysis_fused<kTaps, kV2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_done[dev & 63] = true;
     }
     const long long n_batches = (p.n_pairs + kPairsPerBatch - 1) / kPairsPerBatch;
     const int grid = (int)std::min<long long>(plan.n_sm, n_batches);
-    k_firpfbch2_analysis_fused<kTaps><<<grid, kThreads, kSmemBytes, st>>>(p);
+    k_firpfbch2_analysis_fused<kTaps, kV2><<<grid, kThreads, kSmemBytes, st>>>(p);
     YG_CUDA(cudaGetLastError());
     return YG_OK;
 }
@@ -405,6 +441,7 @@ int32_t firpfbch2_fast_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const 
     YG_CUDA(cudaMalloc(&p.d_twid, tw.size() * sizeof(float2)));
     YG_CUDA(cudaMemcpy(p.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     p.min_frames = 64;
+    if (const char* v = getenv("YG_FAST_VARIANT")) p.variant = atoi(v);      // experiment knob
     p.supported = true;
     return YG_OK;
 }
@@ -430,7 +467,7 @@ int32_t firpfbch2_fast_launch(const Firpfbch2FastPlan& plan, const float2* hist,
     p.n_pairs = (long long)(n_frames / 2);
     p.taps = reinterpret_cast<const float2*>(plan.d_taps);
     p.twid = reinterpret_cast<const float2*>(plan.d_twid);
-    return launch_t<15>(plan, p, st);
+    return plan.variant == 0 ? launch_t<15, false>(plan, p, st) : launch_t<15, true>(plan, p, st);
 }
 
 }  // namespace yg

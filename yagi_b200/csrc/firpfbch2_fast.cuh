@@ -10,7 +10,7 @@ struct Firpfbch2FastPlan {
     size_t min_frames = 0;        // below this the generic kernel is used
     void* d_taps = nullptr;       // kernel-specific tap layout (device)
     void* d_twid = nullptr;       // kernel-specific twiddle layout (device)
-    int variant = 0;
+    int variant = 1;             // 1 = mbarrier pipeline with staggered FFT start (default), 0 = named barriers
     int n_sm = 0;
 };
 
