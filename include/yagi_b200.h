@@ -89,8 +89,9 @@ int32_t yg_firpfbch2_crcf_get_M(yg_firpfbch2_crcf q, uint32_t* M);
 int32_t yg_firpfbch2_crcf_get_m(yg_firpfbch2_crcf q, uint32_t* m);
 int32_t yg_firpfbch2_crcf_get_taps(yg_firpfbch2_crcf q, float* h /* 2*M*m */);
 /* Stream state as plain data (what Clone copies; also the time-shard hand-off).
- * Analyzer: the last (4m-1)*M/2 input samples, oldest first.  Synthesizer: the last 4m-1
- * half-scaled IFFT frames (M each), oldest first.  `flag` = frame parity since reset. */
+ * Both types keep the tail of their INPUT stream, oldest first: analyzer the last (4m-1)*M/2
+ * input samples, synthesizer the last 4m-1 input frames (M each; their IFFTs are recomputed, so the
+ * state stays independent of the kernel used).  `flag` = frame parity since reset. */
 int32_t yg_firpfbch2_crcf_state_len(yg_firpfbch2_crcf q, size_t* n_cf32);
 int32_t yg_firpfbch2_crcf_get_state(yg_firpfbch2_crcf q, yg_cf32* hist, int32_t* flag);
 int32_t yg_firpfbch2_crcf_set_state(yg_firpfbch2_crcf q, const yg_cf32* hist, int32_t flag);

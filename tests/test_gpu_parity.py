@@ -353,3 +353,66 @@ def test_fused_path_full_size_properties():
         ref = o.execute_block(seg)
         got = y[f0: f0 + nf].reshape(-1).cpu().numpy()
         assert_parity(got, ref, "full-size window at frame %d" % f0)
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 5, 6, 8])
+def test_fused_path_other_semi_lengths(m):
+    """The fused kernel is instantiated for M=256, m=1..8 (2m+1 register taps)."""
+    M, K = 256, 700
+    rng = np.random.default_rng(m)
+    h = rng.standard_normal(2 * M * m).astype(np.float32)
+    x = _rand_c(rng, K * M // 2)
+    q = yb.FirPfbCh2.new(A, M, m, h)
+    y = np.concatenate([q.execute_block(x[: 301 * M // 2]), q.execute_block(x[301 * M // 2:])])
+    assert q.last_path() == 2
+    ref = _oracle_analysis(M, m, x, h=h)
+    scale = max(1.0, np.abs(ref).max())
+    assert_parity(y / scale, ref / scale, "fused m=%d" % m)
+
+
+# ------------------------------------------------------------------ fused synthesis (M=256, m=1..7)
+@pytest.mark.parametrize("m", [7, 1, 4])
+def test_fused_synthesis_state_continuity_and_edges(m):
+    """The fused synthesis kernel (last_path == 2) across calls of uneven sizes: odd-parity starts,
+    lengths that are not multiples of 32, history from the previous call, clone mid-stream."""
+    M, K = 256, 3000
+    rng = np.random.default_rng(100 + m)
+    X = _rand_c(rng, K * M)
+    ref = po.FirPfbCh2.new_kaiser(po.SYNTHESIZER, M, m, 60.0).execute_block(X).reshape(K, M // 2)
+    q = yb.FirPfbCh2.new_kaiser(S, M, m, 60.0)
+    cuts = [0, 64, 129, 130, 331, 1000, 1067, 1131, 2001, K]
+    outs = []
+    for a, b in zip(cuts, cuts[1:]):
+        outs.append(q.execute_block(X[a * M: b * M]))
+        if b - a >= 96:
+            assert q.last_path() == 2, (a, b)
+    y = np.concatenate(outs).reshape(K, M // 2)
+    scale = max(1.0, np.abs(ref).max())
+    assert_parity(y / scale, ref / scale, "fused synthesis m=%d" % m)
+    per_frame = np.abs(y - ref).max(axis=1) / scale
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+    # state is plain data: (4m-1) input frames + parity
+    hist, flag = q.get_state()
+    assert flag == K % 2 and hist.size == (4 * m - 1) * M
+    np.testing.assert_array_equal(hist, X[(K - (4 * m - 1)) * M:])
+    c = yb.FirPfbCh2.new_kaiser(S, M, m, 60.0)
+    c.set_state(hist, flag)
+    v = _rand_c(rng, 200 * M)
+    np.testing.assert_array_equal(q.execute_block(v), c.execute_block(v))
+
+
+def test_fused_round_trip_M256():
+    """analysis -> synthesis on the fused kernels reconstructs the input (delay 2Mm - M/2 + 1) and
+    matches the CPU path."""
+    M, m, N = 256, 7, 1 << 20
+    x = stimulus.noise_plus_tones(0, N, M)
+    qa = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    qs = yb.FirPfbCh2.new_kaiser(S, M, m, 60.0)
+    Y = qa.execute_block(x)
+    y = qs.execute_block(Y)
+    assert qa.last_path() == 2 and qs.last_path() == 2
+    yr = po.FirPfbCh2.new_kaiser(po.SYNTHESIZER, M, m, 60.0).execute_block(
+        po.FirPfbCh2.new_kaiser(po.ANALYZER, M, m, 60.0).execute_block(x))
+    assert_parity(y, yr, "round trip vs CPU path")
+    D = 2 * M * m - M // 2 + 1
+    assert np.abs(y[D:] - x[: N - D]).max() < 2e-3

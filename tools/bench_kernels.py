@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""tools/bench_kernels.py -- device-resident throughput of the other kernels on the path (not the
+headline bench): firpfbch2 synthesis, firpfbch many-stream analysis, batched firfilt, and the
+M=1024 round trip of BASELINE config #4.  Prints one JSON line per kernel with its roofline fraction.
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+import yagi_b200 as yb
+
+PEAK = 6537.6
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, steps=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def report(name, ms, algo_bytes, units, unit_name, extra=None):
+    gbs = algo_bytes / (ms * 1e-3) / 1e9
+    line = {"kernel": name, "ms": round(ms, 4), "algorithmic_GBps": round(gbs, 1), "peak_GBps": PEAK,
+            "frac_of_measured_hbm": round(gbs / PEAK, 4), "M%s_per_s" % unit_name: round(units / (ms * 1e-3) / 1e6, 1)}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def randc(n):
+    x = torch.empty(n, 2, dtype=torch.float32, device="cuda")
+    x.normal_(0, 1)
+    return torch.view_as_complex(x)
+
+
+def main():
+    torch.cuda.set_device(0)
+    which = sys.argv[1:] or ["synth", "ana1024", "synth1024", "pfbch", "firfilt"]
+    if "synth" in which:
+        M, m = 256, 7
+        K = (1 << 28) // M                      # 2^28 channel samples in, 2^27 samples out
+        X = randc(K * M)
+        y = torch.empty(K * M // 2, dtype=torch.complex64, device="cuda")
+        q = yb.FirPfbCh2.new_kaiser(yb.SYNTHESIZER, M, m, 60.0)
+        ms = timed(lambda: q.execute_block(X, K, out=y))
+        report("firpfbch2 synthesis M=256 m=7 (path %d)" % q.last_path(), ms, 24.0 * K * M // 2, K * M // 2, "samples_out",
+               {"kernel_ms": round(float(np.mean(q.kernel_times_ms(16))), 4)})
+        del X, y, q
+    if "ana1024" in which or "synth1024" in which:
+        M, m = 1024, 4
+        N = 1 << 24
+        x = randc(N)
+        Y = torch.empty(2 * N, dtype=torch.complex64, device="cuda")
+        qa = yb.FirPfbCh2.new_kaiser(yb.ANALYZER, M, m, 60.0)
+        ms = timed(lambda: qa.execute_block(x, N // (M // 2), out=Y), steps=5)
+        report("firpfbch2 analysis M=1024 m=4 (path %d)" % qa.last_path(), ms, 24.0 * N, N, "samples_in")
+        y = torch.empty(N, dtype=torch.complex64, device="cuda")
+        qs = yb.FirPfbCh2.new_kaiser(yb.SYNTHESIZER, M, m, 60.0)
+        ms = timed(lambda: qs.execute_block(Y, N // (M // 2), out=y), steps=5)
+        report("firpfbch2 synthesis M=1024 m=4 (path %d)" % qs.last_path(), ms, 24.0 * N, N, "samples_out")
+        del x, Y, y, qa, qs
+    if "pfbch" in which:
+        M, m, S, n = 64, 7, 512, 1 << 18       # config #5: 512 streams per GPU
+        x = randc(S * n)
+        y = torch.empty(S * n, dtype=torch.complex64, device="cuda")
+        q = yb.FirPfbCh.new_kaiser(yb.ANALYZER, M, m, 60.0, n_streams=S)
+        ms = timed(lambda: q.execute_block(x, n // M, out=y), steps=5)
+        report("firpfbch analysis M=64 m=7, 512 streams x 2^18", ms, 16.0 * S * n, S * n, "samples_in")
+        del x, y, q
+    if "firfilt" in which:
+        S, n = 1024, 1 << 18                    # config #2 geometry at a quarter of the length
+        x = randc(S * n)
+        y = torch.empty(S * n, dtype=torch.complex64, device="cuda")
+        q = yb.FirFilt.new_kaiser(63, 0.25, 60.0, 0.0, n_streams=S)
+        ms = timed(lambda: q.execute_block(x, out=y), steps=5)
+        flops = 252.0 * S * n
+        report("firfilt_crcf 63 taps, 1024 streams x 2^18", ms, 16.0 * S * n, S * n, "samples",
+               {"fp32_TFLOPs": round(flops / (ms * 1e-3) / 1e12, 2)})
+
+
+if __name__ == "__main__":
+    main()

@@ -23,7 +23,8 @@ struct yg_firpfbch2_crcf_s {
     std::vector<float> h;         // prototype (L)
     DevBuf<float> d_h;
     DevBuf<float2> d_tw;
-    size_t state_len = 0;         // cf32 entries of history
+    size_t state_len = 0;         // cf32 entries of history exposed through get/set_state
+    size_t hist_len = 0;          // cf32 entries kept on the device (>= state_len; synthesiser keeps 32 frames)
     DevBuf<yg_cf32> d_hist[2];
     int cur = 0;
     int32_t flag = 0;
@@ -38,6 +39,7 @@ struct yg_firpfbch2_crcf_s {
     bool timed = false;
     void next_events() { ev0 = ev0s[n_timed % kRing]; ev1 = ev1s[n_timed % kRing]; n_timed++; }
     Firpfbch2FastPlan fast;       // fused fast path (may be unsupported for this M/m)
+    Firpfbch2FastPlan sfast;      // fused synthesis fast path
 };
 
 namespace {
@@ -92,23 +94,27 @@ __global__ void k_update_hist(float2* __restrict__ hist_new, const float2* __res
     }
 }
 
-// Synthesiser stage 1: U[k] = IDFT_unnorm(X_k) * (1/M) * (M/2)   (two f32 multiplies, as upstream)
-__global__ void k_synth_ifft(const float2* __restrict__ tw, const float2* __restrict__ x, float2* __restrict__ U,
-                             uint32_t M, long long n_frames)
+// Synthesiser stage 1: U[v] = IDFT_unnorm(X_v) * (1/M) * (M/2)   (two f32 multiplies, as upstream)
+// for virtual frames v = v_begin .. v_end-1 of the stream (hist ++ x): frame v >= 0 is x[v], frame
+// v < 0 is input history.  U[0] corresponds to v_begin.
+__global__ void k_synth_ifft(const float2* __restrict__ tw, const float2* __restrict__ hist, long long hist_frames,
+                             const float2* __restrict__ x, float2* __restrict__ U, uint32_t M,
+                             long long v_begin, long long v_end)
 {
     extern __shared__ float2 sm[];
     float2* X = sm;
     float2* Y = sm + M;
     const float s0 = 1.0f / (float)M;
     const float s1 = (float)(M >> 1);
-    for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
-        for (uint32_t c = threadIdx.x; c < M; c += blockDim.x) X[c] = __ldg(&x[f * (long long)M + c]);
+    for (long long v = v_begin + blockIdx.x; v < v_end; v += gridDim.x) {
+        const float2* src = (v >= 0) ? x + v * (long long)M : hist + (hist_frames + v) * (long long)M;
+        for (uint32_t c = threadIdx.x; c < M; c += blockDim.x) X[c] = __ldg(&src[c]);
         const float2* r = block_dft(X, Y, M, tw, 1);
         for (uint32_t c = threadIdx.x; c < M; c += blockDim.x) {
-            float2 v = r[c];
-            v.x *= s0; v.y *= s0;
-            v.x *= s1; v.y *= s1;
-            U[f * (long long)M + c] = v;
+            float2 vv = r[c];
+            vv.x *= s0; vv.y *= s0;
+            vv.x *= s1; vv.y *= s1;
+            U[(v - v_begin) * (long long)M + c] = vv;
         }
         __syncthreads();
     }
@@ -117,15 +123,17 @@ __global__ void k_synth_ifft(const float2* __restrict__ tw, const float2* __rest
 // Synthesiser stage 2: weighted overlap-add.  U points at frame 0 of this call; frames -1..-(4m-1)
 // (history) precede it in memory.  One thread per output sample.
 __global__ void k_synth_wola(const float* __restrict__ h, const float2* __restrict__ U, float2* __restrict__ y,
-                             uint32_t M, uint32_t m, long long n_frames, int flag0)
+                             uint32_t M, uint32_t m, long long n_frames, int par0)
 {
+    // U points at the first frame of this launch; its 4m-1 predecessors precede it in memory.
+    // y points at the first output sample of this launch; par0 = parity of that frame.
     const uint32_t M2 = M >> 1;
     const long long total = n_frames * (long long)M2;
     for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total;
          o += (long long)gridDim.x * blockDim.x) {
         const long long f = o / M2;
         const uint32_t i = (uint32_t)(o - f * M2);
-        const int par = (flag0 + (int)(f & 1)) & 1;
+        const int par = (par0 + (int)(f & 1)) & 1;
         uint32_t col = i + (par ? M2 : 0);
         // two banks (even / odd l), each summed oldest first, then added (upstream y0 + y1)
         float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
@@ -176,7 +184,7 @@ int32_t launch_generic_analysis(yg_firpfbch2_crcf q, const float2* hist, const f
     YG_TRY(set_smem((const void*)k_analysis_generic, smem));
     const int block = (int)std::min<uint32_t>(256, (q->M + 31) / 32 * 32);
     const int grid = (int)std::min<size_t>(f_end - f_begin, 148 * 16);
-    k_analysis_generic<<<grid, block, smem, st>>>(q->d_h.p, q->d_tw.p, hist, (long long)q->state_len, x, y, q->M,
+    k_analysis_generic<<<grid, block, smem, st>>>(q->d_h.p, q->d_tw.p, hist, (long long)q->hist_len, x, y, q->M,
                                                   2 * q->m, (long long)f_begin, (long long)f_end, q->flag);
     YG_CUDA(cudaGetLastError());
     return YG_OK;
@@ -196,7 +204,7 @@ int32_t launch_analysis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames
         const size_t lead = (q->flag & 1) ? 1 : 0;
         const size_t body = (n_frames - lead) & ~(size_t)1;
         YG_CUDA(cudaEventRecord(q->ev0, st));
-        YG_TRY(firpfbch2_fast_launch(q->fast, hist, (long long)q->state_len, x, y, lead, body, st));
+        YG_TRY(firpfbch2_fast_launch(q->fast, hist, (long long)q->hist_len, x, y, lead, body, st));
         YG_CUDA(cudaEventRecord(q->ev1, st));
         q->timed = true;
         q->last_path = 2;
@@ -212,33 +220,56 @@ int32_t launch_analysis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames
     return YG_OK;
 }
 
-int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
+int32_t launch_generic_synthesis(yg_firpfbch2_crcf q, const float2* hist, const float2* x, float2* y,
+                                 size_t f_begin, size_t f_end, cudaStream_t st)
 {
+    if (f_end <= f_begin) return YG_OK;
     const uint32_t M = q->M;
-    const size_t nh = 4 * (size_t)q->m - 1;
-    YG_TRY(q->d_U.reserve((nh + n_frames) * M));
+    const long long nh = 4 * (long long)q->m - 1;
+    const long long nf = (long long)(f_end - f_begin);
+    YG_TRY(q->d_U.reserve((size_t)(nh + nf) * M));
     float2* U = reinterpret_cast<float2*>(q->d_U.p);
-    YG_CUDA(cudaMemcpyAsync(U, q->d_hist[q->cur].p, nh * M * sizeof(yg_cf32), cudaMemcpyDeviceToDevice, st));
     const size_t smem = smem_dft(M);
     YG_TRY(set_smem((const void*)k_synth_ifft, smem));
     const int block = (int)std::min<uint32_t>(256, (M + 31) / 32 * 32);
-    const int grid = (int)std::min<size_t>(n_frames, 148 * 16);
-    q->next_events();
-    YG_CUDA(cudaEventRecord(q->ev0, st));
-    k_synth_ifft<<<grid, block, smem, st>>>(q->d_tw.p, reinterpret_cast<const float2*>(d_x), U + nh * M, M,
-                                            (long long)n_frames);
+    const int grid = (int)std::min<long long>(nh + nf, 148 * 16);
+    k_synth_ifft<<<grid, block, smem, st>>>(q->d_tw.p, hist, (long long)(q->hist_len / M), x, U, M,
+                                            (long long)f_begin - nh, (long long)f_end);
     YG_CUDA(cudaGetLastError());
-    const long long total = (long long)n_frames * q->M2;
+    const long long total = nf * q->M2;
     const int grid2 = (int)std::min<long long>((total + 255) / 256, 148 * 32);
-    k_synth_wola<<<grid2, 256, 0, st>>>(q->d_h.p, U + nh * M, reinterpret_cast<float2*>(d_y), M, q->m,
-                                        (long long)n_frames, q->flag);
+    k_synth_wola<<<grid2, 256, 0, st>>>(q->d_h.p, U + nh * M, y + (long long)f_begin * q->M2, M, q->m, nf,
+                                        (q->flag + (int)(f_begin & 1)) & 1);
     YG_CUDA(cudaGetLastError());
+    return YG_OK;
+}
+
+int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
+{
+    const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
+    const float2* x = reinterpret_cast<const float2*>(d_x);
+    float2* y = reinterpret_cast<float2*>(d_y);
+    q->next_events();
+    // The fused kernel takes an even-parity start and whole rounds of 32 frames; the rest goes to
+    // the generic kernels.  All of them read the same (history ++ x) stream and write disjoint
+    // output ranges, so their order does not matter.
+    const size_t lead = (q->flag & 1) ? 1 : 0;
+    const size_t body = (n_frames > lead) ? ((n_frames - lead) / 32) * 32 : 0;
+    if (q->sfast.supported && body >= q->sfast.min_frames) {
+        YG_CUDA(cudaEventRecord(q->ev0, st));
+        YG_TRY(firpfbch2_synth_fast_launch(q->sfast, hist, x, y, lead, body, st));
+        YG_CUDA(cudaEventRecord(q->ev1, st));
+        q->timed = true;
+        q->last_path = 2;
+        YG_TRY(launch_generic_synthesis(q, hist, x, y, 0, lead, st));
+        YG_TRY(launch_generic_synthesis(q, hist, x, y, lead + body, n_frames, st));
+        return YG_OK;
+    }
+    YG_CUDA(cudaEventRecord(q->ev0, st));
+    YG_TRY(launch_generic_synthesis(q, hist, x, y, 0, n_frames, st));
     YG_CUDA(cudaEventRecord(q->ev1, st));
     q->timed = true;
     q->last_path = 1;
-    // new history = last nh frames of U
-    YG_CUDA(cudaMemcpyAsync(q->d_hist[q->cur].p, U + n_frames * M, nh * M * sizeof(yg_cf32),
-                            cudaMemcpyDeviceToDevice, st));
     return YG_OK;
 }
 
@@ -254,20 +285,18 @@ int32_t execute_dev(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg
 int32_t execute_dev_impl(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
 {
     if (n_frames == 0) return YG_OK;
-    if (q->type == YG_ANALYZER) {
-        YG_TRY(launch_analysis(q, d_x, n_frames, d_y, st));
-        const long long n_new = (long long)n_frames * q->M2;
-        const long long Hlen = (long long)q->state_len;
-        const int nxt = q->cur ^ 1;
-        const int grid = (int)std::min<long long>((Hlen + 255) / 256, 1024);
-        k_update_hist<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(q->d_hist[nxt].p),
-                                            reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
-                                            reinterpret_cast<const float2*>(d_x), n_new);
-        YG_CUDA(cudaGetLastError());
-        q->cur = nxt;
-    } else {
-        YG_TRY(launch_synthesis(q, d_x, n_frames, d_y, st));
-    }
+    if (q->type == YG_ANALYZER) YG_TRY(launch_analysis(q, d_x, n_frames, d_y, st));
+    else YG_TRY(launch_synthesis(q, d_x, n_frames, d_y, st));
+    // both types keep the tail of their INPUT stream as state
+    const long long n_new = (long long)n_frames * (q->type == YG_ANALYZER ? q->M2 : q->M);
+    const long long Hlen = (long long)q->hist_len;
+    const int nxt = q->cur ^ 1;
+    const int grid = (int)std::min<long long>((Hlen + 255) / 256, 1024);
+    k_update_hist<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(q->d_hist[nxt].p),
+                                        reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
+                                        reinterpret_cast<const float2*>(d_x), n_new);
+    YG_CUDA(cudaGetLastError());
+    q->cur = nxt;
     q->flag = (q->flag + (int)(n_frames & 1)) & 1;
     return YG_OK;
 }
@@ -302,11 +331,14 @@ int32_t build(int32_t type, uint32_t M, uint32_t m, const float* h, size_t h_len
     CUDAQ(cudaMemcpy(q->d_tw.p, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
     const size_t nh = 4 * (size_t)m - 1;
     q->state_len = (type == YG_ANALYZER) ? nh * q->M2 : nh * M;
+    // the synthesiser keeps at least 32 input frames so the fused kernel can warm up a whole round
+    q->hist_len = (type == YG_ANALYZER) ? q->state_len : std::max<size_t>(nh, 32) * M;
     for (int b = 0; b < 2; b++) {
-        TRYQ(q->d_hist[b].reserve(q->state_len));
-        CUDAQ(cudaMemset(q->d_hist[b].p, 0, q->state_len * sizeof(yg_cf32)));
+        TRYQ(q->d_hist[b].reserve(q->hist_len));
+        CUDAQ(cudaMemset(q->d_hist[b].p, 0, q->hist_len * sizeof(yg_cf32)));
     }
     if (type == YG_ANALYZER) TRYQ(firpfbch2_fast_plan(q->fast, M, m, q->h.data()));
+    else TRYQ(firpfbch2_synth_fast_plan(q->sfast, M, m, q->h.data()));
 #undef TRYQ
 #undef CUDAQ
     *out = q;
@@ -347,7 +379,7 @@ int32_t yg_firpfbch2_crcf_clone(yg_firpfbch2_crcf q, yg_firpfbch2_crcf* out)
     YG_TRY(q->order.wait_host());
     yg_firpfbch2_crcf c = nullptr;
     YG_TRY(build(q->type, q->M, q->m, q->h.data(), q->h.size(), &c));
-    cudaError_t e = cudaMemcpy(c->d_hist[c->cur].p, q->d_hist[q->cur].p, q->state_len * sizeof(yg_cf32),
+    cudaError_t e = cudaMemcpy(c->d_hist[c->cur].p, q->d_hist[q->cur].p, q->hist_len * sizeof(yg_cf32),
                                cudaMemcpyDeviceToDevice);
     if (e != cudaSuccess) { yg_firpfbch2_crcf_destroy(c); return fail(YG_EINTERNAL, "CUDA error %s", cudaGetErrorString(e)); }
     c->flag = q->flag;
@@ -363,6 +395,7 @@ int32_t yg_firpfbch2_crcf_destroy(yg_firpfbch2_crcf q)
     q->order.wait_host();
     q->order.destroy();
     firpfbch2_fast_release(q->fast);
+    firpfbch2_fast_release(q->sfast);
     q->pipe.destroy();
     q->d_h.release(); q->d_tw.release(); q->d_hist[0].release(); q->d_hist[1].release(); q->d_U.release();
     for (int i = 0; i < yg_firpfbch2_crcf_s::kRing; i++) {
@@ -379,7 +412,7 @@ int32_t yg_firpfbch2_crcf_reset(yg_firpfbch2_crcf q)
     YG_TRY(check(q));
     DeviceGuard g(q->dev);
     YG_TRY(q->order.wait_host());
-    YG_CUDA(cudaMemsetAsync(q->d_hist[q->cur].p, 0, q->state_len * sizeof(yg_cf32), q->stream));
+    YG_CUDA(cudaMemsetAsync(q->d_hist[q->cur].p, 0, q->hist_len * sizeof(yg_cf32), q->stream));
     YG_CUDA(cudaStreamSynchronize(q->stream));
     YG_TRY(q->order.wait_host());
     q->flag = 0;
@@ -403,9 +436,9 @@ int32_t yg_firpfbch2_crcf_execute_block(yg_firpfbch2_crcf q, const yg_cf32* x, s
     DeviceGuard g(q->dev);
     const size_t nin = (q->type == YG_ANALYZER) ? q->M2 : q->M;
     const size_t nout = (q->type == YG_ANALYZER) ? q->M : q->M2;
-    // ~32 MiB of input per chunk, an even number of frames so chunk starts keep the fast path
+    // ~32 MiB of input per chunk
     size_t fpc = ((size_t)32 << 20) / (nin * sizeof(yg_cf32));
-    fpc = std::max<size_t>(2, fpc & ~(size_t)1);
+    fpc = std::max<size_t>(32, fpc & ~(size_t)31);      // whole 32-frame rounds keep chunk starts on the fused paths
     return run_host_pipe(q->pipe, q->stream, x, y, n_frames, nin, nout, fpc,
                          [&](const yg_cf32* dx, size_t f, yg_cf32* dy, cudaStream_t st) {
                              return execute_dev(q, dx, f, dy, st);
@@ -451,7 +484,7 @@ int32_t yg_firpfbch2_crcf_get_state(yg_firpfbch2_crcf q, yg_cf32* hist, int32_t*
     DeviceGuard g(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
     YG_TRY(q->order.wait_host());
-    if (hist) YG_CUDA(cudaMemcpy(hist, q->d_hist[q->cur].p, q->state_len * sizeof(yg_cf32), cudaMemcpyDeviceToHost));
+    if (hist) YG_CUDA(cudaMemcpy(hist, q->d_hist[q->cur].p + (q->hist_len - q->state_len), q->state_len * sizeof(yg_cf32), cudaMemcpyDeviceToHost));
     if (flag) *flag = q->flag;
     return YG_OK;
 }
@@ -463,7 +496,10 @@ int32_t yg_firpfbch2_crcf_set_state(yg_firpfbch2_crcf q, const yg_cf32* hist, in
     DeviceGuard g(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
     YG_TRY(q->order.wait_host());
-    if (hist) YG_CUDA(cudaMemcpy(q->d_hist[q->cur].p, hist, q->state_len * sizeof(yg_cf32), cudaMemcpyHostToDevice));
+    if (hist) {
+        YG_CUDA(cudaMemset(q->d_hist[q->cur].p, 0, q->hist_len * sizeof(yg_cf32)));
+        YG_CUDA(cudaMemcpy(q->d_hist[q->cur].p + (q->hist_len - q->state_len), hist, q->state_len * sizeof(yg_cf32), cudaMemcpyHostToDevice));
+    }
     q->flag = flag;
     return YG_OK;
 }

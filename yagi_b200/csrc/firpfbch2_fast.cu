@@ -21,6 +21,7 @@
 // their new sample on the odd frame of a pair, so their even-frame taps are delayed by one
 // slot: both halves run the same (2m+1)-tap code with per-thread tap tables.
 #include "firpfbch2_fast.cuh"
+#include "fused_common.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -31,6 +32,8 @@
 namespace yg {
 
 namespace {
+
+using namespace yg::dev;
 
 constexpr int kM = 256;                 // channels
 constexpr int kM2 = 128;
@@ -44,132 +47,9 @@ constexpr int kVBufBytes = kPairsPerBatch * kRegionBytes;         // 69632
 constexpr int kSmemBytes = 2 * kInStageBytes + 2 * kVBufBytes + 128;
 // mbarrier slots (8 B each) after the data buffers
 constexpr int kMbInFull = 0;     // [2]    TMA transaction barriers, one per input stage
-constexpr int kMbInFree = 2;     // [2]    8 FIR warps have drained the stage          (pipeline v2)
-constexpr int kMbVFull = 4;      // [2][4] 8 FIR warps have written regions 4g..4g+3   (pipeline v2)
-constexpr int kMbVFree = 12;     // [2]    8 FFT warps have drained the buffer         (pipeline v2)
-
-// named barriers (0 is __syncthreads)
-constexpr int kBarFull0 = 1, kBarEmpty0 = 3, kBarFir = 5;
-
-__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-// explicit shared-space accesses on 32-bit shared addresses (keeps them LDS/STS, never generic LD/ST)
-__device__ __forceinline__ float2 lds64(uint32_t a)
-{
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ float4 lds128(uint32_t a)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, float4 v)
-{
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-// packed f32x2 helpers: a float2 holds the (even frame, odd frame) values of one real quantity
-__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
-__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float2 fnma2(float2 a, float2 b, float2 c) { return __ffma2_rn(make_float2(-a.x, -a.y), b, c); }
-
-struct C2 { float2 re, im; };           // one complex value for each frame of the pair
-
-__device__ __forceinline__ C2 cadd(C2 a, C2 b) { return {add2(a.re, b.re), add2(a.im, b.im)}; }
-__device__ __forceinline__ C2 csub(C2 a, C2 b) { return {sub2(a.re, b.re), sub2(a.im, b.im)}; }
-// a + j b,  a - j b
-__device__ __forceinline__ C2 caddj(C2 a, C2 b) { return {sub2(a.re, b.im), add2(a.im, b.re)}; }
-__device__ __forceinline__ C2 csubj(C2 a, C2 b) { return {add2(a.re, b.im), sub2(a.im, b.re)}; }
-// a * (wr + j wi), scalar twiddle shared by both frames
-__device__ __forceinline__ C2 cmulw(C2 a, float wr, float wi)
-{
-    C2 r;
-    r.re = fnma2(a.im, f2(wi), mul2(a.re, f2(wr)));
-    r.im = fma2(a.im, f2(wr), mul2(a.re, f2(wi)));
-    return r;
-}
-
-// 4-point backward DFT (W4 = +j), in place
-__device__ __forceinline__ void dft4(C2& a0, C2& a1, C2& a2, C2& a3)
-{
-    const C2 s0 = cadd(a0, a2), d0 = csub(a0, a2);
-    const C2 s1 = cadd(a1, a3), d1 = csub(a1, a3);
-    a0 = cadd(s0, s1);
-    a2 = csub(s0, s1);
-    a1 = caddj(d0, d1);
-    a3 = csubj(d0, d1);
-}
-
-// 16-point backward DFT: out[k] = sum_n v[n] e^{+j 2 pi n k / 16}.
-// Input natural order; output left in v[] at index (k1 + 4 k2) -> stored at v[4 k1 + k2]
-// (digit-reversed base 4); callers index through dr4().
-__device__ __forceinline__ constexpr int dr4(int k) { return ((k & 3) << 2) | (k >> 2); }
-
-__device__ __forceinline__ void dft16(C2 (&v)[16])
-{
-    constexpr float c1 = 0.92387953251128674f;      // cos(pi/8)
-    constexpr float s1 = 0.38268343236508977f;      // sin(pi/8)
-    constexpr float r2 = 0.70710678118654752f;      // sqrt(1/2)
-    // stage 1: for each b, DFT4 over a of v[4a + b]  -> T_b[k1] stored at v[4 k1 + b]
-#pragma unroll
-    for (int b = 0; b < 4; b++) dft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
-    // twiddle T_b[k1] *= W16^{b k1}
-    v[4 * 1 + 1] = cmulw(v[4 * 1 + 1], c1, s1);      // e = 1
-    v[4 * 2 + 1] = cmulw(v[4 * 2 + 1], r2, r2);      // e = 2
-    v[4 * 3 + 1] = cmulw(v[4 * 3 + 1], s1, c1);      // e = 3
-    v[4 * 1 + 2] = cmulw(v[4 * 1 + 2], r2, r2);      // e = 2
-    {                                                // e = 4 : * j
-        const C2 t = v[4 * 2 + 2];
-        v[4 * 2 + 2] = {make_float2(-t.im.x, -t.im.y), t.re};
-    }
-    v[4 * 3 + 2] = cmulw(v[4 * 3 + 2], -r2, r2);     // e = 6
-    v[4 * 1 + 3] = cmulw(v[4 * 1 + 3], s1, c1);      // e = 3
-    v[4 * 2 + 3] = cmulw(v[4 * 2 + 3], -r2, r2);     // e = 6
-    v[4 * 3 + 3] = cmulw(v[4 * 3 + 3], -c1, -s1);    // e = 9
-    // stage 2: for each k1, DFT4 over b of v[4 k1 + b] -> X[k1 + 4 k2] stored at v[4 k1 + k2]
-#pragma unroll
-    for (int k1 = 0; k1 < 4; k1++) dft4(v[4 * k1 + 0], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
-}
+constexpr int kMbInFree = 2;     // [2]    8 FIR warps have drained the stage          
+constexpr int kMbVFull = 4;      // [2][4] 8 FIR warps have written regions 4g..4g+3   
+constexpr int kMbVFree = 12;     // [2]    8 FFT warps have drained the buffer         
 
 struct FastParams {
     const float2* hist;       // Hlen samples preceding x[0] of the call
@@ -182,7 +62,7 @@ struct FastParams {
     const float2* twid;       // [16][16] e^{+j 2 pi n2 k1 / 256}
 };
 
-template <int kTaps, bool kV2>          // kTaps = 2m + 1; kV2: mbarrier pipeline with staggered FFT start
+template <int kTaps>                     // 2m + 1
 __device__ __forceinline__ void fir_role(const FastParams& p, uint32_t smem, uint32_t mbar,
                                          long long batch_begin, long long batch_end)
 {
@@ -242,15 +122,9 @@ __device__ __forceinline__ void fir_role(const FastParams& p, uint32_t smem, uin
         const uint32_t in = in_stage0 + st * kInStageBytes + pos * 8;
 #pragma unroll
         for (int r = 0; r < kPairsPerBatch; r++) W[16 * PAR + r] = lds64(in + r * (kM * 8));
-        if (kV2) {
-            __syncwarp();
-            if ((j & 31) == 0) mbar_arrive(mbar + 8 * (kMbInFree + st));  // this warp has drained the stage
-            if (lb >= 2) mbar_wait(mbar + 8 * (kMbVFree + PAR), (uint32_t)(((lb >> 1) - 1) & 1));
-        } else {
-            bar_sync(kBarFir, kFirThreads);                             // everyone has drained this stage
-            if (j == 0 && batch + 2 < batch_end) issue_load(batch + 2);
-            if (lb >= 2) bar_sync(kBarEmpty0 + PAR, kThreads);          // FFT role released V[PAR]
-        }
+        __syncwarp();
+        if ((j & 31) == 0) mbar_arrive(mbar + 8 * (kMbInFree + st));      // this warp has drained the stage
+        if (lb >= 2) mbar_wait(mbar + 8 * (kMbVFree + PAR), (uint32_t)(((lb >> 1) - 1) & 1));   // FFT role released V[PAR]
         const uint32_t vout = vbuf0 + PAR * kVBufBytes + j * 16;
 #pragma unroll
         for (int r = 0; r < kPairsPerBatch; r++) {
@@ -262,18 +136,14 @@ __device__ __forceinline__ void fir_role(const FastParams& p, uint32_t smem, uin
                 aim = fma2(T[i], f2(w.y), aim);
             }
             sts128(vout + r * kRegionBytes, make_float4(are.x, are.y, aim.x, aim.y));
-            if (kV2 && (r & 3) == 3) {
+            if ((r & 3) == 3) {                                         // regions 4g..4g+3 of this warp are written
                 __syncwarp();
                 if ((j & 31) == 0) mbar_arrive(mbar + 8 * (kMbVFull + 4 * PAR + (r >> 2)));
             }
         }
-        if (kV2) {
-            if (j == 0 && batch + 2 < batch_end) {
-                mbar_wait(mbar + 8 * (kMbInFree + st), (uint32_t)((lb >> 1) & 1));
-                issue_load(batch + 2);
-            }
-        } else {
-            bar_arrive(kBarFull0 + PAR, kThreads);
+        if (j == 0 && batch + 2 < batch_end) {                          // all 8 FIR warps drained this stage?
+            mbar_wait(mbar + 8 * (kMbInFree + st), (uint32_t)((lb >> 1) & 1));
+            issue_load(batch + 2);
         }
     };
 
@@ -283,7 +153,6 @@ __device__ __forceinline__ void fir_role(const FastParams& p, uint32_t smem, uin
     }
 }
 
-template <bool kV2>
 __device__ __forceinline__ void fft_role(const FastParams& p, uint32_t smem, uint32_t mbar, long long batch_begin, long long batch_end)
 {
     const int tid = threadIdx.x - kFirThreads;
@@ -303,8 +172,8 @@ __device__ __forceinline__ void fft_role(const FastParams& p, uint32_t smem, uin
         const int b = (int)((batch - batch_begin) & 1);
         const uint32_t region = vbuf0 + b * kVBufBytes + g * kRegionBytes;
         const long long pair = batch * kPairsPerBatch + g;
-        if (kV2) mbar_wait(mbar + 8 * (kMbVFull + 4 * b + (tid >> 6)), (uint32_t)(((batch - batch_begin) >> 1) & 1));
-        else bar_sync(kBarFull0 + b, kThreads);
+        // staggered start: wait only for the four regions this warp pair consumes
+        mbar_wait(mbar + 8 * (kMbVFull + 4 * b + (tid >> 6)), (uint32_t)(((batch - batch_begin) >> 1) & 1));
 
         C2 v[16];
         // pass 1: thread n2 = t gathers X[16 n1 + n2], n1 = 0..15
@@ -332,11 +201,7 @@ __device__ __forceinline__ void fft_role(const FastParams& p, uint32_t smem, uin
             v[n2].im = make_float2(q.z, q.w);
         }
         __syncwarp();
-        if (kV2) {
-            if ((tid & 31) == 0) mbar_arrive(mbar + 8 * (kMbVFree + b));
-        } else {
-            bar_arrive(kBarEmpty0 + b, kThreads);   // V[b] may be overwritten by the FIR role
-        }
+        if ((tid & 31) == 0) mbar_arrive(mbar + 8 * (kMbVFree + b));   // V[b] may be overwritten by the FIR role
         dft16(v);
         if (pair < p.n_pairs) {
             float2* ye = p.y + (p.f0 + 2 * pair) * (long long)kM + t;     // even frame of the pair
@@ -351,7 +216,7 @@ __device__ __forceinline__ void fft_role(const FastParams& p, uint32_t smem, uin
     }
 }
 
-template <int kTaps, bool kV2>
+template <int kTaps>
 __global__ void __launch_bounds__(kThreads, 1) k_firpfbch2_analysis_fused(const FastParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -374,23 +239,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_firpfbch2_analysis_fused(const 
     __syncthreads();
     if (batch_begin >= batch_end) return;
 
-    if (threadIdx.x < kFirThreads) fir_role<kTaps, kV2>(p, smem, mbar, batch_begin, batch_end);
-    else fft_role<kV2>(p, smem, mbar, batch_begin, batch_end);
+    if (threadIdx.x < kFirThreads) fir_role<kTaps>(p, smem, mbar, batch_begin, batch_end);
+    else fft_role(p, smem, mbar, batch_begin, batch_end);
 }
 
-template <int kTaps, bool kV2>
+template <int kTaps>
 int32_t launch_t(const Firpfbch2FastPlan& plan, const FastParams& p, cudaStream_t st)
 {
     static bool attr_done[64] = {};
     int dev = 0;
     YG_CUDA(cudaGetDevice(&dev));
     if (!attr_done[dev & 63]) {
-        YG_CUDA(cudaFuncSetAttribute(k_firpfbch2_analysis_fused<kTaps, kV2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        YG_CUDA(cudaFuncSetAttribute(k_firpfbch2_analysis_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_done[dev & 63] = true;
     }
     const long long n_batches = (p.n_pairs + kPairsPerBatch - 1) / kPairsPerBatch;
     const int grid = (int)std::min<long long>(plan.n_sm, n_batches);
-    k_firpfbch2_analysis_fused<kTaps, kV2><<<grid, kThreads, kSmemBytes, st>>>(p);
+    k_firpfbch2_analysis_fused<kTaps><<<grid, kThreads, kSmemBytes, st>>>(p);
     YG_CUDA(cudaGetLastError());
     return YG_OK;
 }
@@ -403,7 +268,7 @@ int32_t firpfbch2_fast_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const 
     p.M = M;
     p.m = m;
     if (M != (uint32_t)kM) return YG_OK;
-    if (m != 7) return YG_OK;                 // instantiated tap counts (2m+1): 15
+    if (m < 1 || m > 8) return YG_OK;         // instantiated tap counts 2m+1 = 3..17 (ring of 32 holds 16 + 2m)
     const int kTaps = 2 * (int)m + 1;
     int dev = 0;
     YG_CUDA(cudaGetDevice(&dev));
@@ -441,7 +306,6 @@ int32_t firpfbch2_fast_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const 
     YG_CUDA(cudaMalloc(&p.d_twid, tw.size() * sizeof(float2)));
     YG_CUDA(cudaMemcpy(p.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     p.min_frames = 64;
-    if (const char* v = getenv("YG_FAST_VARIANT")) p.variant = atoi(v);      // experiment knob
     p.supported = true;
     return YG_OK;
 }
@@ -467,7 +331,17 @@ int32_t firpfbch2_fast_launch(const Firpfbch2FastPlan& plan, const float2* hist,
     p.n_pairs = (long long)(n_frames / 2);
     p.taps = reinterpret_cast<const float2*>(plan.d_taps);
     p.twid = reinterpret_cast<const float2*>(plan.d_twid);
-    return plan.variant == 0 ? launch_t<15, false>(plan, p, st) : launch_t<15, true>(plan, p, st);
+    switch (plan.m) {
+        case 1: return launch_t<3>(plan, p, st);
+        case 2: return launch_t<5>(plan, p, st);
+        case 3: return launch_t<7>(plan, p, st);
+        case 4: return launch_t<9>(plan, p, st);
+        case 5: return launch_t<11>(plan, p, st);
+        case 6: return launch_t<13>(plan, p, st);
+        case 7: return launch_t<15>(plan, p, st);
+        case 8: return launch_t<17>(plan, p, st);
+        default: return fail(YG_EINTERNAL, "fused kernel not instantiated for m = %u", plan.m);
+    }
 }
 
 }  // namespace yg

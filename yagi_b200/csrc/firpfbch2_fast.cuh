@@ -10,7 +10,6 @@ struct Firpfbch2FastPlan {
     size_t min_frames = 0;        // below this the generic kernel is used
     void* d_taps = nullptr;       // kernel-specific tap layout (device)
     void* d_twid = nullptr;       // kernel-specific twiddle layout (device)
-    int variant = 1;             // 1 = mbarrier pipeline with staggered FFT start (default), 0 = named barriers
     int n_sm = 0;
 };
 
@@ -22,5 +21,11 @@ void firpfbch2_fast_release(Firpfbch2FastPlan& p);
 // even).  `x` points at the first sample of the call, `hist` holds the Hlen samples before it.
 int32_t firpfbch2_fast_launch(const Firpfbch2FastPlan& p, const float2* hist, long long Hlen, const float2* x,
                               float2* y, size_t f0, size_t n_frames, cudaStream_t st);
+
+// Fused synthesis (firpfbch2_synth_fast.cu).  `prefix` = the 32 input frames preceding x[0] of the
+// call; frames [f0, f0 + n_frames) of the call, f0 on even global parity, n_frames a multiple of 32.
+int32_t firpfbch2_synth_fast_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const float* h);
+int32_t firpfbch2_synth_fast_launch(const Firpfbch2FastPlan& p, const float2* prefix, const float2* x, float2* y,
+                                    size_t f0, size_t n_frames, cudaStream_t st);
 
 }  // namespace yg
