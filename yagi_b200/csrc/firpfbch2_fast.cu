@@ -141,8 +141,10 @@ __device__ __forceinline__ void fir_role(const FastParams& p, uint32_t smem, uin
                 if ((j & 31) == 0) mbar_arrive(mbar + 8 * (kMbVFull + 4 * PAR + (r >> 2)));
             }
         }
-        if (j == 0 && batch + 2 < batch_end) {                          // all 8 FIR warps drained this stage?
-            mbar_wait(mbar + 8 * (kMbInFree + st), (uint32_t)((lb >> 1) & 1));
+        // Prefetch batch+2 into the stage just drained.  Issuing a bulk copy stalls its thread for ~0.3 us
+        // (profiles/r01_tma_bench.log), so the eight FIR warps take turns instead of always taxing warp 0.
+        if ((j & 31) == 0 && (j >> 5) == (int)(lb & 7) && batch + 2 < batch_end) {
+            mbar_wait(mbar + 8 * (kMbInFree + st), (uint32_t)((lb >> 1) & 1));   // all 8 FIR warps drained this stage
             issue_load(batch + 2);
         }
     };

@@ -54,6 +54,10 @@ __device__ __forceinline__ float4 lds128(uint32_t a)
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
     return v;
 }
+__device__ __forceinline__ void sts64(uint32_t a, float2 v)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t a, float4 v)
 {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
