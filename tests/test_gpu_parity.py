@@ -416,3 +416,19 @@ def test_fused_round_trip_M256():
     assert_parity(y, yr, "round trip vs CPU path")
     D = 2 * M * m - M // 2 + 1
     assert np.abs(y[D:] - x[: N - D]).max() < 2e-3
+
+
+@pytest.mark.parametrize("h_len,S_,N", [(63, 3, 10000), (64, 2, 4096 + 17), (1, 4, 5000), (23, 1, 9000), (65, 2, 5000)])
+def test_firfilt_fast_kernel_edges(h_len, S_, N):
+    """Register-blocked firfilt kernel (h_len <= 64): ragged tile ends, history across calls, 1..64 taps;
+    h_len = 65 exercises the generic kernel at the same sizes."""
+    rng = np.random.default_rng(h_len * 7 + S_)
+    h = rng.standard_normal(h_len).astype(np.float32)
+    x = _rand_c(rng, S_ * N).reshape(S_, N)
+    q = yb.FirFilt.new(h, n_streams=S_)
+    q.set_scale(1.25)
+    cuts = [0, 4999, N]
+    y = np.concatenate([q.execute_block(np.ascontiguousarray(x[:, a:b])).reshape(S_, -1) for a, b in zip(cuts, cuts[1:])], axis=1)
+    ref = np.stack([po.firfilt_crcf(h, x[s], scale=1.25) for s in range(S_)])
+    scale = max(1.0, np.abs(ref).max())
+    assert_parity(y / scale, ref / scale, "firfilt h_len=%d" % h_len)

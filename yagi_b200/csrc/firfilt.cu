@@ -6,6 +6,13 @@
 
 using namespace yg;
 
+namespace yg {
+// firfilt_fast.cu
+bool firfilt_fast_supported(size_t h_len);
+int32_t firfilt_fast_launch(const float* h, size_t h_len, float scale, const float2* hist, long long Hlen, const float2* x,
+                            float2* y, long long n, long long n_streams, cudaStream_t st);
+}  // namespace yg
+
 struct yg_firfilt_crcf_s {
     size_t h_len = 0;
     uint32_t n_streams = 1;
@@ -101,14 +108,20 @@ int32_t execute_dev_impl(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf3
     if (n == 0) return YG_OK;
     const long long S = q->n_streams;
     const long long Hlen = (long long)q->state_len;
-    const long long tiles = ((long long)n + kOutPerThread - 1) / kOutPerThread;
-    const int grid = (int)std::min<long long>((tiles * S + 127) / 128, 148 * 32);
-    const size_t smem = (q->h_len + 2 * (kOutPerThread - 1)) * sizeof(float);
-    if (smem > 48 * 1024) return fail(YG_ECONFIG, "filter too long for this kernel (%zu taps)", q->h_len);
-    k_firfilt<<<grid, 128, smem, st>>>(q->d_h.p, (int)q->h_len, q->scale,
-                                       reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
-                                       reinterpret_cast<const float2*>(d_x), reinterpret_cast<float2*>(d_y),
-                                       (long long)n, S);
+    if (firfilt_fast_supported(q->h_len) && (long long)n * S >= 4096) {
+        // register-blocked FFMA2 kernel (taps as kernel parameters); generic kernel for long filters / tiny calls
+        YG_TRY(firfilt_fast_launch(q->h.data(), q->h_len, q->scale, reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
+                                   reinterpret_cast<const float2*>(d_x), reinterpret_cast<float2*>(d_y), (long long)n, S, st));
+    } else {
+        const long long tiles = ((long long)n + kOutPerThread - 1) / kOutPerThread;
+        const int grid = (int)std::min<long long>((tiles * S + 127) / 128, 148 * 32);
+        const size_t smem = (q->h_len + 2 * (kOutPerThread - 1)) * sizeof(float);
+        if (smem > 48 * 1024) return fail(YG_ECONFIG, "filter too long for this kernel (%zu taps)", q->h_len);
+        k_firfilt<<<grid, 128, smem, st>>>(q->d_h.p, (int)q->h_len, q->scale,
+                                           reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
+                                           reinterpret_cast<const float2*>(d_x), reinterpret_cast<float2*>(d_y),
+                                           (long long)n, S);
+    }
     YG_CUDA(cudaGetLastError());
     if (Hlen > 0) {
         const int nxt = q->cur ^ 1;
