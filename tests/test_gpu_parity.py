@@ -432,3 +432,22 @@ def test_firfilt_fast_kernel_edges(h_len, S_, N):
     ref = np.stack([po.firfilt_crcf(h, x[s], scale=1.25) for s in range(S_)])
     scale = max(1.0, np.abs(ref).max())
     assert_parity(y / scale, ref / scale, "firfilt h_len=%d" % h_len)
+
+
+@pytest.mark.parametrize("p,S_,Q", [(14, 9, 50), (14, 4, 16), (2, 5, 33), (16, 8, 100), (6, 13, 47)])
+def test_firpfbch_fused_analysis_M64(p, S_, Q):
+    """Fused critically sampled analyser (M=64): groups of four streams on the fused kernel, the
+    remainder on the generic one; ragged 16-frame batches; history carried across calls."""
+    M = 64
+    rng = np.random.default_rng(p * 100 + S_)
+    h = rng.standard_normal(M * p).astype(np.float32)
+    x = _rand_c(rng, S_ * Q * M).reshape(S_, Q * M)
+    q = yb.FirPfbCh.new(A, M, p, h, n_streams=S_)
+    cut = (Q // 2 + 3) * M
+    y = np.concatenate([q.execute_block(np.ascontiguousarray(x[:, :cut])).reshape(S_, -1),
+                        q.execute_block(np.ascontiguousarray(x[:, cut:])).reshape(S_, -1)], axis=1)
+    ref = np.stack([po.FirPfbCh.new(po.ANALYZER, M, p, h).execute_block(x[s]) for s in range(S_)])
+    scale = max(1.0, np.abs(ref).max())
+    assert_parity(y / scale, ref / scale, "fused firpfbch p=%d S=%d" % (p, S_))
+    per_stream = np.abs(y - ref).max(axis=1) / scale
+    assert per_stream.max() <= 1e-4, int(per_stream.argmax())

@@ -4,6 +4,7 @@
 //   analysis : V_q[b] = sum_n h[b+nM] s[qM + M-1 - b - nM];  X[M-1-b] = V_q[b];  y_q = DFT_forward(X)
 //   synthesis: U_q = IDFT_unnorm(X_q);  y[qM + i] = sum_n h[i+nM] U_{q-n}[i]
 #include "common.cuh"
+#include "firpfbch_fast.cuh"
 
 #include <algorithm>
 
@@ -24,6 +25,8 @@ struct yg_firpfbch_crcf_s {
     int cur = 0;
     DevBuf<yg_cf32> d_U;           // synthesiser scratch [stream][(p-1)+n][M]
     DevBuf<yg_cf32> d_stage_x, d_stage_y;
+    FirpfbchFastPlan fast;         // fused analysis kernel (M = 64)
+    int32_t last_path = 0;
 };
 
 namespace {
@@ -182,11 +185,25 @@ int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames
     const long long work = (long long)n_frames * S;
     const int grid = (int)std::min<long long>(work, 148 * 16);
     if (q->type == YG_ANALYZER) {
-        YG_TRY(set_smem((const void*)k_pfbch_analysis, smem));
-        k_pfbch_analysis<<<grid, block, smem, st>>>(q->d_h.p, q->d_tw.p,
-                                                    reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen, x, y, M,
-                                                    p, (long long)n_frames, S);
-        YG_CUDA(cudaGetLastError());
+        const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
+        long long s_fast = 0;
+        if (q->fast.supported && S >= 4 && n_frames >= 16) {
+            // groups of four streams go to the fused kernel, the remaining 0..3 streams to the generic one
+            s_fast = (S / 4) * 4;
+            YG_TRY(firpfbch_fast_launch(q->fast, hist, Hlen, x, y, (long long)n_frames, s_fast, st));
+            q->last_path = 2;
+        } else {
+            q->last_path = 1;
+        }
+        if (s_fast < S) {
+            const long long rest = S - s_fast;
+            const long long per = (long long)n_frames * M;
+            YG_TRY(set_smem((const void*)k_pfbch_analysis, smem));
+            const int g1 = (int)std::min<long long>((long long)n_frames * rest, 148 * 16);
+            k_pfbch_analysis<<<g1, block, smem, st>>>(q->d_h.p, q->d_tw.p, hist + s_fast * Hlen, Hlen, x + s_fast * per,
+                                                      y + s_fast * per, M, p, (long long)n_frames, rest);
+            YG_CUDA(cudaGetLastError());
+        }
         if (Hlen > 0) {
             const int nxt = q->cur ^ 1;
             const int g2 = (int)std::min<long long>((Hlen * S + 255) / 256, 148 * 8);
@@ -246,6 +263,7 @@ int32_t build(int32_t type, uint32_t M, uint32_t p, const float* h, size_t h_len
     TRYQ(q->d_tw.reserve(M));
     CUDAQ(cudaMemcpy(q->d_tw.p, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
     q->state_len = (size_t)(p - 1) * M;
+    TRYQ(firpfbch_fast_plan(q->fast, type, M, p, q->h.data()));
     for (int b = 0; b < 2; b++) {
         TRYQ(q->d_hist[b].reserve(std::max<size_t>(1, q->state_len * n_streams)));
         CUDAQ(cudaMemset(q->d_hist[b].p, 0, std::max<size_t>(1, q->state_len * n_streams) * sizeof(yg_cf32)));
@@ -304,6 +322,7 @@ int32_t yg_firpfbch_crcf_destroy(yg_firpfbch_crcf q)
     q->order.destroy();
     q->d_h.release(); q->d_tw.release(); q->d_hist[0].release(); q->d_hist[1].release(); q->d_U.release();
     q->d_stage_x.release(); q->d_stage_y.release();
+    firpfbch_fast_release(q->fast);
     if (q->stream) cudaStreamDestroy(q->stream);
     delete q;
     return YG_OK;

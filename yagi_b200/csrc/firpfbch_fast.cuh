@@ -1,0 +1,21 @@
+// firpfbch_fast.cuh -- interface of the fused firpfbch (critically sampled) analysis kernel (sm_100a).
+#pragma once
+#include "common.cuh"
+
+namespace yg {
+
+struct FirpfbchFastPlan {
+    bool supported = false;
+    uint32_t p = 0;
+    void* d_taps = nullptr;
+    void* d_twid = nullptr;
+    int n_sm = 0;
+};
+
+int32_t firpfbch_fast_plan(FirpfbchFastPlan& plan, int32_t type, uint32_t M, uint32_t p, const float* h);
+void firpfbch_fast_release(FirpfbchFastPlan& plan);
+// n_streams must be a multiple of 4; layouts as the generic kernel: x[stream][n_frames*64], hist[stream][Hlen]
+int32_t firpfbch_fast_launch(const FirpfbchFastPlan& plan, const float2* hist, long long Hlen, const float2* x, float2* y,
+                             long long n_frames, long long n_streams, cudaStream_t st);
+
+}  // namespace yg
