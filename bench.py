@@ -37,6 +37,9 @@ BYTES_PER_SAMPLE = 24.0            # 8 B read + 16 B written per
 METRIC = "firpfbch2 analysis Msps/GPU at M=256, % HBM roofline, 1/2/4/8 GPUs"
 UNIT = "Msps"
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+# dram__bytes_read.sum + dram__bytes_write.sum of one fused-kernel launch on this workload, from the
+# `ncu --set full` capture summarised in profiles/r01_ncu_analysis.txt (2.152 GB + 4.237 GB)
+NCU_TRAFFIC_BYTES_2P28 = 2.151935e9 + 4.236829e9
 
 
 def env_int(name, default):
@@ -315,7 +318,8 @@ def main():
             "config": workload_config(world, args.log2_samples),
             "per_gpu_msps": value / world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "firpfbch2 analysis (%s)" % ("fused" if path == 2 else "generic"),
+                         "traffic": NCU_TRAFFIC_BYTES_2P28 if (path == 2 and args.log2_samples == 28) else None,
+                         "traffic_source": "ncu --set full, profiles/r01_ncu_analysis.txt", "peak_source": peak_src, "kernel": "firpfbch2 analysis (%s)" % ("fused" if path == 2 else "generic"),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * N},
             "clocks": clocks,
             "gpu_launches": 2 * K,
