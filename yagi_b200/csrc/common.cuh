@@ -161,19 +161,41 @@ __device__ inline float2* block_dft(float2* X, float2* Y, uint32_t M, const floa
 {
     __syncthreads();
     if ((M & (M - 1)) == 0) {
-        // Stockham autosort radix-2
-        uint32_t l = M >> 1, s = 1;
+        // Stockham autosort: radix-4 passes, plus one radix-2 pass when log2(M) is odd
+        uint32_t l = M, s = 1;                       // remaining sub-transform length, stride
         float2* x = X;
         float2* y = Y;
-        for (; l >= 1; l >>= 1, s <<= 1) {
-            for (uint32_t idx = threadIdx.x; idx < (M >> 1); idx += blockDim.x) {
+        const float sgn = backward ? 1.0f : -1.0f;   // multiply by (sgn * j)
+        while (l >= 4) {
+            const uint32_t q = l >> 2;
+            for (uint32_t idx = threadIdx.x; idx < (M >> 2); idx += blockDim.x) {
                 const uint32_t j = idx / s, k = idx - j * s;
-                float2 w = __ldg(&tw[j * s]);
-                if (!backward) w.y = -w.y;
+                float2 w1 = __ldg(&tw[j * s]);
+                float2 w2 = __ldg(&tw[2 * j * s]);
+                float2 w3 = __ldg(&tw[3 * j * s]);
+                if (!backward) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
                 const float2 a = x[k + s * j];
-                const float2 b = x[k + s * (j + l)];
-                y[k + s * (2 * j)] = cadd(a, b);
-                y[k + s * (2 * j + 1)] = cmul(csub(a, b), w);
+                const float2 b = x[k + s * (j + q)];
+                const float2 c = x[k + s * (j + 2 * q)];
+                const float2 d = x[k + s * (j + 3 * q)];
+                const float2 apc = cadd(a, c), amc = csub(a, c);
+                const float2 bpd = cadd(b, d), bmd = csub(b, d);
+                const float2 jbmd = make_float2(-sgn * bmd.y, sgn * bmd.x);
+                y[k + s * (4 * j + 0)] = cadd(apc, bpd);
+                y[k + s * (4 * j + 1)] = cmul(cadd(amc, jbmd), w1);
+                y[k + s * (4 * j + 2)] = cmul(csub(apc, bpd), w2);
+                y[k + s * (4 * j + 3)] = cmul(csub(amc, jbmd), w3);
+            }
+            __syncthreads();
+            float2* t = x; x = y; y = t;
+            l = q;
+            s <<= 2;
+        }
+        if (l == 2) {
+            for (uint32_t k = threadIdx.x; k < s; k += blockDim.x) {
+                const float2 a = x[k], b = x[k + s];
+                y[k] = cadd(a, b);
+                y[k + s] = csub(a, b);
             }
             __syncthreads();
             float2* t = x; x = y; y = t;
