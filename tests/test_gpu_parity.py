@@ -451,3 +451,26 @@ def test_firpfbch_fused_analysis_M64(p, S_, Q):
     assert_parity(y / scale, ref / scale, "fused firpfbch p=%d S=%d" % (p, S_))
     per_stream = np.abs(y - ref).max(axis=1) / scale
     assert per_stream.max() <= 1e-4, int(per_stream.argmax())
+
+
+@pytest.mark.parametrize("m", [4, 2, 7])
+def test_large_M1024_two_stage_path(m):
+    """M=1024 analysis on the two-stage (FIR kernel + in-place FFT kernel) path (last_path == 3):
+    uneven call sizes, odd-parity starts, history from the previous call."""
+    M, K = 1024, 700
+    rng = np.random.default_rng(900 + m)
+    h = rng.standard_normal(2 * M * m).astype(np.float32)
+    x = _rand_c(rng, K * M // 2)
+    ref = _oracle_analysis(M, m, x, h=h).reshape(K, M)
+    q = yb.FirPfbCh2.new(A, M, m, h)
+    cuts = [0, 64, 129, 130, 331, K]
+    outs = []
+    for a, b in zip(cuts, cuts[1:]):
+        outs.append(q.execute_block(x[a * M // 2: b * M // 2]))
+        if b - a >= 64:
+            assert q.last_path() == 3, (a, b)
+    y = np.concatenate(outs).reshape(K, M)
+    scale = max(1.0, np.abs(ref).max())
+    assert_parity(y / scale, ref / scale, "large-M m=%d" % m)
+    per_frame = np.abs(y - ref).max(axis=1) / scale
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())

@@ -40,6 +40,7 @@ struct yg_firpfbch2_crcf_s {
     void next_events() { ev0 = ev0s[n_timed % kRing]; ev1 = ev1s[n_timed % kRing]; n_timed++; }
     Firpfbch2FastPlan fast;       // fused fast path (may be unsupported for this M/m)
     Firpfbch2FastPlan sfast;      // fused synthesis fast path
+    Firpfbch2FastPlan large;      // two-stage large-M analysis path (M = 1024)
 };
 
 namespace {
@@ -200,14 +201,17 @@ int32_t launch_analysis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames
     // left over (a leading odd-parity frame, a trailing single frame) and calls too small to
     // fill the machine go to the generic kernel.
     q->next_events();
-    if (q->fast.supported && n_frames >= q->fast.min_frames) {
+    const bool use_fused = q->fast.supported && n_frames >= q->fast.min_frames;
+    const bool use_large = q->large.supported && n_frames >= q->large.min_frames;
+    if (use_fused || use_large) {
         const size_t lead = (q->flag & 1) ? 1 : 0;
         const size_t body = (n_frames - lead) & ~(size_t)1;
         YG_CUDA(cudaEventRecord(q->ev0, st));
-        YG_TRY(firpfbch2_fast_launch(q->fast, hist, (long long)q->hist_len, x, y, lead, body, st));
+        if (use_fused) YG_TRY(firpfbch2_fast_launch(q->fast, hist, (long long)q->hist_len, x, y, lead, body, st));
+        else YG_TRY(firpfbch2_large_launch(q->large, hist, (long long)q->hist_len, x, y, lead, body, st));
         YG_CUDA(cudaEventRecord(q->ev1, st));
         q->timed = true;
-        q->last_path = 2;
+        q->last_path = use_fused ? 2 : 3;
         YG_TRY(launch_generic_analysis(q, hist, x, y, 0, lead, st));
         YG_TRY(launch_generic_analysis(q, hist, x, y, lead + body, n_frames, st));
         return YG_OK;
@@ -338,6 +342,7 @@ int32_t build(int32_t type, uint32_t M, uint32_t m, const float* h, size_t h_len
         CUDAQ(cudaMemset(q->d_hist[b].p, 0, q->hist_len * sizeof(yg_cf32)));
     }
     if (type == YG_ANALYZER) TRYQ(firpfbch2_fast_plan(q->fast, M, m, q->h.data()));
+    if (type == YG_ANALYZER) TRYQ(firpfbch2_large_plan(q->large, M, m, q->h.data()));
     else TRYQ(firpfbch2_synth_fast_plan(q->sfast, M, m, q->h.data()));
 #undef TRYQ
 #undef CUDAQ
@@ -396,6 +401,7 @@ int32_t yg_firpfbch2_crcf_destroy(yg_firpfbch2_crcf q)
     q->order.destroy();
     firpfbch2_fast_release(q->fast);
     firpfbch2_fast_release(q->sfast);
+    firpfbch2_fast_release(q->large);
     q->pipe.destroy();
     q->d_h.release(); q->d_tw.release(); q->d_hist[0].release(); q->d_hist[1].release(); q->d_U.release();
     for (int i = 0; i < yg_firpfbch2_crcf_s::kRing; i++) {

@@ -1,0 +1,284 @@
+// firpfbch2_large.cu -- firpfbch2 analysis for M = 1024 (BASELINE config #4), m = 1..8, sm_100a.
+//
+// One SM cannot hold a 1024-branch window set plus the transform, so large M runs as TWO kernels per
+// chunk of frames, chained through the 126 MB L2 instead of HBM:
+//   stage A (k_large_fir):  branch FIRs with register-resident windows (the firpfbch2_fast.cu FIR role,
+//                           256 branches per CTA), writes the rolled, 1/M-scaled branch sums V_k straight
+//                           into the output frames;
+//   stage B (k_large_fft):  in-place 1024-point backward DFT of every frame, one warp per frame,
+//                           32 x 32 with a radix-32 in registers and one XOR-swizzled shared exchange.
+// The host walks the call in chunks whose output (8 KB per frame) fits in L2, so V is written and read
+// back in cache and HBM sees the algorithmic 24 B per input sample.
+#include "firpfbch2_fast.cuh"
+#include "fused_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <type_traits>
+#include <vector>
+
+namespace yg {
+
+namespace {
+
+using namespace yg::dev;
+
+constexpr int kM = 1024;
+constexpr int kM2 = 512;
+constexpr int kFirThreads = 256;                 // branches per CTA
+constexpr int kBlocksPerFrame = kM / kFirThreads;
+constexpr int kPairsPerBatch = 16;
+
+struct LargeParams {
+    const float2* hist;       // Hlen samples preceding x[0] of the call
+    long long Hlen;
+    const float2* x;
+    float2* y;
+    long long f0;             // first frame handled (even global parity)
+    long long pair_begin, pair_end;      // frame pairs of this launch, relative to f0
+    int slabs;                // CTAs along the pair axis
+    const float2* taps;       // [1024][2m+1] (even, odd) tap pairs, 1/M folded in
+    const float2* twid;       // [1024] e^{+j 2 pi k / 1024}
+};
+
+// ------------------------------------------------------------------ stage A: branch FIRs
+template <int kTaps>
+__global__ void __launch_bounds__(kFirThreads, 2) k_large_fir(const LargeParams p)
+{
+    constexpr int kHist = kTaps - 1;
+    const int j = blockIdx.y * kFirThreads + threadIdx.x;               // branch
+    const int pos = (j < kM2) ? (kM2 - 1 - j) : (kM + kM2 - 1 - j);       // sample slot inside an M-sample block
+    const long long n_pairs = p.pair_end - p.pair_begin;
+    const long long n_batches = (n_pairs + kPairsPerBatch - 1) / kPairsPerBatch;
+    const long long b0 = (n_batches * blockIdx.x) / p.slabs, b1 = (n_batches * (blockIdx.x + 1)) / p.slabs;
+    if (b0 >= b1) return;
+
+    float2 T[kTaps];
+#pragma unroll
+    for (int i = 0; i < kTaps; i++) T[i] = __ldg(&p.taps[j * kTaps + i]);
+
+    const long long call_off = p.f0 * kM2;                               // sample index of pair 0 relative to x[0]
+    auto sample = [&](long long q) {                                     // u_j[q], q relative to f0
+        const long long ta = q * kM + pos + call_off;
+        if (ta >= 0) return __ldg(&p.x[ta]);
+        if (p.Hlen + ta >= 0) return __ldg(&p.hist[p.Hlen + ta]);
+        return make_float2(0.f, 0.f);
+    };
+
+    float2 W[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) W[i] = make_float2(0.f, 0.f);
+    const long long q_first = p.pair_begin + b0 * kPairsPerBatch;
+#pragma unroll
+    for (int i = 1; i <= kHist; i++) W[(32 - i) & 31] = sample(q_first - i);
+
+    float2 Pf[kPairsPerBatch];                                           // next batch, in flight
+#pragma unroll
+    for (int r = 0; r < kPairsPerBatch; r++) Pf[r] = (q_first + r < p.pair_end) ? sample(q_first + r) : make_float2(0.f, 0.f);
+
+    auto do_batch = [&](auto par_tag, long long batch) {
+        constexpr int PAR = decltype(par_tag)::value;
+        const long long q0 = p.pair_begin + batch * kPairsPerBatch;
+#pragma unroll
+        for (int r = 0; r < kPairsPerBatch; r++) W[16 * PAR + r] = Pf[r];
+        if (batch + 1 < b1) {
+#pragma unroll
+            for (int r = 0; r < kPairsPerBatch; r++) {
+                const long long q = q0 + kPairsPerBatch + r;
+                Pf[r] = (q < p.pair_end) ? sample(q) : make_float2(0.f, 0.f);
+            }
+        }
+        float2* yb = p.y + (p.f0 + 2 * q0) * (long long)kM + j;
+#pragma unroll
+        for (int r = 0; r < kPairsPerBatch; r++) {
+            float2 are = make_float2(0.f, 0.f), aim = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = kTaps - 1; i >= 0; i--) {
+                const float2 w = W[(16 * PAR + r - i) & 31];
+                are = fma2(T[i], f2(w.x), are);
+                aim = fma2(T[i], f2(w.y), aim);
+            }
+            if (q0 + r < p.pair_end) {
+                yb[(long long)(2 * r) * kM] = make_float2(are.x, aim.x);          // even frame, stays in L2 for stage B
+                yb[(long long)(2 * r + 1) * kM] = make_float2(are.y, aim.y);      // odd frame
+            }
+        }
+    };
+    for (long long batch = b0; batch < b1; batch += 2) {
+        do_batch(std::integral_constant<int, 0>{}, batch);
+        if (batch + 1 < b1) do_batch(std::integral_constant<int, 1>{}, batch + 1);
+    }
+}
+
+// ------------------------------------------------------------------ stage B: 1024-point DFT per frame
+// Single-frame (re, im) arithmetic: a complex add is one packed FADD2.
+__device__ __forceinline__ float2 xadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 xsub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 xaddj(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }   // a + j b
+__device__ __forceinline__ float2 xsubj(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }   // a - j b
+__device__ __forceinline__ float2 xmul(float2 a, float wr, float wi)
+{
+    return make_float2(fmaf(a.x, wr, -a.y * wi), fmaf(a.x, wi, a.y * wr));
+}
+__device__ __forceinline__ void xdft4(float2& a0, float2& a1, float2& a2, float2& a3)
+{
+    const float2 s0 = xadd(a0, a2), d0 = xsub(a0, a2), s1 = xadd(a1, a3), d1 = xsub(a1, a3);
+    a0 = xadd(s0, s1); a2 = xsub(s0, s1); a1 = xaddj(d0, d1); a3 = xsubj(d0, d1);
+}
+// 16-point backward DFT of v[o], v[o+1], ...; X[k] left at v[o + dr4(k)]
+template <int O>
+__device__ __forceinline__ void xdft16(float2 (&v)[32])
+{
+    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
+#pragma unroll
+    for (int b = 0; b < 4; b++) xdft4(v[O + b], v[O + 4 + b], v[O + 8 + b], v[O + 12 + b]);
+    v[O + 5] = xmul(v[O + 5], c1, s1);   v[O + 9] = xmul(v[O + 9], r2, r2);    v[O + 13] = xmul(v[O + 13], s1, c1);
+    v[O + 6] = xmul(v[O + 6], r2, r2);   v[O + 10] = make_float2(-v[O + 10].y, v[O + 10].x);   v[O + 14] = xmul(v[O + 14], -r2, r2);
+    v[O + 7] = xmul(v[O + 7], s1, c1);   v[O + 11] = xmul(v[O + 11], -r2, r2); v[O + 15] = xmul(v[O + 15], -c1, -s1);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) xdft4(v[O + 4 * k1], v[O + 4 * k1 + 1], v[O + 4 * k1 + 2], v[O + 4 * k1 + 3]);
+}
+// 32-point backward DFT: X[k] left at v[(k & 1) * 16 + dr4(k >> 1)]
+__device__ __forceinline__ constexpr int dr32(int k) { return ((k & 1) << 4) | dr4(k >> 1); }
+__device__ __forceinline__ void xdft32(float2 (&v)[32], const float2* w32 /* e^{+j 2 pi b / 32}, b < 16, shared */)
+{
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+        const float2 s = xadd(v[b], v[16 + b]), d = xsub(v[b], v[16 + b]);
+        v[b] = s;
+        if (b == 0) v[16] = d;
+        else if (b == 8) v[24] = make_float2(-d.y, d.x);                // W32^8 = j
+        else { const float2 w = w32[b]; v[16 + b] = xmul(d, w.x, w.y); }
+    }
+    xdft16<0>(v);
+    xdft16<16>(v);
+}
+
+constexpr int kFftWarps = 8;                     // frames per CTA
+constexpr int kFftSmem = kFftWarps * 1024 * 8 + 16 * 8;
+
+__global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft(float2* __restrict__ y, long long n_frames,
+                                                                 const float2* __restrict__ twid)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* w32 = reinterpret_cast<float2*>(smem_raw + kFftWarps * 1024 * 8);
+    if (threadIdx.x < 16) w32[threadIdx.x] = __ldg(&twid[threadIdx.x * 32]);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const uint32_t tile = smem_u32(smem_raw) + wrp * 8192;               // 32 x 32 exchange tile of 8-byte units
+    for (long long f = (long long)blockIdx.x * kFftWarps + wrp; f < n_frames; f += (long long)gridDim.x * kFftWarps) {
+        float2* fr = y + f * kM;
+        float2 v[32];
+        // pass 1: lane n2 gathers X[32 n1 + n2] (256-byte coalesced rows, L2 hits: written by stage A)
+#pragma unroll
+        for (int n1 = 0; n1 < 32; n1++) v[n1] = fr[32 * n1 + lane];
+        xdft32(v, w32);
+        // twiddle by W1024^{n2 k1}, write row n2 of the swizzled tile
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) {
+            float2 z = v[dr32(k1)];
+            if (k1 > 0) { const float2 w = __ldg(&twid[lane * k1]); z = xmul(z, w.x, w.y); }
+            sts64(tile + (((lane << 5) | (k1 ^ lane)) << 3), z);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) v[n2] = lds64(tile + (((n2 << 5) | (lane ^ n2)) << 3));
+        __syncwarp();
+        xdft32(v, w32);
+#pragma unroll
+        for (int k2 = 0; k2 < 32; k2++) __stcs(fr + lane + 32 * k2, v[dr32(k2)]);
+    }
+}
+
+template <int kTaps>
+int32_t launch_fir(const LargeParams& p, cudaStream_t st)
+{
+    dim3 grid((unsigned)p.slabs, kBlocksPerFrame);
+    k_large_fir<kTaps><<<grid, kFirThreads, 0, st>>>(p);
+    YG_CUDA(cudaGetLastError());
+    return YG_OK;
+}
+
+}  // namespace
+
+int32_t firpfbch2_large_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, const float* h)
+{
+    plan.supported = false;
+    plan.M = M;
+    plan.m = m;
+    if (M != (uint32_t)kM || m < 1 || m > 8) return YG_OK;
+    int dev = 0;
+    YG_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    YG_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return YG_OK;
+    plan.n_sm = prop.multiProcessorCount;
+    const int kTaps = 2 * (int)m + 1, P = 2 * (int)m;
+    std::vector<float2> taps((size_t)kM * kTaps);
+    const float s = 1.0f / (float)kM;
+    for (int j = 0; j < kM; j++)
+        for (int i = 0; i < kTaps; i++) {
+            float te = 0.f, to = 0.f;
+            if (j < kM2) {
+                if (i < P) { te = h[j + i * kM]; to = h[j + kM2 + i * kM]; }
+            } else {
+                if (i >= 1) te = h[j + (i - 1) * kM];
+                if (i < P) to = h[j - kM2 + i * kM];
+            }
+            taps[(size_t)j * kTaps + i] = make_float2(te * s, to * s);
+        }
+    std::vector<float2> tw(kM);
+    for (int k = 0; k < kM; k++) {
+        const double a = 2.0 * M_PI * (double)k / (double)kM;
+        tw[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float2)));
+    YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(cudaMalloc(&plan.d_twid, tw.size() * sizeof(float2)));
+    YG_CUDA(cudaMemcpy(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(cudaFuncSetAttribute(k_large_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
+    plan.min_frames = 64;
+    plan.supported = true;
+    return YG_OK;
+}
+
+int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist, long long Hlen, const float2* x, float2* y,
+                               size_t f0, size_t n_frames, cudaStream_t st)
+{
+    if (!plan.supported) return fail(YG_EINTERNAL, "large-M path not available for this geometry");
+    if (n_frames == 0) return YG_OK;
+    if (n_frames & 1) return fail(YG_EINTERNAL, "large-M path needs an even number of frames");
+    const long long n_pairs = (long long)(n_frames / 2);
+    // chunk so that a chunk's output (8 KB per frame) stays resident in L2 between the two stages
+    const long long chunk_pairs = std::max<long long>(64, ((long long)96 << 20) / (2 * kM * 8));   // 96 MB of output per chunk (swept 16..96 MB)
+    for (long long q = 0; q < n_pairs; q += chunk_pairs) {
+        LargeParams p;
+        p.hist = hist; p.Hlen = Hlen; p.x = x; p.y = y;
+        p.f0 = (long long)f0;
+        p.pair_begin = q;
+        p.pair_end = std::min(n_pairs, q + chunk_pairs);
+        const long long batches = (p.pair_end - p.pair_begin + kPairsPerBatch - 1) / kPairsPerBatch;
+        p.slabs = (int)std::min<long long>(batches, (long long)plan.n_sm * 2 / kBlocksPerFrame * 2);
+        p.taps = reinterpret_cast<const float2*>(plan.d_taps);
+        p.twid = reinterpret_cast<const float2*>(plan.d_twid);
+        switch (plan.m) {
+            case 1: YG_TRY(launch_fir<3>(p, st)); break;
+            case 2: YG_TRY(launch_fir<5>(p, st)); break;
+            case 3: YG_TRY(launch_fir<7>(p, st)); break;
+            case 4: YG_TRY(launch_fir<9>(p, st)); break;
+            case 5: YG_TRY(launch_fir<11>(p, st)); break;
+            case 6: YG_TRY(launch_fir<13>(p, st)); break;
+            case 7: YG_TRY(launch_fir<15>(p, st)); break;
+            case 8: YG_TRY(launch_fir<17>(p, st)); break;
+            default: return fail(YG_EINTERNAL, "large-M path not instantiated for m = %u", plan.m);
+        }
+        const long long nf = 2 * (p.pair_end - p.pair_begin);
+        const int grid = (int)std::min<long long>((nf + kFftWarps - 1) / kFftWarps, (long long)plan.n_sm * 2);
+        k_large_fft<<<grid, kFftWarps * 32, kFftSmem, st>>>(y + ((long long)f0 + 2 * p.pair_begin) * kM, nf,
+                                                            reinterpret_cast<const float2*>(plan.d_twid));
+        YG_CUDA(cudaGetLastError());
+    }
+    return YG_OK;
+}
+
+}  // namespace yg
