@@ -474,3 +474,25 @@ def test_large_M1024_two_stage_path(m):
     assert_parity(y / scale, ref / scale, "large-M m=%d" % m)
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+
+
+@pytest.mark.parametrize("m", [4, 2, 7])
+def test_large_M1024_two_stage_synthesis(m):
+    """M=1024 synthesis on the two-stage (IFFT kernel into an L2 scratch + overlap-add kernel) path."""
+    M, K = 1024, 500
+    rng = np.random.default_rng(950 + m)
+    h = rng.standard_normal(2 * M * m).astype(np.float32)
+    X = _rand_c(rng, K * M)
+    ref = po.FirPfbCh2.new(po.SYNTHESIZER, M, m, h).execute_block(X).reshape(K, M // 2)
+    q = yb.FirPfbCh2.new(S, M, m, h)
+    cuts = [0, 96, 225, 226, K]
+    outs = []
+    for a, b in zip(cuts, cuts[1:]):
+        outs.append(q.execute_block(X[a * M: b * M]))
+        if b - a >= 97:
+            assert q.last_path() == 3, (a, b)
+    y = np.concatenate(outs).reshape(K, M // 2)
+    scale = max(1.0, np.abs(ref).max())
+    assert_parity(y / scale, ref / scale, "large-M synthesis m=%d" % m)
+    per_frame = np.abs(y - ref).max(axis=1) / scale
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())

@@ -41,6 +41,8 @@ struct yg_firpfbch2_crcf_s {
     Firpfbch2FastPlan fast;       // fused fast path (may be unsupported for this M/m)
     Firpfbch2FastPlan sfast;      // fused synthesis fast path
     Firpfbch2FastPlan large;      // two-stage large-M analysis path (M = 1024)
+    Firpfbch2FastPlan slarge;     // two-stage large-M synthesis path (M = 1024)
+    DevBuf<yg_cf32> d_Uc;         // its L2-sized U scratch
 };
 
 namespace {
@@ -259,12 +261,16 @@ int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frame
     // output ranges, so their order does not matter.
     const size_t lead = (q->flag & 1) ? 1 : 0;
     const size_t body = (n_frames > lead) ? ((n_frames - lead) / 32) * 32 : 0;
-    if (q->sfast.supported && body >= q->sfast.min_frames) {
+    const bool use_fused = q->sfast.supported && body >= q->sfast.min_frames;
+    const bool use_large = q->slarge.supported && body >= q->slarge.min_frames;
+    if (use_fused || use_large) {
+        if (use_large) YG_TRY(q->d_Uc.reserve((size_t)firpfbch2_large_synth_scratch_frames() * q->M));
         YG_CUDA(cudaEventRecord(q->ev0, st));
-        YG_TRY(firpfbch2_synth_fast_launch(q->sfast, hist, x, y, lead, body, st));
+        if (use_fused) YG_TRY(firpfbch2_synth_fast_launch(q->sfast, hist, x, y, lead, body, st));
+        else YG_TRY(firpfbch2_large_synth_launch(q->slarge, hist, x, y, reinterpret_cast<float2*>(q->d_Uc.p), lead, body, st));
         YG_CUDA(cudaEventRecord(q->ev1, st));
         q->timed = true;
-        q->last_path = 2;
+        q->last_path = use_fused ? 2 : 3;
         YG_TRY(launch_generic_synthesis(q, hist, x, y, 0, lead, st));
         YG_TRY(launch_generic_synthesis(q, hist, x, y, lead + body, n_frames, st));
         return YG_OK;
@@ -343,7 +349,10 @@ int32_t build(int32_t type, uint32_t M, uint32_t m, const float* h, size_t h_len
     }
     if (type == YG_ANALYZER) TRYQ(firpfbch2_fast_plan(q->fast, M, m, q->h.data()));
     if (type == YG_ANALYZER) TRYQ(firpfbch2_large_plan(q->large, M, m, q->h.data()));
-    else TRYQ(firpfbch2_synth_fast_plan(q->sfast, M, m, q->h.data()));
+    else {
+        TRYQ(firpfbch2_synth_fast_plan(q->sfast, M, m, q->h.data()));
+        TRYQ(firpfbch2_large_synth_plan(q->slarge, M, m, q->h.data()));
+    }
 #undef TRYQ
 #undef CUDAQ
     *out = q;
@@ -402,6 +411,8 @@ int32_t yg_firpfbch2_crcf_destroy(yg_firpfbch2_crcf q)
     firpfbch2_fast_release(q->fast);
     firpfbch2_fast_release(q->sfast);
     firpfbch2_fast_release(q->large);
+    firpfbch2_fast_release(q->slarge);
+    q->d_Uc.release();
     q->pipe.destroy();
     q->d_h.release(); q->d_tw.release(); q->d_hist[0].release(); q->d_hist[1].release(); q->d_U.release();
     for (int i = 0; i < yg_firpfbch2_crcf_s::kRing; i++) {

@@ -33,4 +33,10 @@ int32_t firpfbch2_large_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const
 int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& p, const float2* hist, long long Hlen, const float2* x, float2* y,
                                size_t f0, size_t n_frames, cudaStream_t st);
 
+// Large-M synthesis (M = 1024): IFFT stage into an L2-resident scratch + overlap-add stage, per chunk.
+int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const float* h);
+long long firpfbch2_large_synth_scratch_frames();
+int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& p, const float2* prefix, const float2* x, float2* y,
+                                     float2* scratch, size_t f0, size_t n_frames, cudaStream_t st);
+
 }  // namespace yg

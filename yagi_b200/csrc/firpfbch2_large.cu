@@ -157,8 +157,12 @@ __device__ __forceinline__ void xdft32(float2 (&v)[32], const float2* w32 /* e^{
 constexpr int kFftWarps = 8;                     // frames per CTA
 constexpr int kFftSmem = kFftWarps * 1024 * 8 + 16 * 8;
 
-__global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft(float2* __restrict__ y, long long n_frames,
-                                                                 const float2* __restrict__ twid)
+// Frame f of the launch is read from the virtual stream (prefix ++ x) at index v0 + f (negative indices
+// live in the 32-frame prefix) and written to dst frame f.  The analysis path calls it in place
+// (x == dst, v0 == 0); the synthesis path transforms input frames into the U scratch.
+__global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft(const float2* prefix, const float2* x, long long v0,
+                                                                 float2* dst, long long n_frames,
+                                                                 const float2* __restrict__ twid, int streaming_store)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* w32 = reinterpret_cast<float2*>(smem_raw + kFftWarps * 1024 * 8);
@@ -167,11 +171,13 @@ __global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft(float2* __restr
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const uint32_t tile = smem_u32(smem_raw) + wrp * 8192;               // 32 x 32 exchange tile of 8-byte units
     for (long long f = (long long)blockIdx.x * kFftWarps + wrp; f < n_frames; f += (long long)gridDim.x * kFftWarps) {
-        float2* fr = y + f * kM;
+        const long long vi = v0 + f;
+        const float2* src = (vi < 0) ? prefix + (32 + vi) * kM : x + vi * kM;
+        float2* fr = dst + f * kM;
         float2 v[32];
         // pass 1: lane n2 gathers X[32 n1 + n2] (256-byte coalesced rows, L2 hits: written by stage A)
 #pragma unroll
-        for (int n1 = 0; n1 < 32; n1++) v[n1] = fr[32 * n1 + lane];
+        for (int n1 = 0; n1 < 32; n1++) v[n1] = src[32 * n1 + lane];
         xdft32(v, w32);
         // twiddle by W1024^{n2 k1}, write row n2 of the swizzled tile
 #pragma unroll
@@ -186,8 +192,101 @@ __global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft(float2* __restr
         __syncwarp();
         xdft32(v, w32);
 #pragma unroll
-        for (int k2 = 0; k2 < 32; k2++) __stcs(fr + lane + 32 * k2, v[dr32(k2)]);
+        if (streaming_store) {
+#pragma unroll
+            for (int k2 = 0; k2 < 32; k2++) __stcs(fr + lane + 32 * k2, v[dr32(k2)]);
+        } else {                                                         // keep U in L2 for the overlap-add stage
+#pragma unroll
+            for (int k2 = 0; k2 < 32; k2++) fr[lane + 32 * k2] = v[dr32(k2)];
+        }
     }
+}
+
+
+// ------------------------------------------------------------------ synthesis stage C: weighted overlap-add
+// Thread j owns COLUMN j of U (the firpfbch2_synth_fast.cu FIR role with global loads): 32-entry register
+// ring over the last 4m frames, values prefetched 8 steps (16 frames) ahead through a 16-entry register
+// queue.  Columns j < M/2 emit on even frames, columns j >= M/2 on odd frames (ring kept one frame behind).
+struct WolaParams {
+    const float2* U;          // U[0] = virtual frame c0 - 32 (the warm-up period), frames of kM columns
+    float2* y;                // output sample 0 of frame c0
+    long long n_frames;       // frames of this chunk (multiple of 32); U holds n_frames + 32 frames
+    int slabs;
+    const float* taps;        // [1024][4m]  0.5 * h[(j & 511) + l * 512]
+};
+
+template <int kTaps>
+__global__ void __launch_bounds__(kFirThreads, 2) k_large_wola(const WolaParams p)
+{
+    const int j = blockIdx.y * kFirThreads + threadIdx.x;
+    const bool hi = j >= kM2;
+    const int i = j & (kM2 - 1);
+    const long long n_periods = p.n_frames / 32;
+    const long long r0 = (n_periods * blockIdx.x) / p.slabs, r1 = (n_periods * (blockIdx.x + 1)) / p.slabs;
+    if (r0 >= r1) return;
+
+    float T[kTaps];
+#pragma unroll
+    for (int l = 0; l < kTaps; l++) T[l] = __ldg(&p.taps[j * kTaps + l]);
+    float2 W[32];
+#pragma unroll
+    for (int s = 0; s < 32; s++) W[s] = make_float2(0.f, 0.f);
+
+    // slab-local frame index g: g = 0 is the first warm-up frame = U frame (r0 * 32); real output frames are
+    // g in [32, 32 + n_out).  Lower half: slot k holds frame k; upper half: slot k holds frame k - 1.
+    const int n_out = (int)(r1 - r0) * 32;
+    const float2* Ub = p.U + (r0 * 32) * (long long)kM + j;
+    float2* yb = p.y + (r0 * 32) * (long long)kM2 + i;
+    const int o = hi ? -1 : 0;
+    const int g_last = 32 + n_out - 1;                                   // last U frame that exists for this slab
+    auto fetch = [&](int g) {                                            // frame g of the slab (clamped; g = -1 only feeds suppressed outputs)
+        g = g < 0 ? 0 : (g > g_last ? g_last : g);
+        return __ldg(Ub + (long long)g * kM);
+    };
+    float2 Pf[16];                                                       // steps s .. s+7 in flight
+#pragma unroll
+    for (int s = 0; s < 8; s++) { Pf[2 * s] = fetch(2 * s + o); Pf[2 * s + 1] = fetch(2 * s + 1 + o); }
+
+    const int n_steps = (32 + n_out) / 2;
+    for (int s0 = 0; s0 < n_steps; s0 += 16) {
+#pragma unroll
+        for (int ss = 0; ss < 16; ss++) {
+            const int s = s0 + ss;
+            W[(2 * ss) & 31] = Pf[(2 * ss) & 15];
+            W[(2 * ss + 1) & 31] = Pf[(2 * ss + 1) & 15];
+            Pf[(2 * ss) & 15] = fetch(2 * (s + 8) + o);
+            Pf[(2 * ss + 1) & 15] = fetch(2 * (s + 8) + 1 + o);
+            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int l = kTaps - 1; l >= 0; l--) {
+                const float2 w = W[(2 * ss - l) & 31];
+                if (l & 1) a1 = fma2(w, f2(T[l]), a1);
+                else a0 = fma2(w, f2(T[l]), a0);
+            }
+            const int rel = 2 * s + o - 32;                              // output frame relative to the slab's first real frame
+            if ((unsigned)rel < (unsigned)n_out) __stcs(yb + (long long)rel * kM2, add2(a0, a1));
+        }
+    }
+    if (hi) {                                                            // last odd frame of the slab: window ends at slot 0
+        W[0] = Pf[0];
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int l = kTaps - 1; l >= 0; l--) {
+            const float2 w = W[(0 - l) & 31];
+            if (l & 1) a1 = fma2(w, f2(T[l]), a1);
+            else a0 = fma2(w, f2(T[l]), a0);
+        }
+        __stcs(yb + (long long)(n_out - 1) * kM2, add2(a0, a1));
+    }
+}
+
+template <int kTaps>
+int32_t launch_wola(const WolaParams& p, cudaStream_t st)
+{
+    dim3 grid((unsigned)p.slabs, kBlocksPerFrame);
+    k_large_wola<kTaps><<<grid, kFirThreads, 0, st>>>(p);
+    YG_CUDA(cudaGetLastError());
+    return YG_OK;
 }
 
 template <int kTaps>
@@ -274,9 +373,79 @@ int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist
         }
         const long long nf = 2 * (p.pair_end - p.pair_begin);
         const int grid = (int)std::min<long long>((nf + kFftWarps - 1) / kFftWarps, (long long)plan.n_sm * 2);
-        k_large_fft<<<grid, kFftWarps * 32, kFftSmem, st>>>(y + ((long long)f0 + 2 * p.pair_begin) * kM, nf,
-                                                            reinterpret_cast<const float2*>(plan.d_twid));
+        float2* yc = y + ((long long)f0 + 2 * p.pair_begin) * kM;
+        k_large_fft<<<grid, kFftWarps * 32, kFftSmem, st>>>(nullptr, yc, 0, yc, nf, reinterpret_cast<const float2*>(plan.d_twid), 1);
         YG_CUDA(cudaGetLastError());
+    }
+    return YG_OK;
+}
+
+int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, const float* h)
+{
+    plan.supported = false;
+    plan.M = M;
+    plan.m = m;
+    if (M != (uint32_t)kM || m < 1 || m > 7) return YG_OK;
+    int dev = 0;
+    YG_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    YG_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return YG_OK;
+    plan.n_sm = prop.multiProcessorCount;
+    const int kTaps = 4 * (int)m;
+    std::vector<float> taps((size_t)kM * kTaps);
+    for (int j = 0; j < kM; j++)
+        for (int l = 0; l < kTaps; l++) taps[(size_t)j * kTaps + l] = 0.5f * h[(j & (kM2 - 1)) + l * kM2];
+    std::vector<float2> tw(kM);
+    for (int k = 0; k < kM; k++) {
+        const double a = 2.0 * M_PI * (double)k / (double)kM;
+        tw[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float)));
+    YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    YG_CUDA(cudaMalloc(&plan.d_twid, tw.size() * sizeof(float2)));
+    YG_CUDA(cudaMemcpy(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(cudaFuncSetAttribute(k_large_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
+    plan.min_frames = 64;
+    plan.supported = true;
+    return YG_OK;
+}
+
+// `prefix` = the 32 input frames preceding x[0]; frames [f0, f0 + n_frames) of the call, f0 on even global
+// parity, n_frames a multiple of 32; `scratch` holds at least (chunk + 32) * 1024 samples (see *_scratch_frames).
+long long firpfbch2_large_synth_scratch_frames() { return ((long long)96 << 20) / (kM * 8) + 32; }
+
+int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& plan, const float2* prefix, const float2* x, float2* y,
+                                     float2* scratch, size_t f0, size_t n_frames, cudaStream_t st)
+{
+    if (!plan.supported) return fail(YG_EINTERNAL, "large-M synthesis path not available for this geometry");
+    if (n_frames == 0) return YG_OK;
+    if (n_frames % 32) return fail(YG_EINTERNAL, "large-M synthesis path needs a multiple of 32 frames");
+    const long long chunk = firpfbch2_large_synth_scratch_frames() - 32;     // multiple of 32
+    for (long long c0 = 0; c0 < (long long)n_frames; c0 += chunk) {
+        const long long nf = std::min<long long>(chunk, (long long)n_frames - c0);
+        // stage B': U[g] = IDFT_unnorm(X[f0 + c0 - 32 + g]), g = 0 .. nf + 31 (the 1/2 scale lives in the taps)
+        const long long nfft = nf + 32;
+        const int gridf = (int)std::min<long long>((nfft + kFftWarps - 1) / kFftWarps, (long long)plan.n_sm * 2);
+        k_large_fft<<<gridf, kFftWarps * 32, kFftSmem, st>>>(prefix, x, (long long)f0 + c0 - 32, scratch, nfft,
+                                                             reinterpret_cast<const float2*>(plan.d_twid), 0);
+        YG_CUDA(cudaGetLastError());
+        WolaParams p;
+        p.U = scratch;
+        p.y = y + ((long long)f0 + c0) * kM2;
+        p.n_frames = nf;
+        p.slabs = (int)std::min<long long>(nf / 32, (long long)plan.n_sm * 2 / kBlocksPerFrame * 2);
+        p.taps = reinterpret_cast<const float*>(plan.d_taps);
+        switch (plan.m) {
+            case 1: YG_TRY(launch_wola<4>(p, st)); break;
+            case 2: YG_TRY(launch_wola<8>(p, st)); break;
+            case 3: YG_TRY(launch_wola<12>(p, st)); break;
+            case 4: YG_TRY(launch_wola<16>(p, st)); break;
+            case 5: YG_TRY(launch_wola<20>(p, st)); break;
+            case 6: YG_TRY(launch_wola<24>(p, st)); break;
+            case 7: YG_TRY(launch_wola<28>(p, st)); break;
+            default: return fail(YG_EINTERNAL, "large-M synthesis path not instantiated for m = %u", plan.m);
+        }
     }
     return YG_OK;
 }
