@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--gather", action="store_true", help="also time the optional NCCL all-gather of the outputs (off the hot path)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -281,6 +282,24 @@ def main():
     ms_per_step = ms_total_max / K
     value = (N * world) / (ms_per_step * 1e-3) / 1e6
 
+    # ---- optional: NCCL all-gather of a slice of the per-channel outputs (off the hot path, timed separately)
+    gather = None
+    if args.gather and world > 1:
+        from yagi_b200.gather import all_gather_frames
+        gf = min(n_frames, 1 << 15)                       # 64 MiB per rank
+        yl = y[: gf * M]
+        all_gather_frames(yl, [gf] * world, M)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            all_gather_frames(yl, [gf] * world, M)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = g0.elapsed_time(g1) / 5
+        gather = {"frames_per_rank": gf, "bytes_per_rank": gf * M * 8, "ms": gms,
+                  "busbw_GBps": gf * M * 8 * (world - 1) / (gms * 1e-3) / 1e9, "backend": "nccl all_gather_into_tensor"}
+
     # ---- e2e: host pinned buffers through the host-pointer C-ABI call
     e2e = None
     if not args.no_e2e:
@@ -327,6 +346,8 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if gather is not None:
+            line["output_gather"] = gather
         if not args.no_cpu and world == 1:
             threads = cpu_threads()
             npt = 1 << 22

@@ -47,8 +47,14 @@ def _worker(rank, world, port, M, m, n_frames, q):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)                 # the max-over-ranks reduction bench.py uses
     parts = [None] * world
     dist.all_gather_object(parts, (sh.frame_begin, y))
+    # the optional output gather (yagi_b200.gather) over the same process group
+    from yagi_b200.gather import all_gather_frames, channel_major
+    shards = firpfbch2_time_shards(n_frames, M, m, world)
+    g = all_gather_frames(torch.from_numpy(y), [s.n_frames for s in shards], M)
+    assert tuple(g.shape) == (n_frames, M)
+    assert tuple(channel_major(g).shape) == (M, n_frames)
     if rank == 0:
-        q.put((t.item(), parts))
+        q.put((t.item(), parts, g.numpy().reshape(-1)))
     dist.destroy_process_group()
 
 
@@ -65,7 +71,7 @@ def test_time_sharded_analysis_equals_single_pass(M, m, n_frames):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, M, m, n_frames, q)) for r in range(2)]
     for p in procs:
         p.start()
-    tmax, parts = q.get(timeout=120)
+    tmax, parts, gathered = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -75,3 +81,4 @@ def test_time_sharded_analysis_equals_single_pass(M, m, n_frames):
     x = stimulus.noise_plus_tones(0, n_frames * M // 2, M)
     whole = po.FirPfbCh2.new_kaiser(po.ANALYZER, M, m, 60.0).execute_block(x)
     np.testing.assert_allclose(y, whole, atol=2e-6)
+    np.testing.assert_array_equal(gathered, y)

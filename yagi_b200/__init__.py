@@ -8,10 +8,11 @@ from ._buffers import PinnedArray
 from .error import (ConfigError, InternalError, ModeError, NoConvergenceError, RangeError, ValueError_, YagiError)
 from .filter import FirFilt, fir_design_kaiser
 from .multichannel import ANALYZER, SYNTHESIZER, FirPfbCh, FirPfbCh2, FirPfbChType
+from .gather import all_gather_frames, channel_major
 from .sharding import TimeShard, firpfbch2_time_shards, stream_shards
 
 __all__ = [
     "ANALYZER", "SYNTHESIZER", "FirPfbChType", "FirPfbCh2", "FirPfbCh", "FirFilt", "fir_design_kaiser",
-    "PinnedArray", "TimeShard", "firpfbch2_time_shards", "stream_shards",
+    "PinnedArray", "TimeShard", "firpfbch2_time_shards", "stream_shards", "all_gather_frames", "channel_major",
     "YagiError", "InternalError", "ConfigError", "ValueError_", "RangeError", "ModeError", "NoConvergenceError",
 ]
