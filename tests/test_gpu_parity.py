@@ -496,3 +496,30 @@ def test_large_M1024_two_stage_synthesis(m):
     assert_parity(y / scale, ref / scale, "large-M synthesis m=%d" % m)
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+
+
+def test_host_pointer_pipeline_multi_chunk():
+    """Host-pointer entry point across several 32 MiB chunks (3-stream H2D / kernel / D2H pipeline):
+    state must carry across chunk boundaries exactly as across calls."""
+    M, m = 256, 7
+    N = (1 << 23) + 5 * (M // 2)                   # 2 full chunks + a ragged tail, odd frame count
+    x = stimulus.noise_plus_tones(0, N, M)
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    y = q.execute_block(x)
+    ref = _oracle_analysis(M, m, x)
+    assert_parity(y, ref, "host pipeline, 3 chunks")
+    # pinned buffers give the same result
+    hx, hy = yb.PinnedArray(N), yb.PinnedArray(2 * N)
+    hx.array[:] = x
+    q.reset()
+    q.execute_block(hx.array, out=hy.array)
+    np.testing.assert_array_equal(hy.array, y)
+    hx.close(); hy.close()
+    # and the synthesiser's host path (chunks of whole 32-frame rounds)
+    K = 40001                                      # > 2 chunks of 16384 frames, odd count
+    X = _rand_c(np.random.default_rng(5), K * M)
+    qs = yb.FirPfbCh2.new_kaiser(S, M, m, 60.0)
+    ys = qs.execute_block(X)
+    refs = po.FirPfbCh2.new_kaiser(po.SYNTHESIZER, M, m, 60.0).execute_block(X)
+    sc = max(1.0, np.abs(refs).max())
+    assert_parity(ys / sc, refs / sc, "host pipeline synthesis")
