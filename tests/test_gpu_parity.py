@@ -434,21 +434,23 @@ def test_firfilt_fast_kernel_edges(h_len, S_, N):
     assert_parity(y / scale, ref / scale, "firfilt h_len=%d" % h_len)
 
 
-@pytest.mark.parametrize("p,S_,Q", [(14, 9, 50), (14, 4, 16), (2, 5, 33), (16, 8, 100), (6, 13, 47)])
-def test_firpfbch_fused_analysis_M64(p, S_, Q):
-    """Fused critically sampled analyser (M=64): groups of four streams on the fused kernel, the
-    remainder on the generic one; ragged 16-frame batches; history carried across calls."""
+@pytest.mark.parametrize("type_,otype", [(A, po.ANALYZER), (S, po.SYNTHESIZER)])
+@pytest.mark.parametrize("p,S_,Q", [(14, 9, 50), (14, 4, 16), (2, 5, 33), (16, 8, 100), (6, 13, 47), (14, 600, 40)])
+def test_firpfbch_fused_M64(p, S_, Q, type_, otype):
+    """Fused critically sampled channelizers (M=64, analysis and synthesis): groups of four streams on the
+    fused kernel, the remainder on the generic one; ragged 16-frame batches; history carried across calls;
+    more stream groups than SMs (slabs that start mid-stream)."""
     M = 64
     rng = np.random.default_rng(p * 100 + S_)
     h = rng.standard_normal(M * p).astype(np.float32)
     x = _rand_c(rng, S_ * Q * M).reshape(S_, Q * M)
-    q = yb.FirPfbCh.new(A, M, p, h, n_streams=S_)
+    q = yb.FirPfbCh.new(type_, M, p, h, n_streams=S_)
     cut = (Q // 2 + 3) * M
     y = np.concatenate([q.execute_block(np.ascontiguousarray(x[:, :cut])).reshape(S_, -1),
                         q.execute_block(np.ascontiguousarray(x[:, cut:])).reshape(S_, -1)], axis=1)
-    ref = np.stack([po.FirPfbCh.new(po.ANALYZER, M, p, h).execute_block(x[s]) for s in range(S_)])
+    ref = np.stack([po.FirPfbCh.new(otype, M, p, h).execute_block(x[s]) for s in range(S_)])
     scale = max(1.0, np.abs(ref).max())
-    assert_parity(y / scale, ref / scale, "fused firpfbch p=%d S=%d" % (p, S_))
+    assert_parity(y / scale, ref / scale, "fused firpfbch type=%d p=%d S=%d" % (int(type_), p, S_))
     per_stream = np.abs(y - ref).max(axis=1) / scale
     assert per_stream.max() <= 1e-4, int(per_stream.argmax())
 

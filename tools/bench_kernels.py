@@ -84,6 +84,10 @@ def main():
         q = yb.FirPfbCh.new_kaiser(yb.ANALYZER, M, m, 60.0, n_streams=S)
         ms = timed(lambda: q.execute_block(x, n // M, out=y), steps=5)
         report("firpfbch analysis M=64 m=7, 512 streams x 2^18", ms, 16.0 * S * n, S * n, "samples_in")
+        qs = yb.FirPfbCh.new_kaiser(yb.SYNTHESIZER, M, m, 60.0, n_streams=S)
+        ms = timed(lambda: qs.execute_block(x, n // M, out=y), steps=5)
+        report("firpfbch synthesis M=64 m=7, 512 streams x 2^18", ms, 16.0 * S * n, S * n, "samples_out")
+        del qs
         del x, y, q
     if "firfilt" in which:
         S, n = 1024, 1 << 18                    # config #2 geometry at a quarter of the length

@@ -20,7 +20,7 @@ struct yg_firpfbch_crcf_s {
     std::vector<float> h;
     DevBuf<float> d_h;
     DevBuf<float2> d_tw;
-    size_t state_len = 0;          // per stream: (p-1)*M entries (input samples | IFFT frames)
+    size_t state_len = 0;          // per stream: entries of INPUT history kept on the device
     DevBuf<yg_cf32> d_hist[2];
     int cur = 0;
     DevBuf<yg_cf32> d_U;           // synthesiser scratch [stream][(p-1)+n][M]
@@ -76,44 +76,27 @@ __global__ void k_pfbch_update_hist(float2* __restrict__ hist_new, const float2*
     }
 }
 
-// U layout: [stream][(p-1) + n_frames][M]; this kernel fills frames (p-1).. from x and the first p-1 from hist
-__global__ void k_pfbch_synth_ifft(const float2* __restrict__ tw, const float2* __restrict__ x, float2* __restrict__ U,
+// U layout: [stream][(p-1) + n_frames][M].  U frame g of a stream is the IDFT of virtual input frame g - (p-1):
+// negative virtual frames are the tail of the stream's input history (hist holds hist_frames frames per stream).
+__global__ void k_pfbch_synth_ifft(const float2* __restrict__ tw, const float2* __restrict__ hist, long long hist_frames,
+                                   const float2* __restrict__ x, float2* __restrict__ U,
                                    uint32_t M, uint32_t p, long long n_frames, long long n_streams)
 {
     extern __shared__ float2 sm[];
     float2* X = sm;
     float2* Y = sm + M;
-    const long long total = n_frames * n_streams;
+    const long long per = n_frames + p - 1;
+    const long long total = per * n_streams;
     for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-        const long long s = w / n_frames, q = w - s * n_frames;
-        const float2* xs = x + (s * n_frames + q) * (long long)M;
+        const long long s = w / per, g = w - s * per;
+        const long long v = g - (long long)(p - 1);
+        const float2* xs = (v >= 0) ? x + (s * n_frames + v) * (long long)M
+                                    : hist + (s * hist_frames + hist_frames + v) * (long long)M;
         for (uint32_t c = threadIdx.x; c < M; c += blockDim.x) X[c] = __ldg(&xs[c]);
         const float2* r = block_dft(X, Y, M, tw, 1);
-        float2* us = U + (s * (n_frames + p - 1) + (p - 1) + q) * (long long)M;
+        float2* us = U + (s * per + g) * (long long)M;
         for (uint32_t c = threadIdx.x; c < M; c += blockDim.x) us[c] = r[c];
         __syncthreads();
-    }
-}
-
-__global__ void k_pfbch_copy_hist_to_U(const float2* __restrict__ hist, float2* __restrict__ U, long long Hlen,
-                                       long long frames_total_M, long long n_streams)
-{
-    const long long total = Hlen * n_streams;
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
-         g += (long long)gridDim.x * blockDim.x) {
-        const long long s = g / Hlen, i = g - s * Hlen;
-        U[s * frames_total_M + i] = hist[g];
-    }
-}
-
-__global__ void k_pfbch_copy_U_to_hist(float2* __restrict__ hist, const float2* __restrict__ U, long long Hlen,
-                                       long long frames_total_M, long long n_streams)
-{
-    const long long total = Hlen * n_streams;
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
-         g += (long long)gridDim.x * blockDim.x) {
-        const long long s = g / Hlen, i = g - s * Hlen;
-        hist[g] = U[s * frames_total_M + (frames_total_M - Hlen) + i];
     }
 }
 
@@ -182,8 +165,6 @@ int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames
     float2* y = reinterpret_cast<float2*>(d_y);
     const size_t smem = 2 * (size_t)M * sizeof(float2);
     const int block = (int)std::min<uint32_t>(256, (M + 31) / 32 * 32);
-    const long long work = (long long)n_frames * S;
-    const int grid = (int)std::min<long long>(work, 148 * 16);
     if (q->type == YG_ANALYZER) {
         const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
         long long s_fast = 0;
@@ -204,36 +185,43 @@ int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames
                                                       y + s_fast * per, M, p, (long long)n_frames, rest);
             YG_CUDA(cudaGetLastError());
         }
-        if (Hlen > 0) {
-            const int nxt = q->cur ^ 1;
-            const int g2 = (int)std::min<long long>((Hlen * S + 255) / 256, 148 * 8);
-            k_pfbch_update_hist<<<g2, 256, 0, st>>>(reinterpret_cast<float2*>(q->d_hist[nxt].p),
-                                                    reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen, x,
-                                                    (long long)n_frames * M, S);
-            YG_CUDA(cudaGetLastError());
-            q->cur = nxt;
-        }
     } else {
-        const long long ftm = (long long)(n_frames + p - 1) * M;
-        YG_TRY(q->d_U.reserve((size_t)ftm * S));
-        float2* U = reinterpret_cast<float2*>(q->d_U.p);
-        float2* hist = reinterpret_cast<float2*>(q->d_hist[q->cur].p);
-        const int g2 = (int)std::min<long long>((Hlen * S + 255) / 256 + 1, 148 * 8);
-        if (Hlen > 0) {
-            k_pfbch_copy_hist_to_U<<<g2, 256, 0, st>>>(hist, U, Hlen, ftm, S);
+        const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
+        const long long hist_frames = Hlen / M;
+        long long s_fast = 0;
+        if (q->fast.supported && S >= 4 && n_frames >= 16) {
+            s_fast = (S / 4) * 4;
+            YG_TRY(firpfbch_fast_synth_launch(q->fast, hist, hist_frames, x, y, (long long)n_frames, s_fast, st));
+            q->last_path = 2;
+        } else {
+            q->last_path = 1;
+        }
+        if (s_fast < S) {
+            const long long rest = S - s_fast;
+            const long long per = (long long)n_frames * M;
+            const long long ftm = (long long)(n_frames + p - 1) * M;
+            YG_TRY(q->d_U.reserve((size_t)ftm * rest));
+            float2* U = reinterpret_cast<float2*>(q->d_U.p);
+            YG_TRY(set_smem((const void*)k_pfbch_synth_ifft, smem));
+            const int g1 = (int)std::min<long long>((long long)(n_frames + p - 1) * rest, 148 * 16);
+            k_pfbch_synth_ifft<<<g1, block, smem, st>>>(q->d_tw.p, hist + s_fast * Hlen, hist_frames, x + s_fast * per, U, M, p,
+                                                        (long long)n_frames, rest);
+            YG_CUDA(cudaGetLastError());
+            const long long total = per * rest;
+            const int g3 = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+            k_pfbch_synth_fir<<<g3, 256, 0, st>>>(q->d_h.p, U, y + s_fast * per, M, p, (long long)n_frames, rest);
             YG_CUDA(cudaGetLastError());
         }
-        YG_TRY(set_smem((const void*)k_pfbch_synth_ifft, smem));
-        k_pfbch_synth_ifft<<<grid, block, smem, st>>>(q->d_tw.p, x, U, M, p, (long long)n_frames, S);
+    }
+    // both types keep the tail of their INPUT stream as state
+    if (Hlen > 0) {
+        const int nxt = q->cur ^ 1;
+        const int g2 = (int)std::min<long long>((Hlen * S + 255) / 256, 148 * 8);
+        k_pfbch_update_hist<<<g2, 256, 0, st>>>(reinterpret_cast<float2*>(q->d_hist[nxt].p),
+                                                reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen, x,
+                                                (long long)n_frames * M, S);
         YG_CUDA(cudaGetLastError());
-        const long long total = (long long)n_frames * M * S;
-        const int g3 = (int)std::min<long long>((total + 255) / 256, 148 * 32);
-        k_pfbch_synth_fir<<<g3, 256, 0, st>>>(q->d_h.p, U, y, M, p, (long long)n_frames, S);
-        YG_CUDA(cudaGetLastError());
-        if (Hlen > 0) {
-            k_pfbch_copy_U_to_hist<<<g2, 256, 0, st>>>(hist, U, Hlen, ftm, S);
-            YG_CUDA(cudaGetLastError());
-        }
+        q->cur = nxt;
     }
     return YG_OK;
 }
@@ -262,7 +250,8 @@ int32_t build(int32_t type, uint32_t M, uint32_t p, const float* h, size_t h_len
     make_twiddles(M, tw);
     TRYQ(q->d_tw.reserve(M));
     CUDAQ(cudaMemcpy(q->d_tw.p, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
-    q->state_len = (size_t)(p - 1) * M;
+    // analyser: the last p-1 input frames; synthesiser: at least 16 (one warm-up batch of the fused kernel)
+    q->state_len = (type == YG_ANALYZER) ? (size_t)(p - 1) * M : (size_t)std::max<uint32_t>(p - 1, 16) * M;
     TRYQ(firpfbch_fast_plan(q->fast, type, M, p, q->h.data()));
     for (int b = 0; b < 2; b++) {
         TRYQ(q->d_hist[b].reserve(std::max<size_t>(1, q->state_len * n_streams)));

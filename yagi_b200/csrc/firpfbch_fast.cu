@@ -277,13 +277,238 @@ int32_t launch_t(const FirpfbchFastPlan& plan, const PfbParams& p, cudaStream_t 
     return YG_OK;
 }
 
+// =================================================================== synthesis
+//   U_q = IDFT_unnorm(X_q);   y[qM + i] = sum_n h[i + nM] U_{q-n}[i]            
+// Roles swapped: TMA -> FFT role (8 threads per frame pair, backward DFT, U written to smem) -> FIR role
+// (thread (stream slot, column i): 32-entry register ring of the column's U values, one output per frame).
+// U is never materialised in HBM, so every stream segment starts with a WARM-UP batch: the 16 frames before
+// it are transformed again with the outputs suppressed (frames before the call come from the 16-frame input
+// history kept per stream).  The four stream slots are independent pipelines with their own mbarriers.
+constexpr int kSMbInFull = 0;     // [2][4]     TMA transaction barrier per stage and slot
+constexpr int kSMbInFree = 8;     // [2][4]     the 2 FFT warps of the slot drained the stage
+constexpr int kSMbUFull = 16;     // [2][4][2]  FFT warp (slot, half) wrote U frames 8h..8h+7
+constexpr int kSMbUFree = 32;     // [2][4]     the 2 FIR warps of the slot drained the buffer
+constexpr int kSynSmemBytes = 2 * kInStageBytes + 2 * kXBufBytes + 40 * 8 + 64;
+
+struct PfbSynParams {
+    const float2* hist;       // [n_streams][hist_frames * 64] input history, oldest first
+    long long hist_frames;    // >= 16
+    const float2* x;          // [n_streams][n_frames * 64]
+    float2* y;                // [n_streams][n_frames * 64]
+    long long n_frames;
+    int n_groups;
+    int batches_per_group;
+    const float* taps;        // [64][p]  h[i + 64 n]
+    const float2* twid;       // [8][8]   e^{+j 2 pi n2 k1 / 64}
+};
+
+// The sequence of work items of a CTA, walked identically by every role: real batches L0..L1-1 of the
+// linearised (group, batch) space, each stream segment preceded by one warm-up item (batch k-1, suppressed).
+struct Walk {
+    int L, L1, nbg, group, k, it;
+    bool warm;
+    __device__ Walk(int L0, int L1_, int nbg_) : L(L0), L1(L1_), nbg(nbg_), group(L0 / nbg_), k(L0 - (L0 / nbg_) * nbg_), it(0), warm(true) {}
+    __device__ bool done() const { return L >= L1; }
+    __device__ int batch() const { return warm ? k - 1 : k; }          // -1: the 16 history frames
+    __device__ void next()
+    {
+        it++;
+        if (warm) { warm = false; return; }
+        L++;
+        if (++k == nbg) { k = 0; group++; warm = true; }
+    }
+};
+
+template <int kTaps>
+__device__ __forceinline__ void syn_fir_role(const PfbSynParams& p, uint32_t smem, uint32_t mbar, int L0, int L1)
+{
+    const int j = threadIdx.x;
+    const int slot = j >> 6, col = j & 63;
+    float T[kTaps];
+#pragma unroll
+    for (int n = 0; n < kTaps; n++) T[n] = __ldg(&p.taps[col * kTaps + n]);
+    float2 W[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) W[i] = make_float2(0.f, 0.f);
+    const uint32_t ub0 = smem + 2 * kInStageBytes + slot * kXStreamBytes + col * 8;
+    const long long stream_len = p.n_frames * kM;
+
+    Walk w(L0, L1, p.batches_per_group);
+    auto do_item = [&](auto par_tag) {
+        constexpr int PAR = decltype(par_tag)::value;
+        const uint32_t ph = (uint32_t)((w.it >> 1) & 1);
+        const uint32_t ub = ub0 + PAR * kXBufBytes;
+        const long long q0 = (long long)w.batch() * kBatch;
+        float2* ys = p.y + (long long)(w.group * kSlots + slot) * stream_len + q0 * kM + col;
+        const bool emit = !w.warm;
+#pragma unroll
+        for (int r = 0; r < kBatch; r++) {
+            if ((r & 7) == 0) mbar_wait(mbar + 8 * (kSMbUFull + 8 * PAR + 2 * slot + (r >> 3)), ph);
+            W[16 * PAR + r] = lds64(ub + r * kRowBytes);
+            if (r == kBatch - 1) {
+                __syncwarp();
+                if ((j & 31) == 0) mbar_arrive(mbar + 8 * (kSMbUFree + 4 * PAR + slot));
+            }
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int n = kTaps - 1; n >= 0; n--) acc = fma2(W[(16 * PAR + r - n) & 31], f2(T[n]), acc);
+            if (emit && q0 + r < p.n_frames) __stcs(ys + r * kM, acc);
+        }
+        w.next();
+    };
+    while (!w.done()) {
+        do_item(std::integral_constant<int, 0>{});
+        if (!w.done()) do_item(std::integral_constant<int, 1>{});
+    }
+}
+
+__device__ __forceinline__ void syn_fft_role(const PfbSynParams& p, uint32_t smem, uint32_t mbar, int L0, int L1)
+{
+    const int tid = threadIdx.x - kFirThreads;
+    const int wv = tid >> 5;
+    const int slot = wv >> 1, half = wv & 1;
+    const int pr = half * 4 + ((tid >> 3) & 3);   // frame pair inside the batch
+    const int t = tid & 7;
+    const bool issuer = (tid & 63) == 0;          // first lane of the slot's first FFT warp
+    const uint32_t in0 = smem + slot * kInStreamBytes;
+    const uint32_t ub0 = smem + 2 * kInStageBytes + slot * kXStreamBytes + (2 * pr) * kRowBytes;
+    const long long stream_len = p.n_frames * kM;
+
+    float twr[8], twi[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+        const float2 tw = __ldg(&p.twid[t * 8 + kk]);
+        twr[kk] = tw.x;
+        twi[kk] = tw.y;
+    }
+
+    auto issue = [&](const Walk& it_w) {           // the slot's 16 frames of this item: one bulk copy
+        const int st = it_w.it & 1;
+        const long long s = (long long)it_w.group * kSlots + slot;
+        const int kb = it_w.batch();
+        const float2* src;
+        uint32_t bytes = kBatch * kM * 8;
+        if (kb < 0) src = p.hist + (s * p.hist_frames + p.hist_frames - kBatch) * kM;
+        else {
+            src = p.x + s * stream_len + (long long)kb * kBatch * kM;
+            const long long left = p.n_frames - (long long)kb * kBatch;
+            if (left < kBatch) bytes = (uint32_t)left * kM * 8;
+        }
+        const uint32_t bar = mbar + 8 * (kSMbInFull + 4 * st + slot);
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(in0 + st * kInStageBytes, src, bytes, bar);
+    };
+
+    Walk w(L0, L1, p.batches_per_group);
+    Walk ahead = w;                                // the item two steps ahead, for prefetch
+    if (issuer) {
+        issue(ahead);
+        ahead.next();
+        if (!ahead.done()) issue(ahead);
+        ahead.next();
+    }
+    while (!w.done()) {
+        const int b = w.it & 1;
+        const uint32_t ph = (uint32_t)((w.it >> 1) & 1);
+        const uint32_t in = in0 + b * kInStageBytes + (2 * pr) * (kM * 8);
+        const uint32_t rows = ub0 + b * kXBufBytes;
+        mbar_wait(mbar + 8 * (kSMbInFull + 4 * b + slot), ph);
+        C2 v[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; n1++) {
+            const float2 e = lds64(in + (8 * n1 + t) * 8);
+            const float2 o = lds64(in + kM * 8 + (8 * n1 + t) * 8);
+            v[n1].re = make_float2(e.x, o.x);
+            v[n1].im = make_float2(e.y, o.y);
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(mbar + 8 * (kSMbInFree + 4 * b + slot));
+        dft8(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 8; k1++) v[dr8(k1)] = cmulw(v[dr8(k1)], twr[k1], twi[k1]);
+        if (w.it >= 2) mbar_wait(mbar + 8 * (kSMbUFree + 4 * b + slot), ph ^ 1);     // FIR role drained U[b] of item it-2
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) {
+            const C2 z = v[dr8(k1)];
+            sts128(rows + (((t << 3) | (k1 ^ t)) << 4), make_float4(z.re.x, z.re.y, z.im.x, z.im.y));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) {
+            const float4 q4 = lds128(rows + (((n2 << 3) | (t ^ n2)) << 4));
+            v[n2].re = make_float2(q4.x, q4.y);
+            v[n2].im = make_float2(q4.z, q4.w);
+        }
+        dft8(v);
+        __syncwarp();                               // exchange tile consumed before U overwrites the rows
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) {
+            const C2 z = v[dr8(k2)];
+            sts64(rows + (t + 8 * k2) * 8, make_float2(z.re.x, z.im.x));
+            sts64(rows + kRowBytes + (t + 8 * k2) * 8, make_float2(z.re.y, z.im.y));
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(mbar + 8 * (kSMbUFull + 8 * b + 2 * slot + half));
+        // prefetch the item two steps ahead into the stage this item has just drained
+        if (issuer && !ahead.done()) {
+            mbar_wait(mbar + 8 * (kSMbInFree + 4 * b + slot), ph);
+            issue(ahead);
+        }
+        if (issuer) ahead.next();
+        w.next();
+    }
+}
+
+template <int kTaps>
+__global__ void __launch_bounds__(kThreads, 1) k_firpfbch_synthesis_fused(const PfbSynParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t smem = smem_u32(smem_raw);
+    const uint32_t mbar = smem + 2 * kInStageBytes + 2 * kXBufBytes;
+    const long long n_batches = (long long)p.n_groups * p.batches_per_group;
+    const int L0 = (int)((n_batches * blockIdx.x) / gridDim.x);
+    const int L1 = (int)((n_batches * (blockIdx.x + 1)) / gridDim.x);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; i++) {
+            mbar_init(mbar + 8 * (kSMbInFull + i), 1);
+            mbar_init(mbar + 8 * (kSMbInFree + i), 2);
+            mbar_init(mbar + 8 * (kSMbUFree + i), 2);
+        }
+        for (int i = 0; i < 16; i++) mbar_init(mbar + 8 * (kSMbUFull + i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (L0 >= L1) return;
+    if (threadIdx.x < kFirThreads) syn_fir_role<kTaps>(p, smem, mbar, L0, L1);
+    else syn_fft_role(p, smem, mbar, L0, L1);
+}
+
+template <int kTaps>
+int32_t launch_syn_t(const FirpfbchFastPlan& plan, const PfbSynParams& p, cudaStream_t st)
+{
+    static bool attr_done[64] = {};
+    int dev = 0;
+    YG_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+        YG_CUDA(cudaFuncSetAttribute(k_firpfbch_synthesis_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSynSmemBytes));
+        attr_done[dev & 63] = true;
+    }
+    const long long n_batches = (long long)p.n_groups * p.batches_per_group;
+    const int grid = (int)std::min<long long>(plan.n_sm, n_batches);
+    k_firpfbch_synthesis_fused<kTaps><<<grid, kThreads, kSynSmemBytes, st>>>(p);
+    YG_CUDA(cudaGetLastError());
+    return YG_OK;
+}
+
 }  // namespace
 
 int32_t firpfbch_fast_plan(FirpfbchFastPlan& plan, int32_t type, uint32_t M, uint32_t p, const float* h)
 {
     plan.supported = false;
     plan.p = p;
-    if (type != YG_ANALYZER || M != (uint32_t)kM) return YG_OK;
+    if (M != (uint32_t)kM) return YG_OK;
+    plan.type = type;
     if (p < 2 || p > 16 || (p & 1)) return YG_OK;        // instantiated: p = 2, 4, ..., 16
     int dev = 0;
     YG_CUDA(cudaGetDevice(&dev));
@@ -293,7 +518,8 @@ int32_t firpfbch_fast_plan(FirpfbchFastPlan& plan, int32_t type, uint32_t M, uin
     plan.n_sm = prop.multiProcessorCount;
     std::vector<float> taps((size_t)kM * p);
     for (int pos = 0; pos < kM; pos++)
-        for (uint32_t n = 0; n < p; n++) taps[(size_t)pos * p + n] = h[(kM - 1 - pos) + n * kM];
+        for (uint32_t n = 0; n < p; n++)
+            taps[(size_t)pos * p + n] = (type == YG_ANALYZER) ? h[(kM - 1 - pos) + n * kM] : h[pos + n * kM];
     std::vector<float2> tw(64);
     for (int n2 = 0; n2 < 8; n2++)
         for (int k1 = 0; k1 < 8; k1++) {
@@ -319,7 +545,7 @@ void firpfbch_fast_release(FirpfbchFastPlan& plan)
 int32_t firpfbch_fast_launch(const FirpfbchFastPlan& plan, const float2* hist, long long Hlen, const float2* x, float2* y,
                              long long n_frames, long long n_streams, cudaStream_t st)
 {
-    if (!plan.supported) return fail(YG_EINTERNAL, "fused firpfbch kernel not available for this geometry");
+    if (!plan.supported || plan.type != YG_ANALYZER) return fail(YG_EINTERNAL, "fused firpfbch kernel not available for this geometry");
     if (n_streams % kSlots) return fail(YG_EINTERNAL, "fused firpfbch kernel takes groups of 4 streams");
     if ((((uintptr_t)x) & 15) != 0) return fail(YG_EVALUE, "input pointer must be 16-byte aligned");
     PfbParams p;
@@ -339,6 +565,35 @@ int32_t firpfbch_fast_launch(const FirpfbchFastPlan& plan, const float2* hist, l
         case 12: return launch_t<12>(plan, p, st);
         case 14: return launch_t<14>(plan, p, st);
         case 16: return launch_t<16>(plan, p, st);
+        default: return fail(YG_EINTERNAL, "fused firpfbch kernel not instantiated for p = %u", plan.p);
+    }
+}
+
+// Synthesis: hist = [n_streams][hist_frames * 64] INPUT history (hist_frames >= 16); n_streams a multiple of 4.
+int32_t firpfbch_fast_synth_launch(const FirpfbchFastPlan& plan, const float2* hist, long long hist_frames, const float2* x,
+                                   float2* y, long long n_frames, long long n_streams, cudaStream_t st)
+{
+    if (!plan.supported || plan.type != YG_SYNTHESIZER) return fail(YG_EINTERNAL, "fused firpfbch synthesis kernel not available");
+    if (n_streams % kSlots) return fail(YG_EINTERNAL, "fused firpfbch kernel takes groups of 4 streams");
+    if (hist_frames < kBatch) return fail(YG_EINTERNAL, "input history too short for the warm-up batch");
+    if ((((uintptr_t)x) & 15) != 0 || (((uintptr_t)hist) & 15) != 0) return fail(YG_EVALUE, "input pointer must be 16-byte aligned");
+    PfbSynParams p;
+    p.hist = hist; p.hist_frames = hist_frames; p.x = x; p.y = y;
+    p.n_frames = n_frames;
+    p.n_groups = (int)(n_streams / kSlots);
+    p.batches_per_group = (int)((n_frames + kBatch - 1) / kBatch);
+    p.taps = reinterpret_cast<const float*>(plan.d_taps);
+    p.twid = reinterpret_cast<const float2*>(plan.d_twid);
+    if ((long long)p.n_groups * p.batches_per_group > 0x3fffffffLL) return fail(YG_ERANGE, "too many batches for one launch");
+    switch (plan.p) {
+        case 2: return launch_syn_t<2>(plan, p, st);
+        case 4: return launch_syn_t<4>(plan, p, st);
+        case 6: return launch_syn_t<6>(plan, p, st);
+        case 8: return launch_syn_t<8>(plan, p, st);
+        case 10: return launch_syn_t<10>(plan, p, st);
+        case 12: return launch_syn_t<12>(plan, p, st);
+        case 14: return launch_syn_t<14>(plan, p, st);
+        case 16: return launch_syn_t<16>(plan, p, st);
         default: return fail(YG_EINTERNAL, "fused firpfbch kernel not instantiated for p = %u", plan.p);
     }
 }

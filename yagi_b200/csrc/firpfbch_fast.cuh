@@ -7,6 +7,7 @@ namespace yg {
 struct FirpfbchFastPlan {
     bool supported = false;
     uint32_t p = 0;
+    int32_t type = 0;
     void* d_taps = nullptr;
     void* d_twid = nullptr;
     int n_sm = 0;
@@ -17,5 +18,8 @@ void firpfbch_fast_release(FirpfbchFastPlan& plan);
 // n_streams must be a multiple of 4; layouts as the generic kernel: x[stream][n_frames*64], hist[stream][Hlen]
 int32_t firpfbch_fast_launch(const FirpfbchFastPlan& plan, const float2* hist, long long Hlen, const float2* x, float2* y,
                              long long n_frames, long long n_streams, cudaStream_t st);
+
+int32_t firpfbch_fast_synth_launch(const FirpfbchFastPlan& plan, const float2* hist, long long hist_frames, const float2* x,
+                                   float2* y, long long n_frames, long long n_streams, cudaStream_t st);
 
 }  // namespace yg
