@@ -90,13 +90,13 @@ def main():
         del qs
         del x, y, q
     if "firfilt" in which:
-        S, n = 1024, 1 << 18                    # config #2 geometry at a quarter of the length
+        S, n = 1024, 1 << 20                    # BASELINE config #2: 1024 streams x 2^20 samples (8 GiB in, 8 GiB out)
         x = randc(S * n)
         y = torch.empty(S * n, dtype=torch.complex64, device="cuda")
         q = yb.FirFilt.new_kaiser(63, 0.25, 60.0, 0.0, n_streams=S)
         ms = timed(lambda: q.execute_block(x, out=y), steps=5)
         flops = 252.0 * S * n
-        report("firfilt_crcf 63 taps, 1024 streams x 2^18", ms, 16.0 * S * n, S * n, "samples",
+        report("firfilt_crcf 63 taps, 1024 streams x 2^20", ms, 16.0 * S * n, S * n, "samples",
                {"fp32_TFLOPs": round(flops / (ms * 1e-3) / 1e12, 2)})
 
 

@@ -168,7 +168,7 @@ int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames
     if (q->type == YG_ANALYZER) {
         const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
         long long s_fast = 0;
-        if (q->fast.supported && S >= 4 && n_frames >= 16) {
+        if (q->fast.supported && S >= 4 && n_frames >= 16 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
             // groups of four streams go to the fused kernel, the remaining 0..3 streams to the generic one
             s_fast = (S / 4) * 4;
             YG_TRY(firpfbch_fast_launch(q->fast, hist, Hlen, x, y, (long long)n_frames, s_fast, st));
@@ -189,7 +189,7 @@ int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames
         const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
         const long long hist_frames = Hlen / M;
         long long s_fast = 0;
-        if (q->fast.supported && S >= 4 && n_frames >= 16) {
+        if (q->fast.supported && S >= 4 && n_frames >= 16 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
             s_fast = (S / 4) * 4;
             YG_TRY(firpfbch_fast_synth_launch(q->fast, hist, hist_frames, x, y, (long long)n_frames, s_fast, st));
             q->last_path = 2;

@@ -203,7 +203,9 @@ int32_t launch_analysis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames
     // left over (a leading odd-parity frame, a trailing single frame) and calls too small to
     // fill the machine go to the generic kernel.
     q->next_events();
-    const bool use_fused = q->fast.supported && n_frames >= q->fast.min_frames;
+    // the fused kernels read the input with TMA bulk copies, which need 16-byte aligned sources
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const bool use_fused = aligned && q->fast.supported && n_frames >= q->fast.min_frames;
     const bool use_large = q->large.supported && n_frames >= q->large.min_frames;
     if (use_fused || use_large) {
         const size_t lead = (q->flag & 1) ? 1 : 0;
@@ -261,7 +263,8 @@ int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frame
     // output ranges, so their order does not matter.
     const size_t lead = (q->flag & 1) ? 1 : 0;
     const size_t body = (n_frames > lead) ? ((n_frames - lead) / 32) * 32 : 0;
-    const bool use_fused = q->sfast.supported && body >= q->sfast.min_frames;
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const bool use_fused = aligned && q->sfast.supported && body >= q->sfast.min_frames;
     const bool use_large = q->slarge.supported && body >= q->slarge.min_frames;
     if (use_fused || use_large) {
         if (use_large) YG_TRY(q->d_Uc.reserve((size_t)firpfbch2_large_synth_scratch_frames() * q->M));
