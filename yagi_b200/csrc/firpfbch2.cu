@@ -234,21 +234,23 @@ int32_t launch_generic_synthesis(yg_firpfbch2_crcf q, const float2* hist, const 
     if (f_end <= f_begin) return YG_OK;
     const uint32_t M = q->M;
     const long long nh = 4 * (long long)q->m - 1;
-    const long long nf = (long long)(f_end - f_begin);
-    YG_TRY(q->d_U.reserve((size_t)(nh + nf) * M));
+    // bounded scratch: at most ~64 MiB of U per pass (the 4m-1 frames before each pass are transformed again)
+    const long long chunk = std::max<long long>(2 * nh, ((long long)64 << 20) / ((long long)M * 8));
+    YG_TRY(q->d_U.reserve((size_t)(nh + std::min<long long>(chunk, (long long)(f_end - f_begin))) * M));
     float2* U = reinterpret_cast<float2*>(q->d_U.p);
     const size_t smem = smem_dft(M);
     YG_TRY(set_smem((const void*)k_synth_ifft, smem));
     const int block = (int)std::min<uint32_t>(256, (M + 31) / 32 * 32);
-    const int grid = (int)std::min<long long>(nh + nf, 148 * 16);
-    k_synth_ifft<<<grid, block, smem, st>>>(q->d_tw.p, hist, (long long)(q->hist_len / M), x, U, M,
-                                            (long long)f_begin - nh, (long long)f_end);
-    YG_CUDA(cudaGetLastError());
-    const long long total = nf * q->M2;
-    const int grid2 = (int)std::min<long long>((total + 255) / 256, 148 * 32);
-    k_synth_wola<<<grid2, 256, 0, st>>>(q->d_h.p, U + nh * M, y + (long long)f_begin * q->M2, M, q->m, nf,
-                                        (q->flag + (int)(f_begin & 1)) & 1);
-    YG_CUDA(cudaGetLastError());
+    for (long long f0 = (long long)f_begin; f0 < (long long)f_end; f0 += chunk) {
+        const long long nf = std::min<long long>(chunk, (long long)f_end - f0);
+        const int grid = (int)std::min<long long>(nh + nf, 148 * 16);
+        k_synth_ifft<<<grid, block, smem, st>>>(q->d_tw.p, hist, (long long)(q->hist_len / M), x, U, M, f0 - nh, f0 + nf);
+        YG_CUDA(cudaGetLastError());
+        const long long total = nf * q->M2;
+        const int grid2 = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+        k_synth_wola<<<grid2, 256, 0, st>>>(q->d_h.p, U + nh * M, y + f0 * q->M2, M, q->m, nf, (q->flag + (int)(f0 & 1)) & 1);
+        YG_CUDA(cudaGetLastError());
+    }
     return YG_OK;
 }
 

@@ -261,13 +261,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_firpfbch2_synthesis_fused(const
 template <int kTaps>
 int32_t launch_t(const Firpfbch2FastPlan& plan, const SynthParams& p, cudaStream_t st)
 {
-    static bool attr_done[64] = {};
-    int dev = 0;
-    YG_CUDA(cudaGetDevice(&dev));
-    if (!attr_done[dev & 63]) {
-        YG_CUDA(cudaFuncSetAttribute(k_firpfbch2_synthesis_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_done[dev & 63] = true;
-    }
+    // idempotent and cheap (a few microseconds); doing it per launch keeps the code free of shared mutable state
+    YG_CUDA(cudaFuncSetAttribute(k_firpfbch2_synthesis_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     const int grid = (int)std::min<long long>(plan.n_sm, p.n_periods);
     k_firpfbch2_synthesis_fused<kTaps><<<grid, kThreads, kSmemBytes, st>>>(p);
     YG_CUDA(cudaGetLastError());

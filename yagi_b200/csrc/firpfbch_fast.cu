@@ -263,13 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_firpfbch_analysis_fused(const P
 template <int kTaps>
 int32_t launch_t(const FirpfbchFastPlan& plan, const PfbParams& p, cudaStream_t st)
 {
-    static bool attr_done[64] = {};
-    int dev = 0;
-    YG_CUDA(cudaGetDevice(&dev));
-    if (!attr_done[dev & 63]) {
-        YG_CUDA(cudaFuncSetAttribute(k_firpfbch_analysis_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_done[dev & 63] = true;
-    }
+    // idempotent and cheap (a few microseconds); doing it per launch keeps the code free of shared mutable state
+    YG_CUDA(cudaFuncSetAttribute(k_firpfbch_analysis_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     const long long n_batches = (long long)p.n_groups * p.batches_per_group;
     const int grid = (int)std::min<long long>(plan.n_sm, n_batches);
     k_firpfbch_analysis_fused<kTaps><<<grid, kThreads, kSmemBytes, st>>>(p);
@@ -487,13 +482,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_firpfbch_synthesis_fused(const 
 template <int kTaps>
 int32_t launch_syn_t(const FirpfbchFastPlan& plan, const PfbSynParams& p, cudaStream_t st)
 {
-    static bool attr_done[64] = {};
-    int dev = 0;
-    YG_CUDA(cudaGetDevice(&dev));
-    if (!attr_done[dev & 63]) {
-        YG_CUDA(cudaFuncSetAttribute(k_firpfbch_synthesis_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSynSmemBytes));
-        attr_done[dev & 63] = true;
-    }
+    // idempotent and cheap (a few microseconds); doing it per launch keeps the code free of shared mutable state
+    YG_CUDA(cudaFuncSetAttribute(k_firpfbch_synthesis_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSynSmemBytes));
     const long long n_batches = (long long)p.n_groups * p.batches_per_group;
     const int grid = (int)std::min<long long>(plan.n_sm, n_batches);
     k_firpfbch_synthesis_fused<kTaps><<<grid, kThreads, kSynSmemBytes, st>>>(p);
