@@ -190,3 +190,72 @@ mod tests {
         assert_eq!(q.get_m(), 12);
     }
 }
+
+/// Critically sampled polyphase filterbank channelizer (upstream firpfbch_crcf), GPU-backed,
+/// batched over `n_streams` independent streams that share the taps (layout x[stream][frame][M]).
+#[derive(Debug)]
+pub struct FirPfbCh {
+    q: sys::yg_firpfbch_crcf,
+    type_: FirPfbChType,
+    num_channels: usize,
+    p: usize,
+    n_streams: usize,
+}
+
+unsafe impl Send for FirPfbCh {}
+
+impl FirPfbCh {
+    pub fn new(type_: FirPfbChType, num_channels: usize, p: usize, h: &[f32], n_streams: usize) -> Result<Self> {
+        let mut q = std::ptr::null_mut();
+        check(unsafe {
+            sys::yg_firpfbch_crcf_create(type_ as i32, num_channels as u32, p as u32, h.as_ptr(), h.len(), n_streams as u32, &mut q)
+        })?;
+        Ok(Self { q, type_, num_channels, p, n_streams })
+    }
+
+    pub fn new_kaiser(type_: FirPfbChType, num_channels: usize, m: usize, as_: f32, n_streams: usize) -> Result<Self> {
+        let mut q = std::ptr::null_mut();
+        check(unsafe {
+            sys::yg_firpfbch_crcf_create_kaiser(type_ as i32, num_channels as u32, m as u32, as_, n_streams as u32, &mut q)
+        })?;
+        Ok(Self { q, type_, num_channels, p: 2 * m, n_streams })
+    }
+
+    pub fn reset(&mut self) {
+        let _ = unsafe { sys::yg_firpfbch_crcf_reset(self.q) };
+    }
+    pub fn get_type(&self) -> FirPfbChType {
+        self.type_
+    }
+    pub fn get_num_channels(&self) -> usize {
+        self.num_channels
+    }
+    pub fn get_p(&self) -> usize {
+        self.p
+    }
+
+    /// `n` frames per stream: x and y hold n_streams * n * num_channels samples.
+    pub fn execute_block(&mut self, x: &[Complex32], n: usize, y: &mut [Complex32]) -> Result<()> {
+        let total = self.n_streams * n * self.num_channels;
+        if x.len() != total || y.len() != total {
+            return Err(Error::Config("input/output block lengths do not match the frame count".into()));
+        }
+        check(unsafe {
+            sys::yg_firpfbch_crcf_execute_block(self.q, x.as_ptr() as *const sys::yg_cf32, n, y.as_mut_ptr() as *mut sys::yg_cf32)
+        })
+    }
+}
+
+impl Clone for FirPfbCh {
+    fn clone(&self) -> Self {
+        let mut q = std::ptr::null_mut();
+        check(unsafe { sys::yg_firpfbch_crcf_clone(self.q, &mut q) }).expect("clone failed");
+        Self { q, type_: self.type_, num_channels: self.num_channels, p: self.p, n_streams: self.n_streams }
+    }
+}
+
+impl Drop for FirPfbCh {
+    fn drop(&mut self) {
+        unsafe { sys::yg_firpfbch_crcf_destroy(self.q) };
+    }
+}

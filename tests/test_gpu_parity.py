@@ -542,3 +542,33 @@ def test_misaligned_device_input_falls_back_to_generic_kernels():
     torch.cuda.synchronize()
     assert q.last_path() == 1
     assert_parity(y.cpu().numpy(), ref, "misaligned input")
+
+
+def test_api_error_behaviour():
+    """Argument errors surface as the reference's Error variants (src/error.rs:6-14), not as crashes."""
+    import torch
+    q = yb.FirPfbCh2.new_kaiser(A, 16, 3, 60.0)
+    with pytest.raises(yb.ConfigError):
+        q.execute(np.zeros(7, dtype=np.complex64))                  # one frame is M/2 = 8 samples
+    with pytest.raises(yb.ConfigError):
+        q.execute_block(np.zeros(20, dtype=np.complex64))           # not a whole number of frames
+    with pytest.raises(yb.ConfigError):
+        q.execute_block(np.zeros(16, dtype=np.complex64), 2, out=np.zeros(16, dtype=np.complex64))   # out too small
+    with pytest.raises(yb.YagiError):
+        q.execute_block(np.zeros(16, dtype=np.complex64), 2, out=np.zeros(32, dtype=np.complex128))  # wrong dtype
+    with pytest.raises(yb.YagiError):
+        q.execute_block(torch.zeros(16, dtype=torch.float32, device="cuda"))                          # wrong dtype on device
+    with pytest.raises(yb.YagiError):
+        q.set_state(np.zeros(q.state_len(), dtype=np.complex64), 2)                                  # flag must be 0/1
+    with pytest.raises(yb.ConfigError):
+        q.set_state(np.zeros(q.state_len() + 1, dtype=np.complex64), 0)
+    # zero frames is a no-op
+    assert q.execute_block(np.zeros(0, dtype=np.complex64)).size == 0
+    f = yb.FirFilt.new(np.ones(5, dtype=np.float32), n_streams=3)
+    with pytest.raises(yb.ConfigError):
+        f.execute_block(np.zeros(10, dtype=np.complex64))           # not divisible by n_streams
+    c = yb.FirPfbCh.new_kaiser(A, 8, 2, 60.0, n_streams=2)
+    with pytest.raises(yb.ConfigError):
+        c.execute(np.zeros(8, dtype=np.complex64))                  # needs M * n_streams samples
+    assert (c.get_type(), c.get_num_channels(), c.get_p(), c.get_n_streams()) == (A, 8, 4, 2)
+    assert repr(q).startswith("FirPfbCh2") and q.get_m() == 3 and q.get_num_channels() == 16
