@@ -456,11 +456,11 @@ def test_firpfbch_fused_M64(p, S_, Q, type_, otype):
     assert per_stream.max() <= 1e-4, int(per_stream.argmax())
 
 
-@pytest.mark.parametrize("m", [4, 2, 7])
-def test_large_M1024_two_stage_path(m):
-    """M=1024 analysis on the two-stage (FIR kernel + in-place FFT kernel) path (last_path == 3):
+@pytest.mark.parametrize("M,m", [(1024, 4), (1024, 2), (1024, 7), (512, 5), (2048, 3), (4096, 2)])
+def test_large_M_two_stage_path(M, m):
+    """Large-M analysis on the two-stage (FIR kernel + in-place FFT kernel) path (last_path == 3):
     uneven call sizes, odd-parity starts, history from the previous call."""
-    M, K = 1024, 700
+    K = 700 if M <= 1024 else 300
     rng = np.random.default_rng(900 + m)
     h = rng.standard_normal(2 * M * m).astype(np.float32)
     x = _rand_c(rng, K * M // 2)
@@ -474,15 +474,15 @@ def test_large_M1024_two_stage_path(m):
             assert q.last_path() == 3, (a, b)
     y = np.concatenate(outs).reshape(K, M)
     scale = max(1.0, np.abs(ref).max())
-    assert_parity(y / scale, ref / scale, "large-M m=%d" % m)
+    assert_parity(y / scale, ref / scale, "large-M M=%d m=%d" % (M, m))
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
 
 
-@pytest.mark.parametrize("m", [4, 2, 7])
-def test_large_M1024_two_stage_synthesis(m):
-    """M=1024 synthesis on the two-stage (IFFT kernel into an L2 scratch + overlap-add kernel) path."""
-    M, K = 1024, 500
+@pytest.mark.parametrize("M,m", [(1024, 4), (1024, 2), (1024, 7), (512, 5), (2048, 3), (4096, 2)])
+def test_large_M_two_stage_synthesis(M, m):
+    """Large-M synthesis on the two-stage (IFFT kernel into an L2 scratch + overlap-add kernel) path."""
+    K = 500 if M <= 1024 else 400
     rng = np.random.default_rng(950 + m)
     h = rng.standard_normal(2 * M * m).astype(np.float32)
     X = _rand_c(rng, K * M)
@@ -496,7 +496,7 @@ def test_large_M1024_two_stage_synthesis(m):
             assert q.last_path() == 3, (a, b)
     y = np.concatenate(outs).reshape(K, M // 2)
     scale = max(1.0, np.abs(ref).max())
-    assert_parity(y / scale, ref / scale, "large-M synthesis m=%d" % m)
+    assert_parity(y / scale, ref / scale, "large-M synthesis M=%d m=%d" % (M, m))
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
 

@@ -1,12 +1,14 @@
-// firpfbch2_large.cu -- firpfbch2 analysis for M = 1024 (BASELINE config #4), m = 1..8, sm_100a.
+// firpfbch2_large.cu -- firpfbch2 analysis and synthesis for large power-of-two M (512 .. 4096; M = 1024 is
+// BASELINE config #4), sm_100a.
 //
 // One SM cannot hold a 1024-branch window set plus the transform, so large M runs as TWO kernels per
 // chunk of frames, chained through the 126 MB L2 instead of HBM:
 //   stage A (k_large_fir):  branch FIRs with register-resident windows (the firpfbch2_fast.cu FIR role,
 //                           256 branches per CTA), writes the rolled, 1/M-scaled branch sums V_k straight
 //                           into the output frames;
-//   stage B (k_large_fft):  in-place 1024-point backward DFT of every frame, one warp per frame,
-//                           32 x 32 with a radix-32 in registers and one XOR-swizzled shared exchange.
+//   stage B (k_large_fft):  in-place M-point backward DFT of every frame: for M = 1024 one warp per frame,
+//                           32 x 32 with a radix-32 in registers and one XOR-swizzled shared exchange;
+//                           for the other sizes one CTA per frame (shared-memory radix-4 Stockham).
 // The host walks the call in chunks whose output (8 KB per frame) fits in L2, so V is written and read
 // back in cache and HBM sees the algorithmic 24 B per input sample.
 #include "firpfbch2_fast.cuh"
@@ -23,10 +25,7 @@ namespace {
 
 using namespace yg::dev;
 
-constexpr int kM = 1024;
-constexpr int kM2 = 512;
-constexpr int kFirThreads = 256;                 // branches per CTA
-constexpr int kBlocksPerFrame = kM / kFirThreads;
+constexpr int kFirThreads = 256;                 // branches per CTA (M / 256 CTAs cover a frame)
 constexpr int kPairsPerBatch = 16;
 
 struct LargeParams {
@@ -37,8 +36,9 @@ struct LargeParams {
     long long f0;             // first frame handled (even global parity)
     long long pair_begin, pair_end;      // frame pairs of this launch, relative to f0
     int slabs;                // CTAs along the pair axis
-    const float2* taps;       // [1024][2m+1] (even, odd) tap pairs, 1/M folded in
-    const float2* twid;       // [1024] e^{+j 2 pi k / 1024}
+    int M;                    // channels (power of two, multiple of 256)
+    const float2* taps;       // [M][2m+1] (even, odd) tap pairs, 1/M folded in
+    const float2* twid;       // [M] e^{+j 2 pi k / M}
 };
 
 // ------------------------------------------------------------------ stage A: branch FIRs
@@ -46,6 +46,7 @@ template <int kTaps>
 __global__ void __launch_bounds__(kFirThreads, 2) k_large_fir(const LargeParams p)
 {
     constexpr int kHist = kTaps - 1;
+    const int kM = p.M, kM2 = p.M >> 1;
     const int j = blockIdx.y * kFirThreads + threadIdx.x;               // branch
     const int pos = (j < kM2) ? (kM2 - 1 - j) : (kM + kM2 - 1 - j);       // sample slot inside an M-sample block
     const long long n_pairs = p.pair_end - p.pair_begin;
@@ -154,6 +155,7 @@ __device__ __forceinline__ void xdft32(float2 (&v)[32], const float2* w32 /* e^{
     xdft16<16>(v);
 }
 
+constexpr int kM = 1024;                         // the warp-per-frame DFT kernel below is the M = 1024 instance
 constexpr int kFftWarps = 8;                     // frames per CTA
 constexpr int kFftSmem = kFftWarps * 1024 * 8 + 16 * 8;
 
@@ -191,7 +193,6 @@ __global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft(const float2* p
         for (int n2 = 0; n2 < 32; n2++) v[n2] = lds64(tile + (((n2 << 5) | (lane ^ n2)) << 3));
         __syncwarp();
         xdft32(v, w32);
-#pragma unroll
         if (streaming_store) {
 #pragma unroll
             for (int k2 = 0; k2 < 32; k2++) __stcs(fr + lane + 32 * k2, v[dr32(k2)]);
@@ -203,6 +204,42 @@ __global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft(const float2* p
 }
 
 
+// Other sizes: one CTA per frame, shared-memory radix-4 Stockham (block_dft in common.cuh).
+__global__ void k_large_fft_block(const float2* prefix, const float2* x, long long v0, float2* dst, long long n_frames,
+                                  int M, const float2* __restrict__ twid, int streaming_store)
+{
+    extern __shared__ float2 sm_blk[];
+    float2* X = sm_blk;
+    float2* Y = sm_blk + M;
+    for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const long long vi = v0 + f;
+        const float2* src = (vi < 0) ? prefix + (32 + vi) * M : x + vi * M;
+        float2* fr = dst + f * M;
+        for (int c = threadIdx.x; c < M; c += blockDim.x) X[c] = src[c];
+        const float2* r = block_dft(X, Y, (uint32_t)M, twid, 1);
+        if (streaming_store) for (int c = threadIdx.x; c < M; c += blockDim.x) __stcs(fr + c, r[c]);
+        else for (int c = threadIdx.x; c < M; c += blockDim.x) fr[c] = r[c];
+        __syncthreads();
+    }
+}
+
+int32_t launch_fft(const Firpfbch2FastPlan& plan, const float2* prefix, const float2* x, long long v0, float2* dst,
+                   long long n_frames, int streaming, cudaStream_t st)
+{
+    const float2* tw = reinterpret_cast<const float2*>(plan.d_twid);
+    if (plan.M == (uint32_t)kM) {
+        const int grid = (int)std::min<long long>((n_frames + kFftWarps - 1) / kFftWarps, (long long)plan.n_sm * 2);
+        k_large_fft<<<grid, kFftWarps * 32, kFftSmem, st>>>(prefix, x, v0, dst, n_frames, tw, streaming);
+    } else {
+        const int M = (int)plan.M;
+        const size_t smem = 2 * (size_t)M * sizeof(float2);
+        const int grid = (int)std::min<long long>(n_frames, (long long)plan.n_sm * 8);
+        k_large_fft_block<<<grid, 256, smem, st>>>(prefix, x, v0, dst, n_frames, M, tw, streaming);
+    }
+    YG_CUDA(cudaGetLastError());
+    return YG_OK;
+}
+
 // ------------------------------------------------------------------ synthesis stage C: weighted overlap-add
 // Thread j owns COLUMN j of U (the firpfbch2_synth_fast.cu FIR role with global loads): 32-entry register
 // ring over the last 4m frames, values prefetched 8 steps (16 frames) ahead through a 16-entry register
@@ -212,12 +249,14 @@ struct WolaParams {
     float2* y;                // output sample 0 of frame c0
     long long n_frames;       // frames of this chunk (multiple of 32); U holds n_frames + 32 frames
     int slabs;
-    const float* taps;        // [1024][4m]  0.5 * h[(j & 511) + l * 512]
+    int M;
+    const float* taps;        // [M][4m]  0.5 * h[(j & (M/2-1)) + l * M/2]
 };
 
 template <int kTaps>
 __global__ void __launch_bounds__(kFirThreads, 2) k_large_wola(const WolaParams p)
 {
+    const int kM = p.M, kM2 = p.M >> 1;
     const int j = blockIdx.y * kFirThreads + threadIdx.x;
     const bool hi = j >= kM2;
     const int i = j & (kM2 - 1);
@@ -283,7 +322,7 @@ __global__ void __launch_bounds__(kFirThreads, 2) k_large_wola(const WolaParams 
 template <int kTaps>
 int32_t launch_wola(const WolaParams& p, cudaStream_t st)
 {
-    dim3 grid((unsigned)p.slabs, kBlocksPerFrame);
+    dim3 grid((unsigned)p.slabs, (unsigned)(p.M / kFirThreads));
     k_large_wola<kTaps><<<grid, kFirThreads, 0, st>>>(p);
     YG_CUDA(cudaGetLastError());
     return YG_OK;
@@ -292,11 +331,43 @@ int32_t launch_wola(const WolaParams& p, cudaStream_t st)
 template <int kTaps>
 int32_t launch_fir(const LargeParams& p, cudaStream_t st)
 {
-    dim3 grid((unsigned)p.slabs, kBlocksPerFrame);
+    dim3 grid((unsigned)p.slabs, (unsigned)(p.M / kFirThreads));
     k_large_fir<kTaps><<<grid, kFirThreads, 0, st>>>(p);
     YG_CUDA(cudaGetLastError());
     return YG_OK;
 }
+
+}  // namespace
+
+namespace {
+
+bool large_geometry_ok(uint32_t M) { return M == 512 || M == 1024 || M == 2048 || M == 4096; }
+
+int32_t plan_common(Firpfbch2FastPlan& plan, uint32_t M)
+{
+    int dev = 0;
+    YG_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    YG_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return YG_OK;
+    plan.n_sm = prop.multiProcessorCount;
+    std::vector<float2> tw(M);
+    for (uint32_t k = 0; k < M; k++) {
+        const double a = 2.0 * M_PI * (double)k / (double)M;
+        tw[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    YG_CUDA(cudaMalloc(&plan.d_twid, tw.size() * sizeof(float2)));
+    YG_CUDA(cudaMemcpy(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    if (M == (uint32_t)kM) YG_CUDA(cudaFuncSetAttribute(k_large_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
+    else if (2 * (size_t)M * sizeof(float2) > 48 * 1024)
+        YG_CUDA(cudaFuncSetAttribute(k_large_fft_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * (size_t)M * sizeof(float2))));
+    plan.min_frames = 64;
+    plan.supported = true;
+    return YG_OK;
+}
+
+// frames of intermediate kept per chunk: 96 MB (swept 16..96 MB at M = 1024: profiles/r01_large_chunk_sweep.log)
+long long chunk_frames(uint32_t M) { return std::max<long long>(128, (((long long)96 << 20) / ((long long)M * 8)) & ~63LL); }
 
 }  // namespace
 
@@ -305,40 +376,25 @@ int32_t firpfbch2_large_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
     plan.supported = false;
     plan.M = M;
     plan.m = m;
-    if (M != (uint32_t)kM || m < 1 || m > 8) return YG_OK;
-    int dev = 0;
-    YG_CUDA(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    YG_CUDA(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major != 10) return YG_OK;
-    plan.n_sm = prop.multiProcessorCount;
+    if (!large_geometry_ok(M) || m < 1 || m > 8) return YG_OK;
+    const int iM = (int)M, iM2 = iM / 2;
     const int kTaps = 2 * (int)m + 1, P = 2 * (int)m;
-    std::vector<float2> taps((size_t)kM * kTaps);
-    const float s = 1.0f / (float)kM;
-    for (int j = 0; j < kM; j++)
+    std::vector<float2> taps((size_t)iM * kTaps);
+    const float s = 1.0f / (float)iM;
+    for (int j = 0; j < iM; j++)
         for (int i = 0; i < kTaps; i++) {
             float te = 0.f, to = 0.f;
-            if (j < kM2) {
-                if (i < P) { te = h[j + i * kM]; to = h[j + kM2 + i * kM]; }
+            if (j < iM2) {
+                if (i < P) { te = h[j + i * iM]; to = h[j + iM2 + i * iM]; }
             } else {
-                if (i >= 1) te = h[j + (i - 1) * kM];
-                if (i < P) to = h[j - kM2 + i * kM];
+                if (i >= 1) te = h[j + (i - 1) * iM];
+                if (i < P) to = h[j - iM2 + i * iM];
             }
             taps[(size_t)j * kTaps + i] = make_float2(te * s, to * s);
         }
-    std::vector<float2> tw(kM);
-    for (int k = 0; k < kM; k++) {
-        const double a = 2.0 * M_PI * (double)k / (double)kM;
-        tw[k] = make_float2((float)cos(a), (float)sin(a));
-    }
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float2)));
     YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    YG_CUDA(cudaMalloc(&plan.d_twid, tw.size() * sizeof(float2)));
-    YG_CUDA(cudaMemcpy(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    YG_CUDA(cudaFuncSetAttribute(k_large_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
-    plan.min_frames = 64;
-    plan.supported = true;
-    return YG_OK;
+    return plan_common(plan, M);
 }
 
 int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist, long long Hlen, const float2* x, float2* y,
@@ -347,17 +403,19 @@ int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist
     if (!plan.supported) return fail(YG_EINTERNAL, "large-M path not available for this geometry");
     if (n_frames == 0) return YG_OK;
     if (n_frames & 1) return fail(YG_EINTERNAL, "large-M path needs an even number of frames");
+    const int M = (int)plan.M;
     const long long n_pairs = (long long)(n_frames / 2);
-    // chunk so that a chunk's output (8 KB per frame) stays resident in L2 between the two stages
-    const long long chunk_pairs = std::max<long long>(64, ((long long)96 << 20) / (2 * kM * 8));   // 96 MB of output per chunk (swept 16..96 MB)
+    // chunk so that a chunk's output (8 M bytes per frame) stays resident in L2 between the two stages
+    const long long chunk_pairs = chunk_frames(plan.M) / 2;
     for (long long q = 0; q < n_pairs; q += chunk_pairs) {
         LargeParams p;
         p.hist = hist; p.Hlen = Hlen; p.x = x; p.y = y;
         p.f0 = (long long)f0;
         p.pair_begin = q;
         p.pair_end = std::min(n_pairs, q + chunk_pairs);
+        p.M = M;
         const long long batches = (p.pair_end - p.pair_begin + kPairsPerBatch - 1) / kPairsPerBatch;
-        p.slabs = (int)std::min<long long>(batches, (long long)plan.n_sm * 2 / kBlocksPerFrame * 2);
+        p.slabs = (int)std::max<long long>(1, std::min<long long>(batches, (long long)plan.n_sm * 4 / (M / kFirThreads)));
         p.taps = reinterpret_cast<const float2*>(plan.d_taps);
         p.twid = reinterpret_cast<const float2*>(plan.d_twid);
         switch (plan.m) {
@@ -372,10 +430,8 @@ int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist
             default: return fail(YG_EINTERNAL, "large-M path not instantiated for m = %u", plan.m);
         }
         const long long nf = 2 * (p.pair_end - p.pair_begin);
-        const int grid = (int)std::min<long long>((nf + kFftWarps - 1) / kFftWarps, (long long)plan.n_sm * 2);
-        float2* yc = y + ((long long)f0 + 2 * p.pair_begin) * kM;
-        k_large_fft<<<grid, kFftWarps * 32, kFftSmem, st>>>(nullptr, yc, 0, yc, nf, reinterpret_cast<const float2*>(plan.d_twid), 1);
-        YG_CUDA(cudaGetLastError());
+        float2* yc = y + ((long long)f0 + 2 * p.pair_begin) * M;
+        YG_TRY(launch_fft(plan, nullptr, yc, 0, yc, nf, 1, st));
     }
     return YG_OK;
 }
@@ -385,35 +441,20 @@ int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t
     plan.supported = false;
     plan.M = M;
     plan.m = m;
-    if (M != (uint32_t)kM || m < 1 || m > 7) return YG_OK;
-    int dev = 0;
-    YG_CUDA(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    YG_CUDA(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major != 10) return YG_OK;
-    plan.n_sm = prop.multiProcessorCount;
+    if (!large_geometry_ok(M) || m < 1 || m > 7) return YG_OK;
+    const int iM = (int)M, iM2 = iM / 2;
     const int kTaps = 4 * (int)m;
-    std::vector<float> taps((size_t)kM * kTaps);
-    for (int j = 0; j < kM; j++)
-        for (int l = 0; l < kTaps; l++) taps[(size_t)j * kTaps + l] = 0.5f * h[(j & (kM2 - 1)) + l * kM2];
-    std::vector<float2> tw(kM);
-    for (int k = 0; k < kM; k++) {
-        const double a = 2.0 * M_PI * (double)k / (double)kM;
-        tw[k] = make_float2((float)cos(a), (float)sin(a));
-    }
+    std::vector<float> taps((size_t)iM * kTaps);
+    for (int j = 0; j < iM; j++)
+        for (int l = 0; l < kTaps; l++) taps[(size_t)j * kTaps + l] = 0.5f * h[(j & (iM2 - 1)) + l * iM2];
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float)));
     YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
-    YG_CUDA(cudaMalloc(&plan.d_twid, tw.size() * sizeof(float2)));
-    YG_CUDA(cudaMemcpy(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    YG_CUDA(cudaFuncSetAttribute(k_large_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
-    plan.min_frames = 64;
-    plan.supported = true;
-    return YG_OK;
+    return plan_common(plan, M);
 }
 
 // `prefix` = the 32 input frames preceding x[0]; frames [f0, f0 + n_frames) of the call, f0 on even global
-// parity, n_frames a multiple of 32; `scratch` holds at least (chunk + 32) * 1024 samples (see *_scratch_frames).
-long long firpfbch2_large_synth_scratch_frames() { return ((long long)96 << 20) / (kM * 8) + 32; }
+// parity, n_frames a multiple of 32; `scratch` holds firpfbch2_large_synth_scratch_frames(M) frames.
+long long firpfbch2_large_synth_scratch_frames(uint32_t M) { return chunk_frames(M) + 32; }
 
 int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& plan, const float2* prefix, const float2* x, float2* y,
                                      float2* scratch, size_t f0, size_t n_frames, cudaStream_t st)
@@ -421,20 +462,18 @@ int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& plan, const float2
     if (!plan.supported) return fail(YG_EINTERNAL, "large-M synthesis path not available for this geometry");
     if (n_frames == 0) return YG_OK;
     if (n_frames % 32) return fail(YG_EINTERNAL, "large-M synthesis path needs a multiple of 32 frames");
-    const long long chunk = firpfbch2_large_synth_scratch_frames() - 32;     // multiple of 32
+    const int M = (int)plan.M;
+    const long long chunk = chunk_frames(plan.M);                              // multiple of 32
     for (long long c0 = 0; c0 < (long long)n_frames; c0 += chunk) {
         const long long nf = std::min<long long>(chunk, (long long)n_frames - c0);
         // stage B': U[g] = IDFT_unnorm(X[f0 + c0 - 32 + g]), g = 0 .. nf + 31 (the 1/2 scale lives in the taps)
-        const long long nfft = nf + 32;
-        const int gridf = (int)std::min<long long>((nfft + kFftWarps - 1) / kFftWarps, (long long)plan.n_sm * 2);
-        k_large_fft<<<gridf, kFftWarps * 32, kFftSmem, st>>>(prefix, x, (long long)f0 + c0 - 32, scratch, nfft,
-                                                             reinterpret_cast<const float2*>(plan.d_twid), 0);
-        YG_CUDA(cudaGetLastError());
+        YG_TRY(launch_fft(plan, prefix, x, (long long)f0 + c0 - 32, scratch, nf + 32, 0, st));
         WolaParams p;
         p.U = scratch;
-        p.y = y + ((long long)f0 + c0) * kM2;
+        p.y = y + ((long long)f0 + c0) * (M / 2);
         p.n_frames = nf;
-        p.slabs = (int)std::min<long long>(nf / 32, (long long)plan.n_sm * 2 / kBlocksPerFrame * 2);
+        p.M = M;
+        p.slabs = (int)std::max<long long>(1, std::min<long long>(nf / 32, (long long)plan.n_sm * 4 / (M / kFirThreads)));
         p.taps = reinterpret_cast<const float*>(plan.d_taps);
         switch (plan.m) {
             case 1: YG_TRY(launch_wola<4>(p, st)); break;
