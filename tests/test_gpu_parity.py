@@ -572,3 +572,26 @@ def test_api_error_behaviour():
         c.execute(np.zeros(8, dtype=np.complex64))                  # needs M * n_streams samples
     assert (c.get_type(), c.get_num_channels(), c.get_p(), c.get_n_streams()) == (A, 8, 4, 2)
     assert repr(q).startswith("FirPfbCh2") and q.get_m() == 3 and q.get_num_channels() == 16
+
+
+@pytest.mark.parametrize("m", [5, 1, 7, 8])
+def test_fused_small_M64_analysis(m):
+    """firpfbch2 analysis M=64 on the fused small-M kernel (four time slabs per CTA): slab boundaries,
+    uneven call sizes, odd-parity starts, ragged 16-pair batches."""
+    M, K = 64, 9000
+    rng = np.random.default_rng(640 + m)
+    h = rng.standard_normal(2 * M * m).astype(np.float32)
+    x = _rand_c(rng, K * M // 2)
+    ref = _oracle_analysis(M, m, x, h=h).reshape(K, M)
+    q = yb.FirPfbCh2.new(A, M, m, h)
+    cuts = [0, 256, 513, 514, 1500, 1501 + 4096, K]
+    outs = []
+    for a, b in zip(cuts, cuts[1:]):
+        outs.append(q.execute_block(x[a * M // 2: b * M // 2]))
+        if b - a >= 256:
+            assert q.last_path() == 2, (a, b)
+    y = np.concatenate(outs).reshape(K, M)
+    scale = max(1.0, np.abs(ref).max())
+    assert_parity(y / scale, ref / scale, "small-M m=%d" % m)
+    per_frame = np.abs(y - ref).max(axis=1) / scale
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())
