@@ -12,7 +12,7 @@ fn main() {
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
 
     let mut objs = Vec::new();
-    for name in ["common", "firpfbch2", "firpfbch2_fast", "firpfbch2_synth_fast", "firpfbch", "firpfbch_fast", "firfilt", "firfilt_fast"] {
+    for name in ["common", "firpfbch2", "firpfbch2_fast", "firpfbch2_small", "firpfbch2_synth_fast", "firpfbch2_large", "firpfbch", "firpfbch_fast", "firfilt", "firfilt_fast"] {
         let src = csrc.join(format!("{name}.cu"));
         let obj = out.join(format!("{name}.o"));
         println!("cargo:rerun-if-changed={}", src.display());

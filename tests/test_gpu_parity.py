@@ -574,11 +574,11 @@ def test_api_error_behaviour():
     assert repr(q).startswith("FirPfbCh2") and q.get_m() == 3 and q.get_num_channels() == 16
 
 
-@pytest.mark.parametrize("m", [5, 1, 7, 8])
-def test_fused_small_M64_analysis(m):
-    """firpfbch2 analysis M=64 on the fused small-M kernel (four time slabs per CTA): slab boundaries,
-    uneven call sizes, odd-parity starts, ragged 16-pair batches."""
-    M, K = 64, 9000
+@pytest.mark.parametrize("M,m", [(64, 5), (64, 1), (64, 7), (64, 8), (128, 7), (128, 2), (128, 8)])
+def test_fused_small_M_analysis(M, m):
+    """firpfbch2 analysis M=64 / M=128 on the fused small-M kernel (256/M time slabs per CTA): slab
+    boundaries, uneven call sizes, odd-parity starts, ragged 16-pair batches."""
+    K = 9000
     rng = np.random.default_rng(640 + m)
     h = rng.standard_normal(2 * M * m).astype(np.float32)
     x = _rand_c(rng, K * M // 2)
@@ -592,6 +592,6 @@ def test_fused_small_M64_analysis(m):
             assert q.last_path() == 2, (a, b)
     y = np.concatenate(outs).reshape(K, M)
     scale = max(1.0, np.abs(ref).max())
-    assert_parity(y / scale, ref / scale, "small-M m=%d" % m)
+    assert_parity(y / scale, ref / scale, "small-M M=%d m=%d" % (M, m))
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())

@@ -78,13 +78,14 @@ def main():
         report("firpfbch2 synthesis M=1024 m=4 N=2^%d (path %d)" % (N.bit_length() - 1, qs.last_path()), ms, 24.0 * N, N, "samples_out")
         del x, Y, y, qa, qs
     if "small" in which:
-        M, m, N = 64, 7, 1 << 28
-        x = randc(N)
-        Y = torch.empty(2 * N, dtype=torch.complex64, device="cuda")
-        qa = yb.FirPfbCh2.new_kaiser(yb.ANALYZER, M, m, 60.0)
-        ms = timed(lambda: qa.execute_block(x, N // (M // 2), out=Y))
-        report("firpfbch2 analysis M=64 m=7 N=2^28 (path %d)" % qa.last_path(), ms, 24.0 * N, N, "samples_in")
-        del x, Y, qa
+        for M in (64, 128):
+            m, N = 7, 1 << 28
+            x = randc(N)
+            Y = torch.empty(2 * N, dtype=torch.complex64, device="cuda")
+            qa = yb.FirPfbCh2.new_kaiser(yb.ANALYZER, M, m, 60.0)
+            ms = timed(lambda: qa.execute_block(x, N // (M // 2), out=Y))
+            report("firpfbch2 analysis M=%d m=7 N=2^28 (path %d)" % (M, qa.last_path()), ms, 24.0 * N, N, "samples_in")
+            del x, Y, qa
     if "largeM" in which:
         for M, m in ((512, 7), (2048, 4), (4096, 4)):
             N = 1 << 26

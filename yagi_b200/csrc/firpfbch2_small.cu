@@ -1,14 +1,14 @@
-// firpfbch2_small.cu -- fused firpfbch2 ANALYSIS kernel for small M (M = 64), m = 1..8, sm_100a.
+// firpfbch2_small.cu -- fused firpfbch2 ANALYSIS kernel for small M (M = 64 and M = 128), m = 1..8, sm_100a.
 //
 // The M = 256 kernel (firpfbch2_fast.cu) gives one thread to every polyphase branch; with 64 branches that
 // would leave three quarters of the FIR role idle.  A single stream has no other parallelism than time, so
-// each CTA works on FOUR independent time slabs of the same stream at once ("slots", 64 FIR threads each),
+// each CTA works on 256/M independent time slabs of the same stream at once ("slots", M FIR threads each),
 // every slab primed with its own (4m-1) M/2-sample history exactly like a time shard.
 // Per slot the pipeline is the M = 256 one: TMA bulk copy of 16 frame pairs (8 KB) -> FIR role (register
 // ring, packed FFMA2 for the even and odd frame of a pair, the upper half's even taps delayed one slot) ->
 // V[pair][branch] in smem -> FFT role (8 threads per frame pair, radix-8 x radix-8 backward DFT in packed
-// (even, odd) lanes, XOR-swizzled exchange in place) -> 64-byte coalesced stores.  Slots are independent
-// pipelines with their own mbarriers.
+// (even, odd) lanes, XOR-swizzled exchange in place) -> 64-byte coalesced stores.  M = 128 uses radix-16 then
+// two radix-8 per thread.  Slots are independent pipelines with their own mbarriers.
 #include "firpfbch2_fast.cuh"
 #include "fused_common.cuh"
 
@@ -23,22 +23,26 @@ namespace {
 
 using namespace yg::dev;
 
-constexpr int kM = 64;
-constexpr int kM2 = 32;
-constexpr int kSlots = 4;                         // time slabs per CTA
 constexpr int kPairsPerBatch = 16;
 constexpr int kFirThreads = 256;
 constexpr int kThreads = 512;
-constexpr int kInSlotBytes = kPairsPerBatch * kM * 8;          // 8 KB of input per slot per batch
-constexpr int kInStageBytes = kSlots * kInSlotBytes;
-constexpr int kRegionBytes = kM * 16;                          // 1 KB: V of one pair {reE, reO, imE, imO} x 64 = its 8x8 exchange tile
-constexpr int kVSlotBytes = kPairsPerBatch * kRegionBytes;     // 16 KB
-constexpr int kVBufBytes = kSlots * kVSlotBytes;
+constexpr int kInStageBytes = kFirThreads * kPairsPerBatch * 8;      // 32 KB of input per batch (all slots)
+constexpr int kVBufBytes = kFirThreads * kPairsPerBatch * 16;        // 64 KB of V per batch (all slots)
 constexpr int kSmemBytes = 2 * kInStageBytes + 2 * kVBufBytes + 56 * 8 + 64;
 constexpr int kMbInFull = 0;      // [2][4]     TMA transaction barrier per stage and slot
-constexpr int kMbInFree = 8;      // [2][4]     the 2 FIR warps of the slot drained the stage
-constexpr int kMbVFull = 16;      // [2][4][4]  the 2 FIR warps of the slot wrote regions 4g..4g+3
-constexpr int kMbVFree = 48;      // [2][4]     the 2 FFT warps of the slot drained the buffer
+constexpr int kMbInFree = 8;      // [2][4]     the FIR warps of the slot drained the stage
+constexpr int kMbVFull = 16;      // [2][4][4]  the FIR warps of the slot wrote regions 4g..4g+3
+constexpr int kMbVFree = 48;      // [2][4]     the FFT warps of the slot drained the buffer
+
+template <int kM>
+struct Geo {
+    static constexpr int M2 = kM / 2;
+    static constexpr int slots = kFirThreads / kM;                   // time slabs per CTA
+    static constexpr int warps_per_slot = kM / 32;                   // in each role
+    static constexpr int in_slot_bytes = kPairsPerBatch * kM * 8;
+    static constexpr int region_bytes = kM * 16;                     // V of one pair {reE, reO, imE, imO} x M = its exchange tile
+    static constexpr int v_slot_bytes = kPairsPerBatch * region_bytes;
+};
 
 struct SmallParams {
     const float2* hist;       // Hlen samples preceding x[0] of the call
@@ -47,9 +51,9 @@ struct SmallParams {
     float2* y;
     long long f0;             // first frame handled here (even global parity)
     long long n_pairs;        // frame pairs handled here
-    int n_slabs;              // = gridDim.x * kSlots
-    const float2* taps;       // [64][2m+1] (even, odd) tap pairs, 1/M folded in
-    const float2* twid;       // [8][8] e^{+j 2 pi n2 k1 / 64}
+    int n_slabs;              // = gridDim.x * slots
+    const float2* taps;       // [M][2m+1] (even, odd) tap pairs, 1/M folded in
+    const float2* twid;       // [8][M/8] e^{+j 2 pi n2 k1 / M}
 };
 
 __device__ __forceinline__ constexpr int dr8(int k) { return ((k & 1) << 2) | (k >> 1); }
@@ -80,12 +84,14 @@ __device__ __forceinline__ void slab_range(const SmallParams& p, int slab, long 
     b1 = (n_batches * (slab + 1)) / p.n_slabs;
 }
 
-template <int kTaps>
+template <int kM, int kTaps>
 __device__ __forceinline__ void fir_role(const SmallParams& p, uint32_t smem, uint32_t mbar)
 {
+    using G = Geo<kM>;
+    constexpr int kM2 = G::M2, kSlots = G::slots, kInSlotBytes = G::in_slot_bytes, kRegionBytes = G::region_bytes, kVSlotBytes = G::v_slot_bytes;
     constexpr int kHist = kTaps - 1;
     const int j = threadIdx.x;
-    const int slot = j >> 6, br = j & 63;
+    const int slot = j / kM, br = j % kM;
     const int pos = (br < kM2) ? (kM2 - 1 - br) : (kM + kM2 - 1 - br);
     const bool issuer = br == 0;
     long long b0, b1;
@@ -166,21 +172,23 @@ __device__ __forceinline__ void fir_role(const SmallParams& p, uint32_t smem, ui
     }
 }
 
+template <int kM>
 __device__ __forceinline__ void fft_role(const SmallParams& p, uint32_t smem, uint32_t mbar)
 {
+    using G = Geo<kM>;
+    constexpr int kSlots = G::slots, kRegionBytes = G::region_bytes, kVSlotBytes = G::v_slot_bytes;
+    constexpr int kR1 = kM / 8;                   // first-pass radix: 8 (M = 64) or 16 (M = 128); 8 threads per pair
     const int tid = threadIdx.x - kFirThreads;
-    const int slot = tid >> 6;
-    const int wv = (tid >> 5) & 1;                // warp of the slot: regions 4wv..4wv+3, then 8+4wv..
-    const int sub = (tid >> 3) & 3;               // pair inside the warp's group of four
+    const int slot = tid / kM;
     const int t = tid & 7;
     long long b0, b1;
     slab_range(p, blockIdx.x * kSlots + slot, b0, b1);
     if (b0 >= b1) return;
 
-    float twr[8], twi[8];
+    float twr[kR1], twi[kR1];
 #pragma unroll
-    for (int kk = 0; kk < 8; kk++) {
-        const float2 tw = __ldg(&p.twid[t * 8 + kk]);
+    for (int kk = 0; kk < kR1; kk++) {
+        const float2 tw = __ldg(&p.twid[t * kR1 + kk]);
         twr[kk] = tw.x;
         twi[kk] = tw.y;
     }
@@ -190,54 +198,103 @@ __device__ __forceinline__ void fft_role(const SmallParams& p, uint32_t smem, ui
         const long long lb = batch - b0;
         const int b = (int)(lb & 1);
         const uint32_t ph = (uint32_t)((lb >> 1) & 1);
+        if constexpr (kM == 64) {
+            const int wv = (tid >> 5) & 1;            // warp of the slot: regions 4wv..4wv+3, then 8+4wv..
+            const int sub = (tid >> 3) & 3;
 #pragma unroll
-        for (int round = 0; round < 2; round++) {
-            const int g = 2 * round + wv;                                  // group of four regions
-            const int pr = 4 * g + sub;                                    // pair inside the batch
+            for (int round = 0; round < 2; round++) {
+                const int g = 2 * round + wv;
+                const int pr = 4 * g + sub;
+                const uint32_t region = vb0 + b * kVBufBytes + pr * kRegionBytes;
+                mbar_wait(mbar + 8 * (kMbVFull + 16 * b + 4 * slot + g), ph);
+                C2 v[8];
+#pragma unroll
+                for (int n1 = 0; n1 < 8; n1++) {
+                    const float4 q4 = lds128(region + (8 * n1 + t) * 16);
+                    v[n1].re = make_float2(q4.x, q4.y);
+                    v[n1].im = make_float2(q4.z, q4.w);
+                }
+                dft8(v);
+                __syncwarp();
+#pragma unroll
+                for (int k1 = 0; k1 < 8; k1++) {
+                    C2 z = v[dr8(k1)];
+                    if (k1 > 0) z = cmulw(z, twr[k1], twi[k1]);
+                    sts128(region + (((t << 3) | (k1 ^ t)) << 4), make_float4(z.re.x, z.re.y, z.im.x, z.im.y));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int n2 = 0; n2 < 8; n2++) {
+                    const float4 q4 = lds128(region + (((n2 << 3) | (t ^ n2)) << 4));
+                    v[n2].re = make_float2(q4.x, q4.y);
+                    v[n2].im = make_float2(q4.z, q4.w);
+                }
+                if (round == 1) {
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(mbar + 8 * (kMbVFree + 4 * b + slot));
+                }
+                dft8(v);
+                const long long pair = batch * kPairsPerBatch + pr;
+                if (pair < p.n_pairs) {
+                    float2* ye = p.y + (p.f0 + 2 * pair) * (long long)kM + t;
+#pragma unroll
+                    for (int k2 = 0; k2 < 8; k2++) {
+                        const C2 z = v[dr8(k2)];
+                        __stcs(ye + 8 * k2, make_float2(z.re.x, z.im.x));
+                        __stcs(ye + kM + 8 * k2, make_float2(z.re.y, z.im.y));
+                    }
+                }
+            }
+        } else {
+            // M = 128 = 16 x 8: thread n2 = t runs a radix-16 over n1, then (as k1 = t and t + 8) two radix-8 over n2
+            const int pr = (tid % kM) >> 3;           // pair inside the batch; its warp covers regions 4g..4g+3
             const uint32_t region = vb0 + b * kVBufBytes + pr * kRegionBytes;
-            mbar_wait(mbar + 8 * (kMbVFull + 16 * b + 4 * slot + g), ph);
-            C2 v[8];
+            mbar_wait(mbar + 8 * (kMbVFull + 16 * b + 4 * slot + (pr >> 2)), ph);
+            C2 v[16];
 #pragma unroll
-            for (int n1 = 0; n1 < 8; n1++) {
+            for (int n1 = 0; n1 < 16; n1++) {
                 const float4 q4 = lds128(region + (8 * n1 + t) * 16);
                 v[n1].re = make_float2(q4.x, q4.y);
                 v[n1].im = make_float2(q4.z, q4.w);
             }
-            dft8(v);
+            dft16(v);
             __syncwarp();
 #pragma unroll
-            for (int k1 = 0; k1 < 8; k1++) {
-                C2 z = v[dr8(k1)];
+            for (int k1 = 0; k1 < 16; k1++) {
+                C2 z = v[dr4(k1)];
                 if (k1 > 0) z = cmulw(z, twr[k1], twi[k1]);
-                sts128(region + (((t << 3) | (k1 ^ t)) << 4), make_float4(z.re.x, z.re.y, z.im.x, z.im.y));
+                sts128(region + (((t << 4) | (k1 ^ t)) << 4), make_float4(z.re.x, z.re.y, z.im.x, z.im.y));   // row n2, 16 columns
             }
             __syncwarp();
+            C2 va[8], vb[8];
 #pragma unroll
             for (int n2 = 0; n2 < 8; n2++) {
-                const float4 q4 = lds128(region + (((n2 << 3) | (t ^ n2)) << 4));
-                v[n2].re = make_float2(q4.x, q4.y);
-                v[n2].im = make_float2(q4.z, q4.w);
+                const float4 qa = lds128(region + (((n2 << 4) | (t ^ n2)) << 4));
+                const float4 qb = lds128(region + (((n2 << 4) | ((t ^ n2) + 8)) << 4));
+                va[n2].re = make_float2(qa.x, qa.y); va[n2].im = make_float2(qa.z, qa.w);
+                vb[n2].re = make_float2(qb.x, qb.y); vb[n2].im = make_float2(qb.z, qb.w);
             }
-            if (round == 1) {
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(mbar + 8 * (kMbVFree + 4 * b + slot));
-            }
-            dft8(v);
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(mbar + 8 * (kMbVFree + 4 * b + slot));
+            dft8(va);
+            dft8(vb);
             const long long pair = batch * kPairsPerBatch + pr;
             if (pair < p.n_pairs) {
                 float2* ye = p.y + (p.f0 + 2 * pair) * (long long)kM + t;
 #pragma unroll
                 for (int k2 = 0; k2 < 8; k2++) {
-                    const C2 z = v[dr8(k2)];
-                    __stcs(ye + 8 * k2, make_float2(z.re.x, z.im.x));
-                    __stcs(ye + kM + 8 * k2, make_float2(z.re.y, z.im.y));
+                    const C2 za = va[dr8(k2)], zb = vb[dr8(k2)];
+                    __stcs(ye + 16 * k2, make_float2(za.re.x, za.im.x));
+                    __stcs(ye + 16 * k2 + 8, make_float2(zb.re.x, zb.im.x));
+                    __stcs(ye + kM + 16 * k2, make_float2(za.re.y, za.im.y));
+                    __stcs(ye + kM + 16 * k2 + 8, make_float2(zb.re.y, zb.im.y));
                 }
             }
         }
     }
 }
 
-template <int kTaps>
+template <int kM, int kTaps>
 __global__ void __launch_bounds__(kThreads, 1) k_firpfbch2_analysis_small(const SmallParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -246,26 +303,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_firpfbch2_analysis_small(const 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; i++) {
             mbar_init(mbar + 8 * (kMbInFull + i), 1);
-            mbar_init(mbar + 8 * (kMbInFree + i), 2);
-            mbar_init(mbar + 8 * (kMbVFree + i), 2);
+            mbar_init(mbar + 8 * (kMbInFree + i), Geo<kM>::warps_per_slot);
+            mbar_init(mbar + 8 * (kMbVFree + i), Geo<kM>::warps_per_slot);
         }
-        for (int i = 0; i < 32; i++) mbar_init(mbar + 8 * (kMbVFull + i), 2);
+        for (int i = 0; i < 32; i++) mbar_init(mbar + 8 * (kMbVFull + i), Geo<kM>::warps_per_slot);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x < kFirThreads) fir_role<kTaps>(p, smem, mbar);
-    else fft_role(p, smem, mbar);
+    if (threadIdx.x < kFirThreads) fir_role<kM, kTaps>(p, smem, mbar);
+    else fft_role<kM>(p, smem, mbar);
 }
 
-template <int kTaps>
+template <int kM, int kTaps>
 int32_t launch_t(const Firpfbch2FastPlan& plan, SmallParams p, cudaStream_t st)
 {
-    YG_CUDA(cudaFuncSetAttribute(k_firpfbch2_analysis_small<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    constexpr int kSlots = Geo<kM>::slots;
+    YG_CUDA(cudaFuncSetAttribute(k_firpfbch2_analysis_small<kM, kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     const long long n_batches = (p.n_pairs + kPairsPerBatch - 1) / kPairsPerBatch;
     const int grid = (int)std::min<long long>(plan.n_sm, (n_batches + kSlots - 1) / kSlots);
     p.n_slabs = grid * kSlots;
-    k_firpfbch2_analysis_small<kTaps><<<grid, kThreads, kSmemBytes, st>>>(p);
+    k_firpfbch2_analysis_small<kM, kTaps><<<grid, kThreads, kSmemBytes, st>>>(p);
     YG_CUDA(cudaGetLastError());
     return YG_OK;
 }
@@ -277,32 +335,34 @@ int32_t firpfbch2_small_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
     plan.supported = false;
     plan.M = M;
     plan.m = m;
-    if (M != (uint32_t)kM || m < 1 || m > 8) return YG_OK;
+    if ((M != 64 && M != 128) || m < 1 || m > 8) return YG_OK;
     int dev = 0;
     YG_CUDA(cudaGetDevice(&dev));
     cudaDeviceProp prop;
     YG_CUDA(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) return YG_OK;
     plan.n_sm = prop.multiProcessorCount;
+    const int iM = (int)M, iM2 = iM / 2;
     const int kTaps = 2 * (int)m + 1, P = 2 * (int)m;
-    std::vector<float2> taps((size_t)kM * kTaps);
-    const float s = 1.0f / (float)kM;
-    for (int j = 0; j < kM; j++)
+    std::vector<float2> taps((size_t)iM * kTaps);
+    const float s = 1.0f / (float)iM;
+    for (int j = 0; j < iM; j++)
         for (int i = 0; i < kTaps; i++) {
             float te = 0.f, to = 0.f;
-            if (j < kM2) {
-                if (i < P) { te = h[j + i * kM]; to = h[j + kM2 + i * kM]; }
+            if (j < iM2) {
+                if (i < P) { te = h[j + i * iM]; to = h[j + iM2 + i * iM]; }
             } else {
-                if (i >= 1) te = h[j + (i - 1) * kM];
-                if (i < P) to = h[j - kM2 + i * kM];
+                if (i >= 1) te = h[j + (i - 1) * iM];
+                if (i < P) to = h[j - iM2 + i * iM];
             }
             taps[(size_t)j * kTaps + i] = make_float2(te * s, to * s);
         }
-    std::vector<float2> tw(64);
+    const int R1 = iM / 8;                                   // twiddles e^{+j 2 pi n2 k1 / M}, n2 < 8, k1 < M/8
+    std::vector<float2> tw((size_t)8 * R1);
     for (int n2 = 0; n2 < 8; n2++)
-        for (int k1 = 0; k1 < 8; k1++) {
-            const double a = 2.0 * M_PI * (double)(n2 * k1) / 64.0;
-            tw[n2 * 8 + k1] = make_float2((float)cos(a), (float)sin(a));
+        for (int k1 = 0; k1 < R1; k1++) {
+            const double a = 2.0 * M_PI * (double)(n2 * k1) / (double)iM;
+            tw[(size_t)n2 * R1 + k1] = make_float2((float)cos(a), (float)sin(a));
         }
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float2)));
     YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
@@ -313,13 +373,31 @@ int32_t firpfbch2_small_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
     return YG_OK;
 }
 
+namespace {
+template <int kM>
+int32_t launch_m(const Firpfbch2FastPlan& plan, const SmallParams& p, cudaStream_t st)
+{
+    switch (plan.m) {
+        case 1: return launch_t<kM, 3>(plan, p, st);
+        case 2: return launch_t<kM, 5>(plan, p, st);
+        case 3: return launch_t<kM, 7>(plan, p, st);
+        case 4: return launch_t<kM, 9>(plan, p, st);
+        case 5: return launch_t<kM, 11>(plan, p, st);
+        case 6: return launch_t<kM, 13>(plan, p, st);
+        case 7: return launch_t<kM, 15>(plan, p, st);
+        case 8: return launch_t<kM, 17>(plan, p, st);
+        default: return fail(YG_EINTERNAL, "fused kernel not instantiated for m = %u", plan.m);
+    }
+}
+}  // namespace
+
 int32_t firpfbch2_small_launch(const Firpfbch2FastPlan& plan, const float2* hist, long long Hlen, const float2* x, float2* y,
                                size_t f0, size_t n_frames, cudaStream_t st)
 {
     if (!plan.supported) return fail(YG_EINTERNAL, "small-M fused kernel not available for this geometry");
     if (n_frames == 0) return YG_OK;
     if (n_frames & 1) return fail(YG_EINTERNAL, "fused kernel needs an even number of frames");
-    if (((uintptr_t)(x + f0 * kM2) & 15) != 0) return fail(YG_EVALUE, "input pointer must be 16-byte aligned");
+    if (((uintptr_t)(x + f0 * (plan.M / 2)) & 15) != 0) return fail(YG_EVALUE, "input pointer must be 16-byte aligned");
     SmallParams p;
     p.hist = hist; p.Hlen = Hlen; p.x = x; p.y = y;
     p.f0 = (long long)f0;
@@ -327,17 +405,7 @@ int32_t firpfbch2_small_launch(const Firpfbch2FastPlan& plan, const float2* hist
     p.n_slabs = 0;
     p.taps = reinterpret_cast<const float2*>(plan.d_taps);
     p.twid = reinterpret_cast<const float2*>(plan.d_twid);
-    switch (plan.m) {
-        case 1: return launch_t<3>(plan, p, st);
-        case 2: return launch_t<5>(plan, p, st);
-        case 3: return launch_t<7>(plan, p, st);
-        case 4: return launch_t<9>(plan, p, st);
-        case 5: return launch_t<11>(plan, p, st);
-        case 6: return launch_t<13>(plan, p, st);
-        case 7: return launch_t<15>(plan, p, st);
-        case 8: return launch_t<17>(plan, p, st);
-        default: return fail(YG_EINTERNAL, "fused kernel not instantiated for m = %u", plan.m);
-    }
+    return plan.M == 64 ? launch_m<64>(plan, p, st) : launch_m<128>(plan, p, st);
 }
 
 }  // namespace yg
