@@ -311,7 +311,10 @@ void firpfbch2_fast_release(Firpfbch2FastPlan& p)
 {
     if (p.d_taps) cudaFree(p.d_taps);
     if (p.d_twid) cudaFree(p.d_twid);
-    p.d_taps = p.d_twid = nullptr;
+    if (p.d_scratch) cudaFree(p.d_scratch);
+    if (p.d_flags) cudaFree(p.d_flags);
+    p.d_taps = p.d_twid = p.d_scratch = p.d_flags = nullptr;
+    p.n_groups = 0;
     p.supported = false;
 }
 

@@ -8,7 +8,8 @@
 //                           into the output frames;
 //   stage B (k_large_fft):  in-place M-point backward DFT of every frame: for M = 1024 one warp per frame,
 //                           32 x 32 with a radix-32 in registers and one XOR-swizzled shared exchange;
-//                           for the other sizes one CTA per frame (shared-memory radix-4 Stockham).
+//                           M = 2048 / 4096 add one decimation-in-frequency step (2 / 4 warps per frame);
+//                           M = 512 runs 16 x 32 with one warp per pair of frames.
 // The host walks the call in chunks whose output (8 KB per frame) fits in L2, so V is written and read
 // back in cache and HBM sees the algorithmic 24 B per input sample.
 #include "firpfbch2_fast.cuh"
@@ -155,86 +156,399 @@ __device__ __forceinline__ void xdft32(float2 (&v)[32], const float2* w32 /* e^{
     xdft16<16>(v);
 }
 
-constexpr int kM = 1024;                         // the warp-per-frame DFT kernel below is the M = 1024 instance
-constexpr int kFftWarps = 8;                     // frames per CTA
+constexpr int kFftWarps = 8;                     // warps per CTA, one 1024-point transform each
 constexpr int kFftSmem = kFftWarps * 1024 * 8 + 16 * 8;
 
+// ---- warp-level transforms.  M = 1024 S (S = 1, 2, 4): one decimation-in-frequency step splits a frame into S
+// interleaved 1024-point transforms, X[S k + r] = DFT1024{ (sum_q x[1024 q + n] W_S^{q r}) W_M^{n r} }[k]; a warp takes
+// one (frame, r) item: 32 x 32 with a radix-32 in registers and one XOR-swizzled 8 KB shared exchange tile.
+// kCg: the source was written by other SMs during this launch (fused kernel) -> read through L2 (ld.global.cg).
+template <bool kCg>
+__device__ __forceinline__ float2 ldv(const float2* p) { return kCg ? __ldcg(p) : *p; }
+
+template <int S, bool kCg>
+__device__ __forceinline__ void fft_load(float2 (&v)[32], const float2* src, int r, const float2* __restrict__ twid, int lane)
+{
+    float2 ws[S];                                                        // W_S^{q r}
+#pragma unroll
+    for (int q = 0; q < S; q++) ws[q] = __ldg(&twid[((q * r) & (S - 1)) * 1024]);
+    // lane n2 gathers x[32 n1 + n2]: 256-byte coalesced rows, L2 hits (written by the FIR stage)
+#pragma unroll
+    for (int n1 = 0; n1 < 32; n1++) {
+        const int n = 32 * n1 + lane;
+        float2 a = ldv<kCg>(src + n);
+        if (S > 1) {
+#pragma unroll
+            for (int q = 1; q < S; q++) {
+                const float2 z = ldv<kCg>(src + 1024 * q + n);
+                if (S == 2) a = r ? xsub(a, z) : xadd(a, z);
+                else a = xadd(a, xmul(z, ws[q].x, ws[q].y));
+            }
+            const float2 w = __ldg(&twid[n * r]);
+            a = xmul(a, w.x, w.y);
+        }
+        v[n1] = a;
+    }
+}
+
+template <int S>
+__device__ __forceinline__ void fft_compute(float2 (&v)[32], uint32_t tile, const float2* w32, const float2* __restrict__ twid, int lane)
+{
+    xdft32(v, w32);
+    // twiddle by W1024^{n2 k1}, write row n2 of the swizzled tile
+#pragma unroll
+    for (int k1 = 0; k1 < 32; k1++) {
+        float2 z = v[dr32(k1)];
+        if (k1 > 0) { const float2 w = __ldg(&twid[lane * k1 * S]); z = xmul(z, w.x, w.y); }
+        sts64(tile + (((lane << 5) | (k1 ^ lane)) << 3), z);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; n2++) v[n2] = lds64(tile + (((n2 << 5) | (lane ^ n2)) << 3));
+    __syncwarp();
+    xdft32(v, w32);
+}
+
+template <int S>
+__device__ __forceinline__ void fft_store(const float2 (&v)[32], float2* fr, int r, int lane, int streaming_store)
+{
+    if (streaming_store) {
+#pragma unroll
+        for (int k2 = 0; k2 < 32; k2++) __stcs(fr + S * (lane + 32 * k2) + r, v[dr32(k2)]);
+    } else {                                                             // keep U in L2 for the overlap-add stage
+#pragma unroll
+        for (int k2 = 0; k2 < 32; k2++) fr[S * (lane + 32 * k2) + r] = v[dr32(k2)];
+    }
+}
+
+// M = 512 = 16 x 32: one warp per PAIR of frames.  Pass 1: lane n2 runs the 16-point transforms over n1 of both
+// frames; pass 2: lane (frame, k1) runs one 32-point transform over n2.  Same 8 KB swizzled tile per warp.
+template <bool kCg>
+__device__ __forceinline__ void fft512_load(float2 (&v)[32], const float2* src0, const float2* src1, int lane)
+{
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) v[n1] = ldv<kCg>(src0 + 32 * n1 + lane);
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) v[16 + n1] = ldv<kCg>(src1 + 32 * n1 + lane);
+}
+
+__device__ __forceinline__ void fft512_compute(float2 (&v)[32], uint32_t tile, const float2* w32, const float2* __restrict__ twid, int lane)
+{
+    xdft16<0>(v);
+    xdft16<16>(v);
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) {
+            float2 z = v[16 * h + dr4(k1)];
+            if (k1 > 0) { const float2 w = __ldg(&twid[lane * k1]); z = xmul(z, w.x, w.y); }
+            sts64(tile + (((h << 9) | (lane << 4) | (k1 ^ (lane & 15))) << 3), z);
+        }
+    __syncwarp();
+    const int h = lane >> 4, k1 = lane & 15;
+#pragma unroll
+    for (int n2 = 0; n2 < 32; n2++) v[n2] = lds64(tile + (((h << 9) | (n2 << 4) | (k1 ^ (n2 & 15))) << 3));
+    __syncwarp();
+    xdft32(v, w32);
+}
+
+// lane (h, k1) holds X_h[k1 + 16 k2]; `fr` = frame h of the pair (nullptr: frame beyond the end)
+__device__ __forceinline__ void fft512_store(const float2 (&v)[32], float2* fr, int lane, int streaming_store)
+{
+    if (!fr) return;
+    fr += lane & 15;
+    if (streaming_store) {
+#pragma unroll
+        for (int k2 = 0; k2 < 32; k2++) __stcs(fr + 16 * k2, v[dr32(k2)]);
+    } else {
+#pragma unroll
+        for (int k2 = 0; k2 < 32; k2++) fr[16 * k2] = v[dr32(k2)];
+    }
+}
+
+// ------------------------------------------------------------------ stage B kernels (two-stage path)
 // Frame f of the launch is read from the virtual stream (prefix ++ x) at index v0 + f (negative indices
 // live in the 32-frame prefix) and written to dst frame f.  The analysis path calls it in place
-// (x == dst, v0 == 0); the synthesis path transforms input frames into the U scratch.
+// (x == dst, v0 == 0): the S warps of a frame (neighbours in one CTA) meet on a named barrier between
+// their loads and their stores.  The synthesis path transforms input frames into the U scratch.
+template <int S>
 __global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft(const float2* prefix, const float2* x, long long v0,
                                                                  float2* dst, long long n_frames,
                                                                  const float2* __restrict__ twid, int streaming_store)
 {
+    constexpr int kM = 1024 * S;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* w32 = reinterpret_cast<float2*>(smem_raw + kFftWarps * 1024 * 8);
-    if (threadIdx.x < 16) w32[threadIdx.x] = __ldg(&twid[threadIdx.x * 32]);
+    if (threadIdx.x < 16) w32[threadIdx.x] = __ldg(&twid[threadIdx.x * 32 * S]);
     __syncthreads();
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    const uint32_t tile = smem_u32(smem_raw) + wrp * 8192;               // 32 x 32 exchange tile of 8-byte units
-    for (long long f = (long long)blockIdx.x * kFftWarps + wrp; f < n_frames; f += (long long)gridDim.x * kFftWarps) {
+    const int r = wrp & (S - 1);                                         // residue this warp produces
+    const uint32_t tile = smem_u32(smem_raw) + wrp * 8192;
+    const long long n_items = n_frames * S;
+    for (long long it = (long long)blockIdx.x * kFftWarps + wrp; it < n_items; it += (long long)gridDim.x * kFftWarps) {
+        const long long f = it / S;
         const long long vi = v0 + f;
         const float2* src = (vi < 0) ? prefix + (32 + vi) * kM : x + vi * kM;
-        float2* fr = dst + f * kM;
         float2 v[32];
-        // pass 1: lane n2 gathers X[32 n1 + n2] (256-byte coalesced rows, L2 hits: written by stage A)
+        fft_load<S, false>(v, src, r, twid, lane);
+        fft_compute<S>(v, tile, w32, twid, lane);
+        if (S > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + wrp / S), "r"(S * 32) : "memory");
+        fft_store<S>(v, dst + f * kM, r, lane, streaming_store);
+    }
+}
+
+__global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft512(const float2* prefix, const float2* x, long long v0,
+                                                                    float2* dst, long long n_frames,
+                                                                    const float2* __restrict__ twid, int streaming_store)
+{
+    constexpr int kM = 512;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* w32 = reinterpret_cast<float2*>(smem_raw + kFftWarps * 1024 * 8);
+    if (threadIdx.x < 16) w32[threadIdx.x] = __ldg(&twid[threadIdx.x * 16]);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const uint32_t tile = smem_u32(smem_raw) + wrp * 8192;
+    const long long n_pairs = (n_frames + 1) >> 1;
+    for (long long pr = (long long)blockIdx.x * kFftWarps + wrp; pr < n_pairs; pr += (long long)gridDim.x * kFftWarps) {
+        const float2* src[2];
 #pragma unroll
-        for (int n1 = 0; n1 < 32; n1++) v[n1] = src[32 * n1 + lane];
-        xdft32(v, w32);
-        // twiddle by W1024^{n2 k1}, write row n2 of the swizzled tile
-#pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) {
-            float2 z = v[dr32(k1)];
-            if (k1 > 0) { const float2 w = __ldg(&twid[lane * k1]); z = xmul(z, w.x, w.y); }
-            sts64(tile + (((lane << 5) | (k1 ^ lane)) << 3), z);
+        for (int h = 0; h < 2; h++) {
+            const long long vi = v0 + min(2 * pr + h, n_frames - 1);     // an odd tail recomputes the last frame
+            src[h] = (vi < 0) ? prefix + (32 + vi) * kM : x + vi * kM;
         }
-        __syncwarp();
+        float2 v[32];
+        fft512_load<false>(v, src[0], src[1], lane);
+        fft512_compute(v, tile, w32, twid, lane);
+        const long long f = 2 * pr + (lane >> 4);
+        fft512_store(v, f < n_frames ? dst + f * kM : nullptr, lane, streaming_store);
+    }
+}
+
+// ------------------------------------------------------------------ fused kernel: one launch, groups of M/256 CTAs
+// A GROUP of G = M / 256 persistent CTAs walks a contiguous slab of 16-pair batches.  In every CTA warps 0-7
+// are the FIR role of stage A for 256 of the M branches, warps 8-15 transform whole frames (stage B): the
+// 32 frames of a batch are 8 G warp items (M = 512: 16 frame pairs; M = 1024 S: 32 S (frame, residue) items),
+// one per DFT warp of the group.  The branch sums cross the group through a small per-group ring of V batches
+// in global memory that never leaves L2 (kSlots x 32 frames x 8 M bytes per group, 18 MB for the whole grid),
+// guarded by two monotone counters per slot: full (one release-add per FIR warp of the group per use) and
+// free (one per DFT warp, after its loads of the slot have landed).  HBM sees the algorithmic 24 B per input
+// sample; the launch is cooperative so that every member of a group is resident while the others wait for it.
+constexpr int kSlots = 4;
+constexpr int kInStageBytes = kPairsPerBatch * kFirThreads * 8;      // 32 KB: one batch of input for 256 branches
+constexpr int kFusedSmem = kFftSmem + 2 * kInStageBytes;
+constexpr int kFlagStride = 32;                  // 128 B of counters per group: full[kSlots], free[kSlots]
+
+struct FusedParams {
+    LargeParams base;                            // pair_begin .. pair_end: whole batches
+    float2* scratch;                             // [n_groups][kSlots][32][M]
+    unsigned* flags;                             // [n_groups][kFlagStride], zero at launch
+    int n_groups;
+};
+
+// The V ring is written with st.global.cg and read with ld.global.cg (L2 on both sides), so the waiters poll
+// with relaxed loads: an acquire load would flush the SM's L1 (CCTL.IVALL) on every poll for nothing.
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// producer side: the warp's V stores, then one release-add by lane 0 (the grid-sync idiom: barrier, fence, atomic)
+__device__ __forceinline__ void warp_publish(unsigned* p, int lane)
+{
+    __syncwarp();
+    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+// consumer side: every lane has USED the values it loaded from the slot (so the loads have landed); nothing to flush
+__device__ __forceinline__ void warp_retire(unsigned* p, int lane)
+{
+    __syncwarp();
+    if (lane == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ void warp_wait(const unsigned* p, unsigned target, int lane)
+{
+    if (lane == 0) {
+        unsigned spins = 0;
+        while (ld_relaxed_gpu(p) < target) {
+            if (++spins > (1u << 27)) __trap();  // seconds without progress: fail the launch rather than hang the GPU
+        }
+    }
+    __syncwarp();
+}
+
+template <int kTaps>
+__device__ __forceinline__ void fused_fir_role(const FusedParams& fp, int group, int c, long long b0, long long b1,
+                                               uint32_t smem_in)
+{
+    const LargeParams& p = fp.base;
+    constexpr int kHist = kTaps - 1;
+    const int kM = p.M, kM2 = p.M >> 1;
+    const int lane = threadIdx.x & 31;
+    const int j = c * kFirThreads + threadIdx.x;                          // branch
+    const int pos = (j < kM2) ? (kM2 - 1 - j) : (kM + kM2 - 1 - j);
+    const unsigned n_dft_warps = (unsigned)(kFftWarps * (kM / kFirThreads));
+    unsigned* flags = fp.flags + group * kFlagStride;
+    float2* sbase = fp.scratch + (long long)group * kSlots * 32 * kM + j;
+
+    float2 T[kTaps];
 #pragma unroll
-        for (int n2 = 0; n2 < 32; n2++) v[n2] = lds64(tile + (((n2 << 5) | (lane ^ n2)) << 3));
-        __syncwarp();
-        xdft32(v, w32);
-        if (streaming_store) {
+    for (int i = 0; i < kTaps; i++) T[i] = __ldg(&p.taps[j * kTaps + i]);
+
+    const long long call_off = p.f0 * kM2;
+    auto sample = [&](long long q) {
+        const long long ta = q * kM + pos + call_off;
+        if (ta >= 0) return __ldg(&p.x[ta]);
+        if (p.Hlen + ta >= 0) return __ldg(&p.hist[p.Hlen + ta]);
+        return make_float2(0.f, 0.f);
+    };
+
+    float2 W[32];
 #pragma unroll
-            for (int k2 = 0; k2 < 32; k2++) __stcs(fr + lane + 32 * k2, v[dr32(k2)]);
-        } else {                                                         // keep U in L2 for the overlap-add stage
+    for (int i = 0; i < 32; i++) W[i] = make_float2(0.f, 0.f);
+    const long long q_first = p.pair_begin + b0 * kPairsPerBatch;
 #pragma unroll
-            for (int k2 = 0; k2 < 32; k2++) fr[lane + 32 * k2] = v[dr32(k2)];
+    for (int i = 1; i <= kHist; i++) W[(32 - i) & 31] = sample(q_first - i);
+
+    // input staging: every lane copies the 16 samples of its own branch for the next batch into its private
+    // column of a double-buffered shared stage with cp.async (nothing outstanding in the LSU when the V slot is
+    // published, no registers held across the batch, no cross-thread hand-off)
+    const uint32_t stage0 = smem_in + threadIdx.x * 8;
+    const float2* xs = p.x + (p.pair_begin * (long long)kM + pos + call_off);     // sample of pair 0 of the launch
+    auto prefetch = [&](long long batch, int st) {
+        const float2* src = xs + batch * (long long)(kPairsPerBatch * kM);
+#pragma unroll
+        for (int r = 0; r < kPairsPerBatch; r++)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(stage0 + st * kInStageBytes + r * (kFirThreads * 8)),
+                         "l"(src + (long long)r * kM) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(b0, 0);
+
+    auto do_batch = [&](auto par_tag, long long batch) {
+        constexpr int PAR = decltype(par_tag)::value;
+        const long long lb = batch - b0;
+        const int slot = (int)(lb % kSlots);
+        const unsigned use = (unsigned)(lb / kSlots);
+        if (batch + 1 < b1) {
+            prefetch(batch + 1, PAR ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+#pragma unroll
+        for (int r = 0; r < kPairsPerBatch; r++) W[16 * PAR + r] = lds64(stage0 + PAR * kInStageBytes + r * (kFirThreads * 8));
+        if (use) warp_wait(flags + kSlots + slot, use * n_dft_warps, lane);      // the slot's previous batch has been read
+        float2* vb = sbase + (long long)slot * 32 * kM;
+#pragma unroll
+        for (int r = 0; r < kPairsPerBatch; r++) {
+            float2 are = make_float2(0.f, 0.f), aim = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = kTaps - 1; i >= 0; i--) {
+                const float2 w = W[(16 * PAR + r - i) & 31];
+                are = fma2(T[i], f2(w.x), are);
+                aim = fma2(T[i], f2(w.y), aim);
+            }
+            __stcg(vb + (long long)(2 * r) * kM, make_float2(are.x, aim.x));
+            __stcg(vb + (long long)(2 * r + 1) * kM, make_float2(are.y, aim.y));
+        }
+        warp_publish(flags + slot, lane);
+    };
+    for (long long batch = b0; batch < b1; batch += 2) {
+        do_batch(std::integral_constant<int, 0>{}, batch);
+        if (batch + 1 < b1) do_batch(std::integral_constant<int, 1>{}, batch + 1);
+    }
+}
+
+__device__ __forceinline__ void fused_dft_role(const FusedParams& fp, int group, int c, long long b0, long long b1,
+                                               uint32_t tile, const float2* w32)
+{
+    const LargeParams& p = fp.base;
+    const int kM = p.M;
+    const int lane = threadIdx.x & 31;
+    const int item = c * kFftWarps + ((threadIdx.x >> 5) - kFirThreads / 32);
+    const unsigned n_fir_warps = (unsigned)((kFirThreads / 32) * (kM / kFirThreads));
+    unsigned* flags = fp.flags + group * kFlagStride;
+    const float2* sbase = fp.scratch + (long long)group * kSlots * 32 * kM;
+    for (long long batch = b0; batch < b1; batch++) {
+        const long long lb = batch - b0;
+        const int slot = (int)(lb % kSlots);
+        const unsigned use = (unsigned)(lb / kSlots);
+        const float2* vb = sbase + (long long)slot * 32 * kM;
+        float2* yb = p.y + (p.f0 + 2 * (p.pair_begin + batch * kPairsPerBatch)) * (long long)kM;
+        warp_wait(flags + slot, (use + 1) * n_fir_warps, lane);
+        float2 v[32];
+        if (kM == 512) {
+            fft512_load<true>(v, vb + (2 * item) * 512, vb + (2 * item + 1) * 512, lane);
+            fft512_compute(v, tile, w32, p.twid, lane);
+            warp_retire(flags + kSlots + slot, lane);
+            fft512_store(v, yb + (2 * item + (lane >> 4)) * 512, lane, 1);
+        } else if (kM == 1024) {
+            fft_load<1, true>(v, vb + item * 1024, 0, p.twid, lane);
+            fft_compute<1>(v, tile, w32, p.twid, lane);
+            warp_retire(flags + kSlots + slot, lane);
+            fft_store<1>(v, yb + item * 1024, 0, lane, 1);
+        } else if (kM == 2048) {
+            fft_load<2, true>(v, vb + (item >> 1) * 2048, item & 1, p.twid, lane);
+            fft_compute<2>(v, tile, w32, p.twid, lane);
+            warp_retire(flags + kSlots + slot, lane);
+            fft_store<2>(v, yb + (item >> 1) * 2048, item & 1, lane, 1);
+        } else {
+            fft_load<4, true>(v, vb + (item >> 2) * 4096, item & 3, p.twid, lane);
+            fft_compute<4>(v, tile, w32, p.twid, lane);
+            warp_retire(flags + kSlots + slot, lane);
+            fft_store<4>(v, yb + (item >> 2) * 4096, item & 3, lane, 1);
         }
     }
 }
 
-
-// Other sizes: one CTA per frame, shared-memory radix-4 Stockham (block_dft in common.cuh).
-__global__ void k_large_fft_block(const float2* prefix, const float2* x, long long v0, float2* dst, long long n_frames,
-                                  int M, const float2* __restrict__ twid, int streaming_store)
+template <int kTaps>
+__global__ void __launch_bounds__(kFirThreads + kFftWarps * 32, 1) k_large_fused(const FusedParams fp)
 {
-    extern __shared__ float2 sm_blk[];
-    float2* X = sm_blk;
-    float2* Y = sm_blk + M;
-    for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
-        const long long vi = v0 + f;
-        const float2* src = (vi < 0) ? prefix + (32 + vi) * M : x + vi * M;
-        float2* fr = dst + f * M;
-        for (int c = threadIdx.x; c < M; c += blockDim.x) X[c] = src[c];
-        const float2* r = block_dft(X, Y, (uint32_t)M, twid, 1);
-        if (streaming_store) for (int c = threadIdx.x; c < M; c += blockDim.x) __stcs(fr + c, r[c]);
-        else for (int c = threadIdx.x; c < M; c += blockDim.x) fr[c] = r[c];
-        __syncthreads();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* w32 = reinterpret_cast<float2*>(smem_raw + kFftWarps * 1024 * 8);
+    if (threadIdx.x < 16) w32[threadIdx.x] = __ldg(&fp.base.twid[threadIdx.x * (fp.base.M >> 5)]);
+    __syncthreads();
+    const int G = fp.base.M / kFirThreads;
+    const int group = blockIdx.x / G, c = blockIdx.x % G;
+    const long long n_batches = (fp.base.pair_end - fp.base.pair_begin) / kPairsPerBatch;
+    const long long b0 = (n_batches * group) / fp.n_groups, b1 = (n_batches * (group + 1)) / fp.n_groups;
+    if (threadIdx.x < kFirThreads) fused_fir_role<kTaps>(fp, group, c, b0, b1, smem_u32(smem_raw) + kFftSmem);
+    else fused_dft_role(fp, group, c, b0, b1, smem_u32(smem_raw) + ((threadIdx.x >> 5) - kFirThreads / 32) * 8192, w32);
+}
+
+template <int kTaps>
+int32_t launch_fused(const FusedParams& fp, cudaStream_t st)
+{
+    static bool attr_set[64] = {};
+    int dev = 0;
+    YG_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        YG_CUDA(cudaFuncSetAttribute(k_large_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
+        attr_set[dev] = true;
     }
+    void* args[] = {const_cast<FusedParams*>(&fp)};
+    const int G = fp.base.M / kFirThreads;
+    YG_CUDA(cudaLaunchCooperativeKernel((const void*)k_large_fused<kTaps>, dim3((unsigned)(G * fp.n_groups)),
+                                        dim3(kFirThreads + kFftWarps * 32), args, (size_t)kFusedSmem, st));
+    return YG_OK;
 }
 
 int32_t launch_fft(const Firpfbch2FastPlan& plan, const float2* prefix, const float2* x, long long v0, float2* dst,
                    long long n_frames, int streaming, cudaStream_t st)
 {
     const float2* tw = reinterpret_cast<const float2*>(plan.d_twid);
-    if (plan.M == (uint32_t)kM) {
-        const int grid = (int)std::min<long long>((n_frames + kFftWarps - 1) / kFftWarps, (long long)plan.n_sm * 2);
-        k_large_fft<<<grid, kFftWarps * 32, kFftSmem, st>>>(prefix, x, v0, dst, n_frames, tw, streaming);
+    if (plan.M >= 1024) {
+        const long long items = n_frames * (plan.M >> 10);
+        const int grid = (int)std::min<long long>((items + kFftWarps - 1) / kFftWarps, (long long)plan.n_sm * 2);
+        if (plan.M == 1024) k_large_fft<1><<<grid, kFftWarps * 32, kFftSmem, st>>>(prefix, x, v0, dst, n_frames, tw, streaming);
+        else if (plan.M == 2048) k_large_fft<2><<<grid, kFftWarps * 32, kFftSmem, st>>>(prefix, x, v0, dst, n_frames, tw, streaming);
+        else k_large_fft<4><<<grid, kFftWarps * 32, kFftSmem, st>>>(prefix, x, v0, dst, n_frames, tw, streaming);
+    } else if (plan.M == 512) {
+        const long long items = (n_frames + 1) >> 1;
+        const int grid = (int)std::min<long long>((items + kFftWarps - 1) / kFftWarps, (long long)plan.n_sm * 2);
+        k_large_fft512<<<grid, kFftWarps * 32, kFftSmem, st>>>(prefix, x, v0, dst, n_frames, tw, streaming);
     } else {
-        const int M = (int)plan.M;
-        const size_t smem = 2 * (size_t)M * sizeof(float2);
-        const int grid = (int)std::min<long long>(n_frames, (long long)plan.n_sm * 8);
-        k_large_fft_block<<<grid, 256, smem, st>>>(prefix, x, v0, dst, n_frames, M, tw, streaming);
+        return fail(YG_EINTERNAL, "large-M path: no transform for M = %u", plan.M);
     }
     YG_CUDA(cudaGetLastError());
     return YG_OK;
@@ -358,11 +672,26 @@ int32_t plan_common(Firpfbch2FastPlan& plan, uint32_t M)
     }
     YG_CUDA(cudaMalloc(&plan.d_twid, tw.size() * sizeof(float2)));
     YG_CUDA(cudaMemcpy(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    if (M == (uint32_t)kM) YG_CUDA(cudaFuncSetAttribute(k_large_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
-    else if (2 * (size_t)M * sizeof(float2) > 48 * 1024)
-        YG_CUDA(cudaFuncSetAttribute(k_large_fft_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * (size_t)M * sizeof(float2))));
+    if (M == 1024) YG_CUDA(cudaFuncSetAttribute(k_large_fft<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
+    else if (M == 2048) YG_CUDA(cudaFuncSetAttribute(k_large_fft<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
+    else if (M == 512) YG_CUDA(cudaFuncSetAttribute(k_large_fft512, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
+    else if (M == 4096) YG_CUDA(cudaFuncSetAttribute(k_large_fft<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
     plan.min_frames = 64;
     plan.supported = true;
+    return YG_OK;
+}
+
+// the fused analysis kernel's per-group V ring and counters
+int32_t plan_fused(Firpfbch2FastPlan& plan)
+{
+    const int G = (int)plan.M / kFirThreads;
+    plan.n_groups = (plan.M <= 2048) ? plan.n_sm / G : 0;     // M = 4096: 16-CTA groups lose to the two-stage path
+    int dev = 0, coop = 0;
+    YG_CUDA(cudaGetDevice(&dev));
+    YG_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop || plan.n_groups < 1) { plan.n_groups = 0; return YG_OK; }
+    YG_CUDA(cudaMalloc(&plan.d_scratch, (size_t)plan.n_groups * kSlots * 32 * plan.M * sizeof(float2)));
+    YG_CUDA(cudaMalloc(&plan.d_flags, (size_t)plan.n_groups * kFlagStride * sizeof(unsigned)));
     return YG_OK;
 }
 
@@ -394,7 +723,9 @@ int32_t firpfbch2_large_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
         }
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float2)));
     YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    return plan_common(plan, M);
+    YG_TRY(plan_common(plan, M));
+    if (plan.supported) YG_TRY(plan_fused(plan));
+    return YG_OK;
 }
 
 int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist, long long Hlen, const float2* x, float2* y,
@@ -405,9 +736,42 @@ int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist
     if (n_frames & 1) return fail(YG_EINTERNAL, "large-M path needs an even number of frames");
     const int M = (int)plan.M;
     const long long n_pairs = (long long)(n_frames / 2);
+    long long fused_pairs = 0;
+    if (plan.n_groups > 0) {
+        // whole 16-pair batches go through the fused kernel; what is left (< 32 frames) takes the two-stage path below
+        const long long n_batches = n_pairs / kPairsPerBatch;
+        fused_pairs = n_batches * kPairsPerBatch;
+        if (n_batches > 0) {
+            FusedParams fp;
+            LargeParams& p = fp.base;
+            p.hist = hist; p.Hlen = Hlen; p.x = x; p.y = y;
+            p.f0 = (long long)f0;
+            p.pair_begin = 0;
+            p.pair_end = fused_pairs;
+            p.slabs = 0;
+            p.M = M;
+            p.taps = reinterpret_cast<const float2*>(plan.d_taps);
+            p.twid = reinterpret_cast<const float2*>(plan.d_twid);
+            fp.scratch = reinterpret_cast<float2*>(plan.d_scratch);
+            fp.flags = reinterpret_cast<unsigned*>(plan.d_flags);
+            fp.n_groups = (int)std::min<long long>(plan.n_groups, n_batches);
+            YG_CUDA(cudaMemsetAsync(fp.flags, 0, (size_t)plan.n_groups * kFlagStride * sizeof(unsigned), st));
+            switch (plan.m) {
+                case 1: YG_TRY(launch_fused<3>(fp, st)); break;
+                case 2: YG_TRY(launch_fused<5>(fp, st)); break;
+                case 3: YG_TRY(launch_fused<7>(fp, st)); break;
+                case 4: YG_TRY(launch_fused<9>(fp, st)); break;
+                case 5: YG_TRY(launch_fused<11>(fp, st)); break;
+                case 6: YG_TRY(launch_fused<13>(fp, st)); break;
+                case 7: YG_TRY(launch_fused<15>(fp, st)); break;
+                case 8: YG_TRY(launch_fused<17>(fp, st)); break;
+                default: return fail(YG_EINTERNAL, "large-M path not instantiated for m = %u", plan.m);
+            }
+        }
+    }
     // chunk so that a chunk's output (8 M bytes per frame) stays resident in L2 between the two stages
     const long long chunk_pairs = chunk_frames(plan.M) / 2;
-    for (long long q = 0; q < n_pairs; q += chunk_pairs) {
+    for (long long q = fused_pairs; q < n_pairs; q += chunk_pairs) {
         LargeParams p;
         p.hist = hist; p.Hlen = Hlen; p.x = x; p.y = y;
         p.f0 = (long long)f0;
