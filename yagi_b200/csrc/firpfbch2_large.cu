@@ -335,12 +335,13 @@ __global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft512(const float2
 // sample; the launch is cooperative so that every member of a group is resident while the others wait for it.
 constexpr int kSlots = 4;
 constexpr int kInStageBytes = kPairsPerBatch * kFirThreads * 8;      // 32 KB: one batch of input for 256 branches
-constexpr int kFusedSmem = kFftSmem + 2 * kInStageBytes;
+constexpr int kDftSmem = 256 * 17 * 16;                                // 256 DFT threads x one padded 16-entry row
+constexpr int kFusedSmem = kDftSmem + 2 * kInStageBytes;
 constexpr int kFlagStride = 32;                  // 128 B of counters per group: full[kSlots], free[kSlots]
 
 struct FusedParams {
     LargeParams base;                            // pair_begin .. pair_end: whole batches
-    float2* scratch;                             // [n_groups][kSlots][32][M]
+    float2* scratch;                             // [n_groups][kSlots][16 pairs][M] packed (re_e, re_o, im_e, im_o)
     unsigned* flags;                             // [n_groups][kFlagStride], zero at launch
     int n_groups;
 };
@@ -388,7 +389,7 @@ __device__ __forceinline__ void fused_fir_role(const FusedParams& fp, int group,
     const int pos = (j < kM2) ? (kM2 - 1 - j) : (kM + kM2 - 1 - j);
     const unsigned n_dft_warps = (unsigned)(kFftWarps * (kM / kFirThreads));
     unsigned* flags = fp.flags + group * kFlagStride;
-    float2* sbase = fp.scratch + (long long)group * kSlots * 32 * kM + j;
+    float4* sbase = reinterpret_cast<float4*>(fp.scratch) + (long long)group * kSlots * kPairsPerBatch * kM + j;
 
     float2 T[kTaps];
 #pragma unroll
@@ -438,7 +439,7 @@ __device__ __forceinline__ void fused_fir_role(const FusedParams& fp, int group,
 #pragma unroll
         for (int r = 0; r < kPairsPerBatch; r++) W[16 * PAR + r] = lds64(stage0 + PAR * kInStageBytes + r * (kFirThreads * 8));
         if (use) warp_wait(flags + kSlots + slot, use * n_dft_warps, lane);      // the slot's previous batch has been read
-        float2* vb = sbase + (long long)slot * 32 * kM;
+        float4* vb = sbase + (long long)slot * kPairsPerBatch * kM;
 #pragma unroll
         for (int r = 0; r < kPairsPerBatch; r++) {
             float2 are = make_float2(0.f, 0.f), aim = make_float2(0.f, 0.f);
@@ -448,8 +449,7 @@ __device__ __forceinline__ void fused_fir_role(const FusedParams& fp, int group,
                 are = fma2(T[i], f2(w.x), are);
                 aim = fma2(T[i], f2(w.y), aim);
             }
-            __stcg(vb + (long long)(2 * r) * kM, make_float2(are.x, aim.x));
-            __stcg(vb + (long long)(2 * r + 1) * kM, make_float2(are.y, aim.y));
+            __stcg(vb + (long long)r * kM, make_float4(are.x, are.y, aim.x, aim.y));    // packed (even, odd) pair
         }
         warp_publish(flags + slot, lane);
     };
@@ -459,45 +459,122 @@ __device__ __forceinline__ void fused_fir_role(const FusedParams& fp, int group,
     }
 }
 
-__device__ __forceinline__ void fused_dft_role(const FusedParams& fp, int group, int c, long long b0, long long b1,
-                                               uint32_t tile, const float2* w32)
+// ---- DFT role of the fused kernel: frame PAIRS in packed (even, odd) form, M = 16 x 16 x R.
+// A team of T = M / 16 threads owns one pair; every thread carries 16 packed values through three passes:
+//   pass 1  thread n2:      16-point DFT over n1 of V[T n1 + n2], times W_M^{n2 k1}
+//   pass 2  thread (b, k1): 16-point DFT over a of the values n2 = R a + b, times W_T^{b e}
+//   pass 3  thread (g, k1): 16 / R radix-R DFTs over b for e in its slice  ->  X[k1 + 16 (e + 16 f)]
+// with two exchanges through one shared region per team (17-entry padded rows for the first, k1-fastest for the
+// second); 128-byte contiguous stores per half-warp and frame.
+__device__ __forceinline__ C2 ldc2(uint32_t a)
 {
+    const float4 q = lds128(a);
+    return {make_float2(q.x, q.y), make_float2(q.z, q.w)};
+}
+__device__ __forceinline__ void stc2(uint32_t a, C2 z) { sts128(a, make_float4(z.re.x, z.re.y, z.im.x, z.im.y)); }
+
+template <int R> __device__ __forceinline__ void dft_r(C2* u);          // natural order in, natural order out
+template <> __device__ __forceinline__ void dft_r<2>(C2* u)
+{
+    const C2 s = cadd(u[0], u[1]), d = csub(u[0], u[1]);
+    u[0] = s; u[1] = d;
+}
+template <> __device__ __forceinline__ void dft_r<4>(C2* u) { dft4(u[0], u[1], u[2], u[3]); }
+template <> __device__ __forceinline__ void dft_r<8>(C2* u)
+{
+    constexpr float r2 = 0.70710678118654752f;
+    dft4(u[0], u[2], u[4], u[6]);                                        // E[k] at u[2k]
+    dft4(u[1], u[3], u[5], u[7]);                                        // O[k] at u[2k + 1]
+    const C2 e0 = u[0], e1 = u[2], e2 = u[4], e3 = u[6];
+    const C2 o0 = u[1], p1 = w8u(u[3]), o2 = u[5], p3 = w8u3(u[7]);      // p1, p3 still to be scaled by r2
+    u[0] = cadd(e0, o0);       u[4] = csub(e0, o0);
+    u[1] = cfma(p1, r2, e1);   u[5] = cfma(p1, -r2, e1);
+    u[2] = caddj(e2, o2);      u[6] = csubj(e2, o2);
+    u[3] = cfma(p3, r2, e3);   u[7] = cfma(p3, -r2, e3);
+}
+template <> __device__ __forceinline__ void dft_r<16>(C2* u)
+{
+    C2(&v)[16] = *reinterpret_cast<C2(*)[16]>(u);
+    dft16(v);
+    C2 t[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) t[k] = v[dr4(k)];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = t[k];
+}
+
+template <int R>
+__device__ __forceinline__ void team_bar(int id)
+{
+    if (R == 2) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(16 * R) : "memory");
+}
+
+template <int R>
+__device__ __forceinline__ void fused_dft_role_r(const FusedParams& fp, int group, int c, long long b0, long long b1,
+                                                 uint32_t smem_dft)
+{
+    constexpr int T = 16 * R, kM = 256 * R, E = 16 / R, G = R;
     const LargeParams& p = fp.base;
-    const int kM = p.M;
     const int lane = threadIdx.x & 31;
-    const int item = c * kFftWarps + ((threadIdx.x >> 5) - kFirThreads / 32);
-    const unsigned n_fir_warps = (unsigned)((kFirThreads / 32) * (kM / kFirThreads));
+    const int dt = threadIdx.x - kFirThreads;                            // 0 .. 255
+    const int team = dt / T, tt = dt % T;
+    const int hi = tt >> 4, k1 = tt & 15;                                // pass 2: b = hi; pass 3: g = hi
+    const int pr = c * (256 / T) + team;                                 // pair of the batch owned by this team
+    const uint32_t region = smem_dft + team * (T * 17 * 16);
+    const unsigned n_fir_warps = (unsigned)((kFirThreads / 32) * G);
     unsigned* flags = fp.flags + group * kFlagStride;
-    const float2* sbase = fp.scratch + (long long)group * kSlots * 32 * kM;
+    const float4* sbase = reinterpret_cast<const float4*>(fp.scratch) + ((long long)group * kSlots * kPairsPerBatch + pr) * kM + tt;
     for (long long batch = b0; batch < b1; batch++) {
         const long long lb = batch - b0;
         const int slot = (int)(lb % kSlots);
         const unsigned use = (unsigned)(lb / kSlots);
-        const float2* vb = sbase + (long long)slot * 32 * kM;
-        float2* yb = p.y + (p.f0 + 2 * (p.pair_begin + batch * kPairsPerBatch)) * (long long)kM;
         warp_wait(flags + slot, (use + 1) * n_fir_warps, lane);
-        float2 v[32];
-        if (kM == 512) {
-            fft512_load<true>(v, vb + (2 * item) * 512, vb + (2 * item + 1) * 512, lane);
-            fft512_compute(v, tile, w32, p.twid, lane);
-            warp_retire(flags + kSlots + slot, lane);
-            fft512_store(v, yb + (2 * item + (lane >> 4)) * 512, lane, 1);
-        } else if (kM == 1024) {
-            fft_load<1, true>(v, vb + item * 1024, 0, p.twid, lane);
-            fft_compute<1>(v, tile, w32, p.twid, lane);
-            warp_retire(flags + kSlots + slot, lane);
-            fft_store<1>(v, yb + item * 1024, 0, lane, 1);
-        } else if (kM == 2048) {
-            fft_load<2, true>(v, vb + (item >> 1) * 2048, item & 1, p.twid, lane);
-            fft_compute<2>(v, tile, w32, p.twid, lane);
-            warp_retire(flags + kSlots + slot, lane);
-            fft_store<2>(v, yb + (item >> 1) * 2048, item & 1, lane, 1);
-        } else {
-            fft_load<4, true>(v, vb + (item >> 2) * 4096, item & 3, p.twid, lane);
-            fft_compute<4>(v, tile, w32, p.twid, lane);
-            warp_retire(flags + kSlots + slot, lane);
-            fft_store<4>(v, yb + (item >> 2) * 4096, item & 3, lane, 1);
+        const float4* vs = sbase + (long long)slot * kPairsPerBatch * kM;
+        C2 v[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            const float4 q = __ldcg(vs + T * n1);
+            v[n1].re = make_float2(q.x, q.y);
+            v[n1].im = make_float2(q.z, q.w);
         }
+        dft16(v);
+        warp_retire(flags + kSlots + slot, lane);                        // this warp's loads of the slot have been consumed
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            C2 z = v[dr4(k)];
+            if (k > 0) { const float2 w = __ldg(&p.twid[tt * k]); z = cmulw(z, w.x, w.y); }
+            stc2(region + (tt * 17 + k) * 16, z);
+        }
+        team_bar<R>(1 + team);
+#pragma unroll
+        for (int a = 0; a < 16; a++) v[a] = ldc2(region + ((R * a + hi) * 17 + k1) * 16);
+        team_bar<R>(1 + team);
+        dft16(v);
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            C2 z = v[dr4(e)];
+            if (e > 0) { const float2 w = __ldg(&p.twid[16 * hi * e]); z = cmulw(z, w.x, w.y); }
+            stc2(region + (((hi * 16 + e) * 16) + k1) * 16, z);
+        }
+        team_bar<R>(1 + team);
+#pragma unroll
+        for (int ei = 0; ei < E; ei++)
+#pragma unroll
+            for (int bb = 0; bb < R; bb++) v[ei * R + bb] = ldc2(region + (((bb * 16 + hi * E + ei) * 16) + k1) * 16);
+        team_bar<R>(1 + team);                                           // region free for the next pair
+#pragma unroll
+        for (int ei = 0; ei < E; ei++) dft_r<R>(&v[ei * R]);
+        float2* ye = p.y + (p.f0 + 2 * (p.pair_begin + batch * kPairsPerBatch + pr)) * (long long)kM + k1 + 16 * (hi * E);
+        float2* yo = ye + kM;
+#pragma unroll
+        for (int ei = 0; ei < E; ei++)
+#pragma unroll
+            for (int f = 0; f < R; f++) {
+                const C2 z = v[ei * R + f];
+                __stcs(ye + 16 * (ei + 16 * f), make_float2(z.re.x, z.im.x));
+                __stcs(yo + 16 * (ei + 16 * f), make_float2(z.re.y, z.im.y));
+            }
     }
 }
 
@@ -505,15 +582,15 @@ template <int kTaps>
 __global__ void __launch_bounds__(kFirThreads + kFftWarps * 32, 1) k_large_fused(const FusedParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* w32 = reinterpret_cast<float2*>(smem_raw + kFftWarps * 1024 * 8);
-    if (threadIdx.x < 16) w32[threadIdx.x] = __ldg(&fp.base.twid[threadIdx.x * (fp.base.M >> 5)]);
-    __syncthreads();
     const int G = fp.base.M / kFirThreads;
     const int group = blockIdx.x / G, c = blockIdx.x % G;
     const long long n_batches = (fp.base.pair_end - fp.base.pair_begin) / kPairsPerBatch;
     const long long b0 = (n_batches * group) / fp.n_groups, b1 = (n_batches * (group + 1)) / fp.n_groups;
-    if (threadIdx.x < kFirThreads) fused_fir_role<kTaps>(fp, group, c, b0, b1, smem_u32(smem_raw) + kFftSmem);
-    else fused_dft_role(fp, group, c, b0, b1, smem_u32(smem_raw) + ((threadIdx.x >> 5) - kFirThreads / 32) * 8192, w32);
+    if (threadIdx.x < kFirThreads) fused_fir_role<kTaps>(fp, group, c, b0, b1, smem_u32(smem_raw) + kDftSmem);
+    else if (fp.base.M == 512) fused_dft_role_r<2>(fp, group, c, b0, b1, smem_u32(smem_raw));
+    else if (fp.base.M == 1024) fused_dft_role_r<4>(fp, group, c, b0, b1, smem_u32(smem_raw));
+    else if (fp.base.M == 2048) fused_dft_role_r<8>(fp, group, c, b0, b1, smem_u32(smem_raw));
+    else fused_dft_role_r<16>(fp, group, c, b0, b1, smem_u32(smem_raw));
 }
 
 template <int kTaps>
@@ -685,7 +762,7 @@ int32_t plan_common(Firpfbch2FastPlan& plan, uint32_t M)
 int32_t plan_fused(Firpfbch2FastPlan& plan)
 {
     const int G = (int)plan.M / kFirThreads;
-    plan.n_groups = (plan.M <= 2048) ? plan.n_sm / G : 0;     // M = 4096: 16-CTA groups lose to the two-stage path
+    plan.n_groups = plan.n_sm / G;
     int dev = 0, coop = 0;
     YG_CUDA(cudaGetDevice(&dev));
     YG_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
