@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft512(const float2
 constexpr int kSlots = 4;
 constexpr int kInStageBytes = kPairsPerBatch * kFirThreads * 8;      // 32 KB: one batch of input for 256 branches
 constexpr int kDftSmem = 256 * 17 * 16;                                // 256 DFT threads x one padded 16-entry row
-constexpr int kFusedSmem = kDftSmem + 2 * kInStageBytes;
+constexpr int kVStageBytes = 256 * 16 * 16;                            // next pair's V, one 16-entry column per DFT thread
+constexpr int kFusedSmem = kDftSmem + kVStageBytes + 2 * kInStageBytes;
 constexpr int kFlagStride = 32;                  // 128 B of counters per group: full[kSlots], free[kSlots]
 
 struct FusedParams {
@@ -372,6 +373,19 @@ __device__ __forceinline__ void warp_wait(const unsigned* p, unsigned target, in
         unsigned spins = 0;
         while (ld_relaxed_gpu(p) < target) {
             if (++spins > (1u << 27)) __trap();  // seconds without progress: fail the launch rather than hang the GPU
+        }
+    }
+    __syncwarp();
+}
+// A counter read costs an L2 round trip (a microsecond under load), so each role reads the counter it will need
+// for its NEXT batch one batch early (peek) and only falls back to polling when that early value was too small.
+__device__ __forceinline__ unsigned warp_peek(const unsigned* p, int lane) { return lane == 0 ? ld_relaxed_gpu(p) : 0u; }
+__device__ __forceinline__ void warp_wait_seen(unsigned seen, const unsigned* p, unsigned target, int lane)
+{
+    if (lane == 0 && seen < target) {
+        unsigned spins = 0;
+        while (ld_relaxed_gpu(p) < target) {
+            if (++spins > (1u << 27)) __trap();
         }
     }
     __syncwarp();
@@ -424,12 +438,15 @@ __device__ __forceinline__ void fused_fir_role(const FusedParams& fp, int group,
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     prefetch(b0, 0);
+    unsigned seen_free = 0;                                               // early read of this batch's free counter
 
     auto do_batch = [&](auto par_tag, long long batch) {
         constexpr int PAR = decltype(par_tag)::value;
         const long long lb = batch - b0;
         const int slot = (int)(lb % kSlots);
         const unsigned use = (unsigned)(lb / kSlots);
+        const unsigned seen_now = seen_free;
+        seen_free = warp_peek(flags + kSlots + (int)((lb + 1) % kSlots), lane);  // in flight across this batch's arithmetic
         if (batch + 1 < b1) {
             prefetch(batch + 1, PAR ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -438,7 +455,7 @@ __device__ __forceinline__ void fused_fir_role(const FusedParams& fp, int group,
         }
 #pragma unroll
         for (int r = 0; r < kPairsPerBatch; r++) W[16 * PAR + r] = lds64(stage0 + PAR * kInStageBytes + r * (kFirThreads * 8));
-        if (use) warp_wait(flags + kSlots + slot, use * n_dft_warps, lane);      // the slot's previous batch has been read
+        if (use) warp_wait_seen(seen_now, flags + kSlots + slot, use * n_dft_warps, lane);   // the slot's previous batch has been read
         float4* vb = sbase + (long long)slot * kPairsPerBatch * kM;
 #pragma unroll
         for (int r = 0; r < kPairsPerBatch; r++) {
@@ -512,7 +529,7 @@ __device__ __forceinline__ void team_bar(int id)
 
 template <int R>
 __device__ __forceinline__ void fused_dft_role_r(const FusedParams& fp, int group, int c, long long b0, long long b1,
-                                                 uint32_t smem_dft)
+                                                 uint32_t smem_dft, uint32_t smem_stage)
 {
     constexpr int T = 16 * R, kM = 256 * R, E = 16 / R, G = R;
     const LargeParams& p = fp.base;
@@ -525,21 +542,34 @@ __device__ __forceinline__ void fused_dft_role_r(const FusedParams& fp, int grou
     const unsigned n_fir_warps = (unsigned)((kFirThreads / 32) * G);
     unsigned* flags = fp.flags + group * kFlagStride;
     const float4* sbase = reinterpret_cast<const float4*>(fp.scratch) + ((long long)group * kSlots * kPairsPerBatch + pr) * kM + tt;
+    // V of the next batch streams into a private shared column of this thread (cp.async) while the current pair
+    // is transformed
+    const uint32_t vstage = smem_stage + dt * 16;
+    auto fetch_v = [&](long long lb) {
+        const float4* vs = sbase + (long long)(lb % kSlots) * kPairsPerBatch * kM;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vstage + n1 * (256 * 16)), "l"(vs + T * n1) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    warp_wait(flags + 0, n_fir_warps, lane);
+    fetch_v(0);
+    unsigned seen_full = (b0 + 1 < b1) ? warp_peek(flags + 1 % kSlots, lane) : 0u;
     for (long long batch = b0; batch < b1; batch++) {
         const long long lb = batch - b0;
         const int slot = (int)(lb % kSlots);
-        const unsigned use = (unsigned)(lb / kSlots);
-        warp_wait(flags + slot, (use + 1) * n_fir_warps, lane);
-        const float4* vs = sbase + (long long)slot * kPairsPerBatch * kM;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         C2 v[16];
 #pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) {
-            const float4 q = __ldcg(vs + T * n1);
-            v[n1].re = make_float2(q.x, q.y);
-            v[n1].im = make_float2(q.z, q.w);
-        }
+        for (int n1 = 0; n1 < 16; n1++) v[n1] = ldc2(vstage + n1 * (256 * 16));
+        warp_retire(flags + kSlots + slot, lane);                        // every lane's copy of the slot has landed
         dft16(v);
-        warp_retire(flags + kSlots + slot, lane);                        // this warp's loads of the slot have been consumed
+        if (batch + 1 < b1) {                                            // own column has been consumed: refill it
+            const unsigned seen_now = seen_full;
+            if (batch + 2 < b1) seen_full = warp_peek(flags + (int)((lb + 2) % kSlots), lane);
+            warp_wait_seen(seen_now, flags + (int)((lb + 1) % kSlots), (unsigned)((lb + 1) / kSlots + 1) * n_fir_warps, lane);
+            fetch_v(lb + 1);
+        }
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             C2 z = v[dr4(k)];
@@ -586,11 +616,11 @@ __global__ void __launch_bounds__(kFirThreads + kFftWarps * 32, 1) k_large_fused
     const int group = blockIdx.x / G, c = blockIdx.x % G;
     const long long n_batches = (fp.base.pair_end - fp.base.pair_begin) / kPairsPerBatch;
     const long long b0 = (n_batches * group) / fp.n_groups, b1 = (n_batches * (group + 1)) / fp.n_groups;
-    if (threadIdx.x < kFirThreads) fused_fir_role<kTaps>(fp, group, c, b0, b1, smem_u32(smem_raw) + kDftSmem);
-    else if (fp.base.M == 512) fused_dft_role_r<2>(fp, group, c, b0, b1, smem_u32(smem_raw));
-    else if (fp.base.M == 1024) fused_dft_role_r<4>(fp, group, c, b0, b1, smem_u32(smem_raw));
-    else if (fp.base.M == 2048) fused_dft_role_r<8>(fp, group, c, b0, b1, smem_u32(smem_raw));
-    else fused_dft_role_r<16>(fp, group, c, b0, b1, smem_u32(smem_raw));
+    if (threadIdx.x < kFirThreads) fused_fir_role<kTaps>(fp, group, c, b0, b1, smem_u32(smem_raw) + kDftSmem + kVStageBytes);
+    else if (fp.base.M == 512) fused_dft_role_r<2>(fp, group, c, b0, b1, smem_u32(smem_raw), smem_u32(smem_raw) + kDftSmem);
+    else if (fp.base.M == 1024) fused_dft_role_r<4>(fp, group, c, b0, b1, smem_u32(smem_raw), smem_u32(smem_raw) + kDftSmem);
+    else if (fp.base.M == 2048) fused_dft_role_r<8>(fp, group, c, b0, b1, smem_u32(smem_raw), smem_u32(smem_raw) + kDftSmem);
+    else fused_dft_role_r<16>(fp, group, c, b0, b1, smem_u32(smem_raw), smem_u32(smem_raw) + kDftSmem);
 }
 
 template <int kTaps>
