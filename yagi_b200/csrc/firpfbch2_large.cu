@@ -424,16 +424,19 @@ __device__ __forceinline__ void fused_fir_role(const FusedParams& fp, int group,
 #pragma unroll
     for (int i = 1; i <= kHist; i++) W[(32 - i) & 31] = sample(q_first - i);
 
-    // input staging: every lane copies the 16 samples of its own branch for the next batch into its private
-    // column of a double-buffered shared stage with cp.async (nothing outstanding in the LSU when the V slot is
-    // published, no registers held across the batch, no cross-thread hand-off)
-    const uint32_t stage0 = smem_in + threadIdx.x * 8;
-    const float2* xs = p.x + (p.pair_begin * (long long)kM + pos + call_off);     // sample of pair 0 of the launch
+    // input staging (double-buffered, cp.async.cg so that the stream does not wash the twiddles out of L1):
+    // branches j and j + 1 read neighbouring samples (pos falls as j rises, pos(even tid) is odd), so a lane pair
+    // shares 16-byte copies -- the even lane fetches rows 0-7 of the batch, the odd lane rows 8-15 -- and each
+    // lane then finds its own sample in slot tid ^ 1 of the row.
+    const uint32_t stage_wr = smem_in + (threadIdx.x & ~1) * 8 + (threadIdx.x & 1) * (8 * kFirThreads * 8);
+    const uint32_t stage_rd = smem_in + (threadIdx.x ^ 1) * 8;
+    const float2* xs = p.x + (p.pair_begin * (long long)kM + (pos & ~1) + call_off)       // 16-byte aligned chunk of the pair
+                       + (threadIdx.x & 1) * (8 * (long long)kM);
     auto prefetch = [&](long long batch, int st) {
         const float2* src = xs + batch * (long long)(kPairsPerBatch * kM);
 #pragma unroll
-        for (int r = 0; r < kPairsPerBatch; r++)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(stage0 + st * kInStageBytes + r * (kFirThreads * 8)),
+        for (int r = 0; r < 8; r++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_wr + st * kInStageBytes + r * (kFirThreads * 8)),
                          "l"(src + (long long)r * kM) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -453,8 +456,9 @@ __device__ __forceinline__ void fused_fir_role(const FusedParams& fp, int group,
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
+        __syncwarp();                                                     // the partner lane's half of the rows has landed too
 #pragma unroll
-        for (int r = 0; r < kPairsPerBatch; r++) W[16 * PAR + r] = lds64(stage0 + PAR * kInStageBytes + r * (kFirThreads * 8));
+        for (int r = 0; r < kPairsPerBatch; r++) W[16 * PAR + r] = lds64(stage_rd + PAR * kInStageBytes + r * (kFirThreads * 8));
         if (use) warp_wait_seen(seen_now, flags + kSlots + slot, use * n_dft_warps, lane);   // the slot's previous batch has been read
         float4* vb = sbase + (long long)slot * kPairsPerBatch * kM;
 #pragma unroll
@@ -527,6 +531,40 @@ __device__ __forceinline__ void team_bar(int id)
     else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(16 * R) : "memory");
 }
 
+// passes 1 (twiddle + exchange) .. 3 of the team transform; on entry v[dr4(k1)] holds the 16-point DFT over n1,
+// on exit v[ei R + f] = X[k1 + 16 (hi E + ei + 16 f)] with hi = tt >> 4, k1 = tt & 15, E = 16 / R
+template <int R>
+__device__ __forceinline__ void team_dft_tail(C2 (&v)[16], uint32_t region, int team, int tt, const float2* __restrict__ twid)
+{
+    constexpr int E = 16 / R;
+    const int hi = tt >> 4, k1 = tt & 15;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        C2 z = v[dr4(k)];
+        if (k > 0) { const float2 w = __ldg(&twid[tt * k]); z = cmulw(z, w.x, w.y); }
+        stc2(region + (tt * 17 + k) * 16, z);
+    }
+    team_bar<R>(1 + team);
+#pragma unroll
+    for (int a = 0; a < 16; a++) v[a] = ldc2(region + ((R * a + hi) * 17 + k1) * 16);
+    team_bar<R>(1 + team);
+    dft16(v);
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        C2 z = v[dr4(e)];
+        if (e > 0) { const float2 w = __ldg(&twid[16 * hi * e]); z = cmulw(z, w.x, w.y); }
+        stc2(region + (((hi * 16 + e) * 16) + k1) * 16, z);
+    }
+    team_bar<R>(1 + team);
+#pragma unroll
+    for (int ei = 0; ei < E; ei++)
+#pragma unroll
+        for (int bb = 0; bb < R; bb++) v[ei * R + bb] = ldc2(region + (((bb * 16 + hi * E + ei) * 16) + k1) * 16);
+    team_bar<R>(1 + team);                                               // region free for the next pair
+#pragma unroll
+    for (int ei = 0; ei < E; ei++) dft_r<R>(&v[ei * R]);
+}
+
 template <int R>
 __device__ __forceinline__ void fused_dft_role_r(const FusedParams& fp, int group, int c, long long b0, long long b1,
                                                  uint32_t smem_dft, uint32_t smem_stage)
@@ -570,31 +608,7 @@ __device__ __forceinline__ void fused_dft_role_r(const FusedParams& fp, int grou
             warp_wait_seen(seen_now, flags + (int)((lb + 1) % kSlots), (unsigned)((lb + 1) / kSlots + 1) * n_fir_warps, lane);
             fetch_v(lb + 1);
         }
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            C2 z = v[dr4(k)];
-            if (k > 0) { const float2 w = __ldg(&p.twid[tt * k]); z = cmulw(z, w.x, w.y); }
-            stc2(region + (tt * 17 + k) * 16, z);
-        }
-        team_bar<R>(1 + team);
-#pragma unroll
-        for (int a = 0; a < 16; a++) v[a] = ldc2(region + ((R * a + hi) * 17 + k1) * 16);
-        team_bar<R>(1 + team);
-        dft16(v);
-#pragma unroll
-        for (int e = 0; e < 16; e++) {
-            C2 z = v[dr4(e)];
-            if (e > 0) { const float2 w = __ldg(&p.twid[16 * hi * e]); z = cmulw(z, w.x, w.y); }
-            stc2(region + (((hi * 16 + e) * 16) + k1) * 16, z);
-        }
-        team_bar<R>(1 + team);
-#pragma unroll
-        for (int ei = 0; ei < E; ei++)
-#pragma unroll
-            for (int bb = 0; bb < R; bb++) v[ei * R + bb] = ldc2(region + (((bb * 16 + hi * E + ei) * 16) + k1) * 16);
-        team_bar<R>(1 + team);                                           // region free for the next pair
-#pragma unroll
-        for (int ei = 0; ei < E; ei++) dft_r<R>(&v[ei * R]);
+        team_dft_tail<R>(v, region, team, tt, p.twid);
         float2* ye = p.y + (p.f0 + 2 * (p.pair_begin + batch * kPairsPerBatch + pr)) * (long long)kM + k1 + 16 * (hi * E);
         float2* yo = ye + kM;
 #pragma unroll
@@ -740,6 +754,224 @@ __global__ void __launch_bounds__(kFirThreads, 2) k_large_wola(const WolaParams 
     }
 }
 
+// ------------------------------------------------------------------ fused synthesis kernel
+// The mirror image of k_large_fused: in every group of G = M / 256 CTAs the DFT teams (warps 8-15) transform
+// input frame pairs (staged from HBM with cp.async one batch ahead) and publish U batches of 16 pairs in the
+// group's L2-resident ring; the overlap-add threads (warps 0-7, one branch each, the k_large_wola arithmetic)
+// read their branch's column of the ring eight steps ahead of use.  A slab starts with one warm-up batch: the
+// 32 input frames before its first output frame.
+struct SynthFusedParams {
+    const float2* prefix;     // the 32 input frames preceding x[0]
+    const float2* x;          // input frames of the call, [frame][M]
+    float2* y;                // output sample 0 of the call
+    long long f0;             // first frame handled (even global parity)
+    long long n_batches;      // output batches of 32 frames
+    int M;
+    const float* taps;        // [M][4m]
+    const float2* twid;       // [M]
+    float4* scratch;          // [n_groups][kSlots][16 pairs][M] packed (re_e, re_o, im_e, im_o)
+    unsigned* flags;
+    int n_groups;
+};
+
+constexpr int kXStageBytes = 256 * 32 * 8;                               // one pair per DFT thread column: 2 x 16 samples
+constexpr int kUStageBytes = 256 * 16 * 16;                              // one batch of U per overlap-add thread column
+constexpr int synth_fused_smem(int taps) { return kDftSmem + kXStageBytes + (taps > 16 ? kUStageBytes : 0); }
+
+template <int R>
+__device__ __forceinline__ void synth_dft_role_r(const SynthFusedParams& p, int group, int c, long long B0, long long B1,
+                                                 uint32_t smem_dft, uint32_t smem_stage)
+{
+    constexpr int T = 16 * R, kM = 256 * R, E = 16 / R, G = R;
+    const int lane = threadIdx.x & 31;
+    const int dt = threadIdx.x - kFirThreads;
+    const int team = dt / T, tt = dt % T;
+    const int hi = tt >> 4, k1 = tt & 15;
+    const int pr = c * (256 / T) + team;
+    const uint32_t region = smem_dft + team * (T * 17 * 16);
+    const unsigned n_wola_warps = (unsigned)((kFirThreads / 32) * G);
+    unsigned* flags = p.flags + group * kFlagStride;
+    float4* sbase = p.scratch + ((long long)group * kSlots * kPairsPerBatch + pr) * kM + k1 + 16 * (hi * E);
+    const long long nb = B1 - B0 + 1;                                    // batches of this slab, warm-up included
+    // X staging: row 2 n1 + parity of the column block holds sample T n1 + tt of that frame of the pair; a lane pair
+    // shares 16-byte copies (even lane: rows 0-15, odd lane: rows 16-31)
+    const uint32_t xstage = smem_stage + dt * 8;
+    const uint32_t xstage_wr = smem_stage + (dt & ~1) * 8 + (dt & 1) * (16 * 256 * 8);
+    auto fetch_x = [&](long long lb) {                                   // frames f0 + 32 (B0 + lb - 1) + 2 pr, + 1
+        const long long vi = p.f0 + 32 * (B0 + lb - 1) + 2 * pr;
+        const float2* src = ((vi < 0) ? p.prefix + (32 + vi) * kM : p.x + vi * kM) + (tt & ~1) + (dt & 1) * (8 * T);
+#pragma unroll
+        for (int n1 = 0; n1 < 8; n1++) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xstage_wr + (2 * n1) * (256 * 8)), "l"(src + T * n1) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xstage_wr + (2 * n1 + 1) * (256 * 8)), "l"(src + kM + T * n1) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch_x(0);
+    unsigned seen_free = 0;
+    for (long long lb = 0; lb < nb; lb++) {
+        const int slot = (int)(lb % kSlots);
+        const unsigned use = (unsigned)(lb / kSlots);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();                                                    // the partner lane's rows have landed too
+        C2 v[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            const float2 e = lds64(xstage + (2 * n1) * (256 * 8)), o = lds64(xstage + (2 * n1 + 1) * (256 * 8));
+            v[n1].re = make_float2(e.x, o.x);
+            v[n1].im = make_float2(e.y, o.y);
+        }
+        dft16(v);
+        if (lb + 1 < nb) fetch_x(lb + 1);                                // own column has been consumed: refill it
+        const unsigned seen_now = seen_free;
+        seen_free = warp_peek(flags + kSlots + (int)((lb + 1) % kSlots), lane);
+        team_dft_tail<R>(v, region, team, tt, p.twid);
+        if (use) warp_wait_seen(seen_now, flags + kSlots + slot, use * n_wola_warps, lane);  // the slot's previous batch has been read
+        float4* ub = sbase + (long long)slot * kPairsPerBatch * kM;
+#pragma unroll
+        for (int ei = 0; ei < E; ei++)
+#pragma unroll
+            for (int f = 0; f < R; f++) {
+                const C2 z = v[ei * R + f];
+                __stcg(ub + 16 * (ei + 16 * f), make_float4(z.re.x, z.re.y, z.im.x, z.im.y));
+            }
+        warp_publish(flags + slot, lane);
+    }
+}
+
+template <int kTaps>
+__device__ __forceinline__ void synth_wola_role(const SynthFusedParams& p, int group, int c, long long B0, long long B1,
+                                                uint32_t smem_stage)
+{
+    const int kM = p.M, kM2 = p.M >> 1;
+    const int lane = threadIdx.x & 31;
+    const int j = c * kFirThreads + threadIdx.x;
+    const bool hi = j >= kM2;
+    const int i = j & (kM2 - 1);
+    const unsigned n_dft_warps = (unsigned)(8 * (kM / kFirThreads));
+    unsigned* flags = p.flags + group * kFlagStride;
+    const float4* sbase = p.scratch + (long long)group * kSlots * kPairsPerBatch * kM + j;
+    const long long nb = B1 - B0 + 1;
+
+    float T[kTaps];
+#pragma unroll
+    for (int l = 0; l < kTaps; l++) T[l] = __ldg(&p.taps[j * kTaps + l]);
+    float2 W[32];
+#pragma unroll
+    for (int s = 0; s < 32; s++) W[s] = make_float2(0.f, 0.f);
+    float2* yb = p.y + (p.f0 + 32 * B0) * (long long)kM2 + i;             // first real output frame of the slab
+    const long long n_out = 32 * (B1 - B0);
+
+    // U of this branch arrives eight steps (pairs) ahead of use: in registers while the taps leave room for them
+    // (kTaps <= 16), otherwise through a private shared column filled half a batch at a time with cp.async
+    constexpr bool kStageU = kTaps > 16;
+    const uint32_t ustage = smem_stage + threadIdx.x * 16;               // + half * 32 KB + pair * 4 KB
+    auto fetch = [&](long long q) {                                      // pair q of the slab, q = 16 lb + ss
+        const long long lb = q >> 4;
+        return __ldcg(sbase + ((long long)(lb % kSlots) * kPairsPerBatch + (q & 15)) * kM);
+    };
+    auto fetch8 = [&](long long lb, int half) {
+        const float4* src = sbase + ((long long)(lb % kSlots) * kPairsPerBatch + 8 * half) * kM;
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ustage + half * (8 * 4096) + r * 4096),
+                         "l"(src + (long long)r * kM) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float4 Pf[kStageU ? 1 : 8];
+    warp_wait(flags + 0, n_dft_warps, lane);
+    if (kStageU) fetch8(0, 0);
+    else {
+#pragma unroll
+        for (int s = 0; s < 8; s++) Pf[s & (kStageU ? 0 : 7)] = fetch(s);
+    }
+    float2 carry = make_float2(0.f, 0.f);                                // odd frame of the previous pair (upper half)
+    unsigned seen_full = (nb > 1) ? warp_peek(flags + 1 % kSlots, lane) : 0u;
+    for (long long lb = 0; lb < nb; lb++) {
+#pragma unroll
+        for (int ss = 0; ss < 16; ss++) {
+            const long long q = 16 * lb + ss;
+            if (kStageU && ss == 0) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                fetch8(lb, 1);
+            }
+            if (ss == 8) {                                               // the prefetch is about to cross into the next batch
+                if (kStageU) asm volatile("cp.async.wait_group 0;" ::: "memory");
+                if (lb + 1 < nb) {
+                    const unsigned seen_now = seen_full;
+                    if (lb + 2 < nb) seen_full = warp_peek(flags + (int)((lb + 2) % kSlots), lane);
+                    warp_wait_seen(seen_now, flags + (int)((lb + 1) % kSlots), (unsigned)((lb + 1) / kSlots + 1) * n_dft_warps, lane);
+                    if (kStageU) fetch8(lb + 1, 0);
+                }
+            }
+            float4 u;
+            if (kStageU) u = lds128(ustage + ss * 4096);
+            else {
+                u = Pf[ss & (kStageU ? 0 : 7)];
+                if (q + 8 < 16 * nb) Pf[ss & (kStageU ? 0 : 7)] = fetch(q + 8);
+            }
+            // lower half: slots (2ss, 2ss+1) = frames (2q, 2q+1); upper half: frames (2q-1, 2q)
+            W[(2 * ss) & 31] = hi ? carry : make_float2(u.x, u.z);
+            W[(2 * ss + 1) & 31] = hi ? make_float2(u.x, u.z) : make_float2(u.y, u.w);
+            carry = make_float2(u.y, u.w);
+            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int l = kTaps - 1; l >= 0; l--) {
+                const float2 w = W[(2 * ss - l) & 31];
+                if (l & 1) a1 = fma2(w, f2(T[l]), a1);
+                else a0 = fma2(w, f2(T[l]), a0);
+            }
+            const long long rel = 2 * q + (hi ? -1 : 0) - 32;             // output frame relative to the slab's first real frame
+            if (rel >= 0 && rel < n_out) __stcs(yb + rel * kM2, add2(a0, a1));
+        }
+        warp_retire(flags + kSlots + (int)(lb % kSlots), lane);          // every copy out of this batch's slot has landed
+    }
+    if (hi) {                                                            // last odd frame of the slab: window ends at slot 0
+        W[0] = carry;
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int l = kTaps - 1; l >= 0; l--) {
+            const float2 w = W[(0 - l) & 31];
+            if (l & 1) a1 = fma2(w, f2(T[l]), a1);
+            else a0 = fma2(w, f2(T[l]), a0);
+        }
+        __stcs(yb + (n_out - 1) * kM2, add2(a0, a1));
+    }
+}
+
+template <int kTaps>
+__global__ void __launch_bounds__(kFirThreads + 256, 1) k_large_synth_fused(const SynthFusedParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int G = p.M / kFirThreads;
+    const int group = blockIdx.x / G, c = blockIdx.x % G;
+    const long long B0 = (p.n_batches * group) / p.n_groups, B1 = (p.n_batches * (group + 1)) / p.n_groups;
+    if (B0 >= B1) return;
+    const uint32_t smem = smem_u32(smem_raw);
+    if (threadIdx.x < kFirThreads) synth_wola_role<kTaps>(p, group, c, B0, B1, smem + kDftSmem + kXStageBytes);
+    else if (p.M == 512) synth_dft_role_r<2>(p, group, c, B0, B1, smem, smem + kDftSmem);
+    else if (p.M == 1024) synth_dft_role_r<4>(p, group, c, B0, B1, smem, smem + kDftSmem);
+    else if (p.M == 2048) synth_dft_role_r<8>(p, group, c, B0, B1, smem, smem + kDftSmem);
+    else synth_dft_role_r<16>(p, group, c, B0, B1, smem, smem + kDftSmem);
+}
+
+template <int kTaps>
+int32_t launch_synth_fused(const SynthFusedParams& p, cudaStream_t st)
+{
+    static bool attr_set[64] = {};
+    int dev = 0;
+    YG_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        YG_CUDA(cudaFuncSetAttribute(k_large_synth_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, synth_fused_smem(kTaps)));
+        attr_set[dev] = true;
+    }
+    void* args[] = {const_cast<SynthFusedParams*>(&p)};
+    const int G = p.M / kFirThreads;
+    YG_CUDA(cudaLaunchCooperativeKernel((const void*)k_large_synth_fused<kTaps>, dim3((unsigned)(G * p.n_groups)),
+                                        dim3(kFirThreads + 256), args, (size_t)synth_fused_smem(kTaps), st));
+    return YG_OK;
+}
+
 template <int kTaps>
 int32_t launch_wola(const WolaParams& p, cudaStream_t st)
 {
@@ -844,7 +1076,7 @@ int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist
     const int M = (int)plan.M;
     const long long n_pairs = (long long)(n_frames / 2);
     long long fused_pairs = 0;
-    if (plan.n_groups > 0) {
+    if (plan.n_groups > 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {      // the fused kernel stages 16-byte chunks
         // whole 16-pair batches go through the fused kernel; what is left (< 32 frames) takes the two-stage path below
         const long long n_batches = n_pairs / kPairsPerBatch;
         fused_pairs = n_batches * kPairsPerBatch;
@@ -920,7 +1152,9 @@ int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t
         for (int l = 0; l < kTaps; l++) taps[(size_t)j * kTaps + l] = 0.5f * h[(j & (iM2 - 1)) + l * iM2];
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float)));
     YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
-    return plan_common(plan, M);
+    YG_TRY(plan_common(plan, M));
+    if (plan.supported) YG_TRY(plan_fused(plan));
+    return YG_OK;
 }
 
 // `prefix` = the 32 input frames preceding x[0]; frames [f0, f0 + n_frames) of the call, f0 on even global
@@ -934,6 +1168,29 @@ int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& plan, const float2
     if (n_frames == 0) return YG_OK;
     if (n_frames % 32) return fail(YG_EINTERNAL, "large-M synthesis path needs a multiple of 32 frames");
     const int M = (int)plan.M;
+    if (plan.n_groups > 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(prefix)) & 15) == 0) {
+        SynthFusedParams p;
+        p.prefix = prefix; p.x = x; p.y = y;
+        p.f0 = (long long)f0;
+        p.n_batches = (long long)(n_frames / 32);
+        p.M = M;
+        p.taps = reinterpret_cast<const float*>(plan.d_taps);
+        p.twid = reinterpret_cast<const float2*>(plan.d_twid);
+        p.scratch = reinterpret_cast<float4*>(plan.d_scratch);
+        p.flags = reinterpret_cast<unsigned*>(plan.d_flags);
+        p.n_groups = (int)std::min<long long>(plan.n_groups, p.n_batches);
+        YG_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)plan.n_groups * kFlagStride * sizeof(unsigned), st));
+        switch (plan.m) {
+            case 1: return launch_synth_fused<4>(p, st);
+            case 2: return launch_synth_fused<8>(p, st);
+            case 3: return launch_synth_fused<12>(p, st);
+            case 4: return launch_synth_fused<16>(p, st);
+            case 5: return launch_synth_fused<20>(p, st);
+            case 6: return launch_synth_fused<24>(p, st);
+            case 7: return launch_synth_fused<28>(p, st);
+            default: return fail(YG_EINTERNAL, "large-M synthesis path not instantiated for m = %u", plan.m);
+        }
+    }
     const long long chunk = chunk_frames(plan.M);                              // multiple of 32
     for (long long c0 = 0; c0 < (long long)n_frames; c0 += chunk) {
         const long long nf = std::min<long long>(chunk, (long long)n_frames - c0);
