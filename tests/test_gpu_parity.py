@@ -458,8 +458,9 @@ def test_firpfbch_fused_M64(p, S_, Q, type_, otype):
 
 @pytest.mark.parametrize("M,m", [(1024, 4), (1024, 2), (1024, 7), (512, 5), (2048, 3), (4096, 2)])
 def test_large_M_two_stage_path(M, m):
-    """Large-M analysis on the two-stage (FIR kernel + in-place FFT kernel) path (last_path == 3):
-    uneven call sizes, odd-parity starts, history from the previous call."""
+    """Large-M analysis (last_path == 3): whole 32-frame batches on the fused cooperative kernel, the rest on
+    the two-stage (FIR kernel + in-place FFT kernel) path; uneven call sizes, odd-parity starts, history from
+    the previous call."""
     K = 700 if M <= 1024 else 300
     rng = np.random.default_rng(900 + m)
     h = rng.standard_normal(2 * M * m).astype(np.float32)
@@ -481,7 +482,7 @@ def test_large_M_two_stage_path(M, m):
 
 @pytest.mark.parametrize("M,m", [(1024, 4), (1024, 2), (1024, 7), (512, 5), (2048, 3), (4096, 2)])
 def test_large_M_two_stage_synthesis(M, m):
-    """Large-M synthesis on the two-stage (IFFT kernel into an L2 scratch + overlap-add kernel) path."""
+    """Large-M synthesis (last_path == 3): fused cooperative kernel (DFT teams -> L2 ring -> overlap-add role)."""
     K = 500 if M <= 1024 else 400
     rng = np.random.default_rng(950 + m)
     h = rng.standard_normal(2 * M * m).astype(np.float32)
@@ -499,6 +500,61 @@ def test_large_M_two_stage_synthesis(M, m):
     assert_parity(y / scale, ref / scale, "large-M synthesis M=%d m=%d" % (M, m))
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+
+
+@pytest.mark.parametrize("M,m", [(512, 7), (1024, 4), (2048, 4), (4096, 3)])
+def test_large_M_fused_many_batches_per_group(M, m):
+    """Fused large-M kernels with every group of M/256 CTAs walking >= 6 batches, so that the L2 ring
+    (4 slots) wraps and both counters of every slot are reused: analysis, then synthesis of the channel
+    matrix, each against the CPU path over the whole call."""
+    groups = 148 // (M // 256)
+    K = 32 * (6 * groups + 3) + 6                  # a few frames beyond whole batches: tail on the two-stage path
+    rng = np.random.default_rng(4000 + M)
+    h = rng.standard_normal(2 * M * m).astype(np.float32)
+    x = _rand_c(rng, K * M // 2)
+    ref = _oracle_analysis(M, m, x, h=h).reshape(K, M)
+    q = yb.FirPfbCh2.new(A, M, m, h)
+    y = q.execute_block(x).reshape(K, M)
+    assert q.last_path() == 3
+    scale = max(1.0, np.abs(ref).max())
+    per_frame = np.abs(y - ref).max(axis=1) / scale
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+    assert_parity(y / scale, ref / scale, "fused large-M analysis M=%d" % M)
+    refs = po.FirPfbCh2.new(po.SYNTHESIZER, M, m, h).execute_block(ref.reshape(-1)).reshape(K, M // 2)
+    qs = yb.FirPfbCh2.new(S, M, m, h)
+    ys = qs.execute_block(ref.reshape(-1)).reshape(K, M // 2)
+    assert qs.last_path() == 3
+    sc = max(1.0, np.abs(refs).max())
+    per_frame = np.abs(ys - refs).max(axis=1) / sc
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+    assert_parity(ys / sc, refs / sc, "fused large-M synthesis M=%d" % M)
+
+
+@pytest.mark.parametrize("M,m", [(1024, 4), (512, 3)])
+def test_large_M_misaligned_device_buffers_use_two_stage_kernels(M, m):
+    """The fused large-M kernels stage 16-byte chunks; device buffers that start on an odd sample must take the
+    two-stage kernels for the whole call (analysis and synthesis) and still match the CPU path."""
+    import torch
+    K = 400
+    rng = np.random.default_rng(77 + M)
+    h = rng.standard_normal(2 * M * m).astype(np.float32)
+    x = _rand_c(rng, K * M // 2)
+    ref = _oracle_analysis(M, m, x, h=h)
+    buf = torch.zeros(K * M // 2 + 1, dtype=torch.complex64, device="cuda")
+    buf[1:] = torch.from_numpy(x).cuda()
+    q = yb.FirPfbCh2.new(A, M, m, h)
+    y = q.execute_block(buf[1:]).cpu().numpy()
+    assert q.last_path() == 3
+    scale = max(1.0, np.abs(ref).max())
+    assert_parity(y / scale, ref / scale, "misaligned large-M analysis")
+    refs = po.FirPfbCh2.new(po.SYNTHESIZER, M, m, h).execute_block(ref)
+    bufs = torch.zeros(K * M + 1, dtype=torch.complex64, device="cuda")
+    bufs[1:] = torch.from_numpy(ref).cuda()
+    qs = yb.FirPfbCh2.new(S, M, m, h)
+    ys = qs.execute_block(bufs[1:]).cpu().numpy()
+    assert qs.last_path() == 3
+    sc = max(1.0, np.abs(refs).max())
+    assert_parity(ys / sc, refs / sc, "misaligned large-M synthesis")
 
 
 def test_host_pointer_pipeline_multi_chunk():

@@ -272,7 +272,8 @@ int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frame
     const bool use_fused = aligned && q->sfast.supported && body >= q->sfast.min_frames;
     const bool use_large = q->slarge.supported && body >= q->slarge.min_frames;
     if (use_fused || use_large) {
-        if (use_large) YG_TRY(q->d_Uc.reserve((size_t)firpfbch2_large_synth_scratch_frames(q->M) * q->M));
+        if (use_large && firpfbch2_large_synth_needs_scratch(q->slarge, hist, x))
+            YG_TRY(q->d_Uc.reserve((size_t)firpfbch2_large_synth_scratch_frames(q->M) * q->M));
         YG_CUDA(cudaEventRecord(q->ev0, st));
         if (use_fused) YG_TRY(firpfbch2_synth_fast_launch(q->sfast, hist, x, y, lead, body, st));
         else YG_TRY(firpfbch2_large_synth_launch(q->slarge, hist, x, y, reinterpret_cast<float2*>(q->d_Uc.p), lead, body, st));

@@ -36,14 +36,18 @@ int32_t firpfbch2_small_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const
 int32_t firpfbch2_small_launch(const Firpfbch2FastPlan& p, const float2* hist, long long Hlen, const float2* x, float2* y,
                                size_t f0, size_t n_frames, cudaStream_t st);
 
-// Large-M analysis (firpfbch2_large.cu, M = 512 / 1024 / 2048 / 4096): FIR stage + in-place FFT stage per L2-sized chunk.
+// Large-M analysis (firpfbch2_large.cu, M = 512 / 1024 / 2048 / 4096): one fused cooperative kernel (FIR role -> L2 ring
+// -> DFT teams) for whole 32-frame batches; FIR stage + in-place FFT stage per L2-sized chunk for the rest.
 int32_t firpfbch2_large_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const float* h);
 int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& p, const float2* hist, long long Hlen, const float2* x, float2* y,
                                size_t f0, size_t n_frames, cudaStream_t st);
 
-// Large-M synthesis (same sizes): IFFT stage into an L2-resident scratch + overlap-add stage, per chunk.
+// Large-M synthesis (same sizes): one fused cooperative kernel (DFT teams -> L2 ring -> overlap-add role), or, when
+// that cannot launch, IFFT stage into an L2-resident scratch + overlap-add stage per chunk.
 int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const float* h);
 long long firpfbch2_large_synth_scratch_frames(uint32_t M);
+// false when the fused kernel will take the call (its ring lives in the plan) and `scratch` may be null
+bool firpfbch2_large_synth_needs_scratch(const Firpfbch2FastPlan& p, const float2* prefix, const float2* x);
 int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& p, const float2* prefix, const float2* x, float2* y,
                                      float2* scratch, size_t f0, size_t n_frames, cudaStream_t st);
 

@@ -1161,6 +1161,18 @@ int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t
 // parity, n_frames a multiple of 32; `scratch` holds firpfbch2_large_synth_scratch_frames(M) frames.
 long long firpfbch2_large_synth_scratch_frames(uint32_t M) { return chunk_frames(M) + 32; }
 
+namespace {
+bool synth_fused_ok(const Firpfbch2FastPlan& plan, const float2* prefix, const float2* x)
+{
+    return plan.n_groups > 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(prefix)) & 15) == 0;
+}
+}  // namespace
+
+bool firpfbch2_large_synth_needs_scratch(const Firpfbch2FastPlan& plan, const float2* prefix, const float2* x)
+{
+    return !synth_fused_ok(plan, prefix, x);
+}
+
 int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& plan, const float2* prefix, const float2* x, float2* y,
                                      float2* scratch, size_t f0, size_t n_frames, cudaStream_t st)
 {
@@ -1168,7 +1180,7 @@ int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& plan, const float2
     if (n_frames == 0) return YG_OK;
     if (n_frames % 32) return fail(YG_EINTERNAL, "large-M synthesis path needs a multiple of 32 frames");
     const int M = (int)plan.M;
-    if (plan.n_groups > 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(prefix)) & 15) == 0) {
+    if (synth_fused_ok(plan, prefix, x)) {                 // the fused kernel stages 16-byte chunks
         SynthFusedParams p;
         p.prefix = prefix; p.x = x; p.y = y;
         p.f0 = (long long)f0;
