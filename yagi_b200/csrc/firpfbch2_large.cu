@@ -1,17 +1,19 @@
 // firpfbch2_large.cu -- firpfbch2 analysis and synthesis for large power-of-two M (512 .. 4096; M = 1024 is
 // BASELINE config #4), sm_100a.
 //
-// One SM cannot hold a 1024-branch window set plus the transform, so large M runs as TWO kernels per
-// chunk of frames, chained through the 126 MB L2 instead of HBM:
-//   stage A (k_large_fir):  branch FIRs with register-resident windows (the firpfbch2_fast.cu FIR role,
-//                           256 branches per CTA), writes the rolled, 1/M-scaled branch sums V_k straight
-//                           into the output frames;
-//   stage B (k_large_fft):  in-place M-point backward DFT of every frame: for M = 1024 one warp per frame,
-//                           32 x 32 with a radix-32 in registers and one XOR-swizzled shared exchange;
-//                           M = 2048 / 4096 add one decimation-in-frequency step (2 / 4 warps per frame);
-//                           M = 512 runs 16 x 32 with one warp per pair of frames.
-// The host walks the call in chunks whose output (8 KB per frame) fits in L2, so V is written and read
-// back in cache and HBM sees the algorithmic 24 B per input sample.
+// One SM cannot hold M >= 512 branch windows plus the transform.  Two implementations live here:
+//
+//  * FUSED (k_large_fused / k_large_synth_fused, one cooperative launch per call): groups of G = M / 256
+//    persistent CTAs; in every CTA warps 0-7 own 256 polyphase branches (the register-window FIR / overlap-add
+//    arithmetic of the M = 256 kernels) and warps 8-15 transform frame pairs in packed (even, odd) form as teams
+//    of M / 16 threads (16 x 16 x R, three passes, two shared exchanges).  The two roles of a group meet in a
+//    ring of 16-pair batches in global memory that stays in L2, guarded by two counters per slot.  HBM sees the
+//    algorithmic 24 B per sample; the bound is L2 throughput (56 B per sample through it).
+//  * TWO-STAGE (k_large_fir + k_large_fft / k_large_fft + k_large_wola per 96 MB chunk, chained through L2):
+//    takes what the fused kernels do not -- fewer than 32 leftover frames, device buffers that are not 16-byte
+//    aligned, devices without cooperative launch.  Stage B is a warp-level DFT: 32 x 32 with a radix-32 in
+//    registers and one XOR-swizzled shared exchange for M = 1024, one decimation-in-frequency step on top for
+//    2048 / 4096 (2 / 4 warps per frame), 16 x 32 on frame pairs for 512.
 #include "firpfbch2_fast.cuh"
 #include "fused_common.cuh"
 
