@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft512(const float2
 // guarded by two monotone counters per slot: full (one release-add per FIR warp of the group per use) and
 // free (one per DFT warp, after its loads of the slot have landed).  HBM sees the algorithmic 24 B per input
 // sample; the launch is cooperative so that every member of a group is resident while the others wait for it.
-constexpr int kSlots = 4;
+constexpr int kSlots = 4;                          // swept 2 / 4 / 8: 2 starves the consumer, 8 spills the ring out of L2
 constexpr int kInStageBytes = kPairsPerBatch * kFirThreads * 8;      // 32 KB: one batch of input for 256 branches
 constexpr int kDftSmem = 256 * 17 * 16;                                // 256 DFT threads x one padded 16-entry row
 constexpr int kVStageBytes = 256 * 16 * 16;                            // next pair's V, one 16-entry column per DFT thread
