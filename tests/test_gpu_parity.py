@@ -489,7 +489,7 @@ def test_large_M_two_stage_synthesis(M, m):
     X = _rand_c(rng, K * M)
     ref = po.FirPfbCh2.new(po.SYNTHESIZER, M, m, h).execute_block(X).reshape(K, M // 2)
     q = yb.FirPfbCh2.new(S, M, m, h)
-    cuts = [0, 96, 225, 226, K]
+    cuts = [0, 96, 225, 226, 323, K]              # the last call starts on an odd frame: its first pair straddles prefix | x
     outs = []
     for a, b in zip(cuts, cuts[1:]):
         outs.append(q.execute_block(X[a * M: b * M]))
@@ -651,3 +651,31 @@ def test_fused_small_M_analysis(M, m):
     assert_parity(y / scale, ref / scale, "small-M M=%d m=%d" % (M, m))
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+
+
+@pytest.mark.parametrize("M,m", [(64, 5), (64, 1), (64, 7), (128, 7), (128, 2), (128, 4)])
+def test_fused_small_M_synthesis(M, m):
+    """firpfbch2 synthesis M=64 / M=128 on the fused small-M kernel (256/M time slabs per CTA, warm-up batch per
+    slab): slab boundaries, more slabs than batches, uneven call sizes, odd-parity starts, state hand-over."""
+    K = 40000 if M == 64 else 21000                # > 148 * S slabs of several batches each
+    rng = np.random.default_rng(660 + M + m)
+    h = rng.standard_normal(2 * M * m).astype(np.float32)
+    X = _rand_c(rng, K * M)
+    ref = po.FirPfbCh2.new(po.SYNTHESIZER, M, m, h).execute_block(X).reshape(K, M // 2)
+    q = yb.FirPfbCh2.new(S, M, m, h)
+    cuts = [0, 256, 513, 514, 1500, 1501 + 4096, K]
+    outs = []
+    for a, b in zip(cuts, cuts[1:]):
+        outs.append(q.execute_block(X[a * M: b * M]))
+        if b - a >= 300:
+            assert q.last_path() == 2, (a, b)
+    y = np.concatenate(outs).reshape(K, M // 2)
+    scale = max(1.0, np.abs(ref).max())
+    per_frame = np.abs(y - ref).max(axis=1) / scale
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+    assert_parity(y / scale, ref / scale, "small-M synthesis M=%d m=%d" % (M, m))
+    hist, flag = q.get_state()
+    c = yb.FirPfbCh2.new(S, M, m, h)
+    c.set_state(hist, flag)
+    v = _rand_c(rng, 700 * M)
+    np.testing.assert_array_equal(q.execute_block(v), c.execute_block(v))

@@ -85,7 +85,13 @@ def main():
             qa = yb.FirPfbCh2.new_kaiser(yb.ANALYZER, M, m, 60.0)
             ms = timed(lambda: qa.execute_block(x, N // (M // 2), out=Y))
             report("firpfbch2 analysis M=%d m=7 N=2^28 (path %d)" % (M, qa.last_path()), ms, 24.0 * N, N, "samples_in")
-            del x, Y, qa
+            del x, qa
+            y = torch.empty(N, dtype=torch.complex64, device="cuda")         # synthesis of the 2^28 channel samples: 2^27 out
+            qs = yb.FirPfbCh2.new_kaiser(yb.SYNTHESIZER, M, m, 60.0)
+            No = N // 2
+            ms = timed(lambda: qs.execute_block(Y[:N], N // M, out=y[:No]))
+            report("firpfbch2 synthesis M=%d m=7 N=2^27 out (path %d)" % (M, qs.last_path()), ms, 24.0 * No, No, "samples_out")
+            del Y, y, qs
     if "largeM" in which:
         for M, m in ((512, 7), (2048, 4), (4096, 4)):
             N = 1 << 26

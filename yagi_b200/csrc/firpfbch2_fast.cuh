@@ -31,6 +31,12 @@ int32_t firpfbch2_synth_fast_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, 
 int32_t firpfbch2_synth_fast_launch(const Firpfbch2FastPlan& p, const float2* prefix, const float2* x, float2* y,
                                     size_t f0, size_t n_frames, cudaStream_t st);
 
+// Small-M fused synthesis (firpfbch2_small_synth.cu, M = 64 / 128): 256 / M time slabs per CTA; same contract as
+// firpfbch2_synth_fast_launch.
+int32_t firpfbch2_small_synth_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const float* h);
+int32_t firpfbch2_small_synth_launch(const Firpfbch2FastPlan& p, const float2* prefix, const float2* x, float2* y,
+                                     size_t f0, size_t n_frames, cudaStream_t st);
+
 // Small-M fused analysis (firpfbch2_small.cu, M = 64): four time slabs per CTA.
 int32_t firpfbch2_small_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const float* h);
 int32_t firpfbch2_small_launch(const Firpfbch2FastPlan& p, const float2* hist, long long Hlen, const float2* x, float2* y,

@@ -489,43 +489,6 @@ __device__ __forceinline__ void fused_fir_role(const FusedParams& fp, int group,
 //   pass 3  thread (g, k1): 16 / R radix-R DFTs over b for e in its slice  ->  X[k1 + 16 (e + 16 f)]
 // with two exchanges through one shared region per team (17-entry padded rows for the first, k1-fastest for the
 // second); 128-byte contiguous stores per half-warp and frame.
-__device__ __forceinline__ C2 ldc2(uint32_t a)
-{
-    const float4 q = lds128(a);
-    return {make_float2(q.x, q.y), make_float2(q.z, q.w)};
-}
-__device__ __forceinline__ void stc2(uint32_t a, C2 z) { sts128(a, make_float4(z.re.x, z.re.y, z.im.x, z.im.y)); }
-
-template <int R> __device__ __forceinline__ void dft_r(C2* u);          // natural order in, natural order out
-template <> __device__ __forceinline__ void dft_r<2>(C2* u)
-{
-    const C2 s = cadd(u[0], u[1]), d = csub(u[0], u[1]);
-    u[0] = s; u[1] = d;
-}
-template <> __device__ __forceinline__ void dft_r<4>(C2* u) { dft4(u[0], u[1], u[2], u[3]); }
-template <> __device__ __forceinline__ void dft_r<8>(C2* u)
-{
-    constexpr float r2 = 0.70710678118654752f;
-    dft4(u[0], u[2], u[4], u[6]);                                        // E[k] at u[2k]
-    dft4(u[1], u[3], u[5], u[7]);                                        // O[k] at u[2k + 1]
-    const C2 e0 = u[0], e1 = u[2], e2 = u[4], e3 = u[6];
-    const C2 o0 = u[1], p1 = w8u(u[3]), o2 = u[5], p3 = w8u3(u[7]);      // p1, p3 still to be scaled by r2
-    u[0] = cadd(e0, o0);       u[4] = csub(e0, o0);
-    u[1] = cfma(p1, r2, e1);   u[5] = cfma(p1, -r2, e1);
-    u[2] = caddj(e2, o2);      u[6] = csubj(e2, o2);
-    u[3] = cfma(p3, r2, e3);   u[7] = cfma(p3, -r2, e3);
-}
-template <> __device__ __forceinline__ void dft_r<16>(C2* u)
-{
-    C2(&v)[16] = *reinterpret_cast<C2(*)[16]>(u);
-    dft16(v);
-    C2 t[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) t[k] = v[dr4(k)];
-#pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = t[k];
-}
-
 template <int R>
 __device__ __forceinline__ void team_bar(int id)
 {
@@ -642,14 +605,7 @@ __global__ void __launch_bounds__(kFirThreads + kFftWarps * 32, 1) k_large_fused
 template <int kTaps>
 int32_t launch_fused(const FusedParams& fp, cudaStream_t st)
 {
-    static bool attr_set[64] = {};
-    int dev = 0;
-    YG_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && !attr_set[dev]) {
-        YG_CUDA(cudaFuncSetAttribute(k_large_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
-        attr_set[dev] = true;
-    }
-    void* args[] = {const_cast<FusedParams*>(&fp)};
+    void* args[] = {const_cast<FusedParams*>(&fp)};              // the shared-memory attribute was set by plan_fused
     const int G = fp.base.M / kFirThreads;
     YG_CUDA(cudaLaunchCooperativeKernel((const void*)k_large_fused<kTaps>, dim3((unsigned)(G * fp.n_groups)),
                                         dim3(kFirThreads + kFftWarps * 32), args, (size_t)kFusedSmem, st));
@@ -799,13 +755,16 @@ __device__ __forceinline__ void synth_dft_role_r(const SynthFusedParams& p, int 
     // shares 16-byte copies (even lane: rows 0-15, odd lane: rows 16-31)
     const uint32_t xstage = smem_stage + dt * 8;
     const uint32_t xstage_wr = smem_stage + (dt & ~1) * 8 + (dt & 1) * (16 * 256 * 8);
-    auto fetch_x = [&](long long lb) {                                   // frames f0 + 32 (B0 + lb - 1) + 2 pr, + 1
+    auto fetch_x = [&](long long lb) {
+        // frames vi, vi + 1; with an odd call-relative start the pair can straddle the prefix | x boundary
         const long long vi = p.f0 + 32 * (B0 + lb - 1) + 2 * pr;
-        const float2* src = ((vi < 0) ? p.prefix + (32 + vi) * kM : p.x + vi * kM) + (tt & ~1) + (dt & 1) * (8 * T);
+        const long long off = (tt & ~1) + (dt & 1) * (8 * T);
+        const float2* se = ((vi < 0) ? p.prefix + (32 + vi) * kM : p.x + vi * kM) + off;
+        const float2* so = ((vi + 1 < 0) ? p.prefix + (33 + vi) * kM : p.x + (vi + 1) * kM) + off;
 #pragma unroll
         for (int n1 = 0; n1 < 8; n1++) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xstage_wr + (2 * n1) * (256 * 8)), "l"(src + T * n1) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xstage_wr + (2 * n1 + 1) * (256 * 8)), "l"(src + kM + T * n1) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xstage_wr + (2 * n1) * (256 * 8)), "l"(se + T * n1) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xstage_wr + (2 * n1 + 1) * (256 * 8)), "l"(so + T * n1) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -960,14 +919,7 @@ __global__ void __launch_bounds__(kFirThreads + 256, 1) k_large_synth_fused(cons
 template <int kTaps>
 int32_t launch_synth_fused(const SynthFusedParams& p, cudaStream_t st)
 {
-    static bool attr_set[64] = {};
-    int dev = 0;
-    YG_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && !attr_set[dev]) {
-        YG_CUDA(cudaFuncSetAttribute(k_large_synth_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, synth_fused_smem(kTaps)));
-        attr_set[dev] = true;
-    }
-    void* args[] = {const_cast<SynthFusedParams*>(&p)};
+    void* args[] = {const_cast<SynthFusedParams*>(&p)};          // the shared-memory attribute was set by plan_fused
     const int G = p.M / kFirThreads;
     YG_CUDA(cudaLaunchCooperativeKernel((const void*)k_large_synth_fused<kTaps>, dim3((unsigned)(G * p.n_groups)),
                                         dim3(kFirThreads + 256), args, (size_t)synth_fused_smem(kTaps), st));
@@ -1023,14 +975,52 @@ int32_t plan_common(Firpfbch2FastPlan& plan, uint32_t M)
 }
 
 // the fused analysis kernel's per-group V ring and counters
-int32_t plan_fused(Firpfbch2FastPlan& plan)
+// resident CTAs per SM of a fused kernel instance (0: it cannot launch with this much shared memory)
+template <typename K>
+int resident_ctas(K kernel, int smem)
+{
+    int n = 0;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kFirThreads + 256, (size_t)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int32_t plan_fused(Firpfbch2FastPlan& plan, bool synthesis)
 {
     const int G = (int)plan.M / kFirThreads;
     plan.n_groups = plan.n_sm / G;
     int dev = 0, coop = 0;
     YG_CUDA(cudaGetDevice(&dev));
     YG_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    if (!coop || plan.n_groups < 1) { plan.n_groups = 0; return YG_OK; }
+    int fit = 0;                          // a cooperative grid of one CTA per SM must be resident all at once
+    if (synthesis) {
+        switch (plan.m) {
+            case 1: fit = resident_ctas(k_large_synth_fused<4>, synth_fused_smem(4)); break;
+            case 2: fit = resident_ctas(k_large_synth_fused<8>, synth_fused_smem(8)); break;
+            case 3: fit = resident_ctas(k_large_synth_fused<12>, synth_fused_smem(12)); break;
+            case 4: fit = resident_ctas(k_large_synth_fused<16>, synth_fused_smem(16)); break;
+            case 5: fit = resident_ctas(k_large_synth_fused<20>, synth_fused_smem(20)); break;
+            case 6: fit = resident_ctas(k_large_synth_fused<24>, synth_fused_smem(24)); break;
+            case 7: fit = resident_ctas(k_large_synth_fused<28>, synth_fused_smem(28)); break;
+            default: break;
+        }
+    } else {
+        switch (plan.m) {
+            case 1: fit = resident_ctas(k_large_fused<3>, kFusedSmem); break;
+            case 2: fit = resident_ctas(k_large_fused<5>, kFusedSmem); break;
+            case 3: fit = resident_ctas(k_large_fused<7>, kFusedSmem); break;
+            case 4: fit = resident_ctas(k_large_fused<9>, kFusedSmem); break;
+            case 5: fit = resident_ctas(k_large_fused<11>, kFusedSmem); break;
+            case 6: fit = resident_ctas(k_large_fused<13>, kFusedSmem); break;
+            case 7: fit = resident_ctas(k_large_fused<15>, kFusedSmem); break;
+            case 8: fit = resident_ctas(k_large_fused<17>, kFusedSmem); break;
+            default: break;
+        }
+    }
+    if (!coop || fit < 1 || plan.n_groups < 1) { plan.n_groups = 0; return YG_OK; }
     YG_CUDA(cudaMalloc(&plan.d_scratch, (size_t)plan.n_groups * kSlots * 32 * plan.M * sizeof(float2)));
     YG_CUDA(cudaMalloc(&plan.d_flags, (size_t)plan.n_groups * kFlagStride * sizeof(unsigned)));
     return YG_OK;
@@ -1065,7 +1055,7 @@ int32_t firpfbch2_large_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float2)));
     YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
     YG_TRY(plan_common(plan, M));
-    if (plan.supported) YG_TRY(plan_fused(plan));
+    if (plan.supported) YG_TRY(plan_fused(plan, false));
     return YG_OK;
 }
 
@@ -1155,7 +1145,7 @@ int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float)));
     YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
     YG_TRY(plan_common(plan, M));
-    if (plan.supported) YG_TRY(plan_fused(plan));
+    if (plan.supported) YG_TRY(plan_fused(plan, true));
     return YG_OK;
 }
 

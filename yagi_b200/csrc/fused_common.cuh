@@ -152,5 +152,44 @@ __device__ __forceinline__ void dft16(C2 (&v)[16])
     }
 }
 
+// packed pair <-> one 16-byte shared-memory entry (re_e, re_o, im_e, im_o)
+__device__ __forceinline__ C2 ldc2(uint32_t a)
+{
+    const float4 q = lds128(a);
+    return {make_float2(q.x, q.y), make_float2(q.z, q.w)};
+}
+__device__ __forceinline__ void stc2(uint32_t a, C2 z) { sts128(a, make_float4(z.re.x, z.re.y, z.im.x, z.im.y)); }
+
+// radix-R backward DFT on packed pairs, natural order in and out (R = 2, 4, 8, 16)
+template <int R> __device__ __forceinline__ void dft_r(C2* u);
+template <> __device__ __forceinline__ void dft_r<2>(C2* u)
+{
+    const C2 s = cadd(u[0], u[1]), d = csub(u[0], u[1]);
+    u[0] = s; u[1] = d;
+}
+template <> __device__ __forceinline__ void dft_r<4>(C2* u) { dft4(u[0], u[1], u[2], u[3]); }
+template <> __device__ __forceinline__ void dft_r<8>(C2* u)
+{
+    constexpr float r2 = 0.70710678118654752f;
+    dft4(u[0], u[2], u[4], u[6]);                                        // E[k] at u[2k]
+    dft4(u[1], u[3], u[5], u[7]);                                        // O[k] at u[2k + 1]
+    const C2 e0 = u[0], e1 = u[2], e2 = u[4], e3 = u[6];
+    const C2 o0 = u[1], p1 = w8u(u[3]), o2 = u[5], p3 = w8u3(u[7]);      // p1, p3 still to be scaled by r2
+    u[0] = cadd(e0, o0);       u[4] = csub(e0, o0);
+    u[1] = cfma(p1, r2, e1);   u[5] = cfma(p1, -r2, e1);
+    u[2] = caddj(e2, o2);      u[6] = csubj(e2, o2);
+    u[3] = cfma(p3, r2, e3);   u[7] = cfma(p3, -r2, e3);
+}
+template <> __device__ __forceinline__ void dft_r<16>(C2* u)
+{
+    C2(&v)[16] = *reinterpret_cast<C2(*)[16]>(u);
+    dft16(v);
+    C2 t[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) t[k] = v[dr4(k)];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = t[k];
+}
+
 }  // namespace dev
 }  // namespace yg
