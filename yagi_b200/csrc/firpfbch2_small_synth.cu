@@ -8,8 +8,8 @@
 //
 //   DFT role (warps 8-15): a team of T = M / 16 threads owns one frame pair of one slab per batch.  Its input
 //     (2 x 16 samples per thread) is staged one batch ahead with cp.async.cg, 16 bytes shared by a lane pair.
-//     Packed (even, odd) transform M = 16 x T: radix 16 in registers, twiddle, one exchange through the
-//     warp's own (already consumed) staging columns with an XOR swizzle, radix T, then U -> shared batch.
+//     Packed (even, odd) transform M = 16 x T: radix 16 in registers, twiddle, one XOR-swizzled exchange through
+//     the team's own segment of the U row it is about to write, radix T, then U -> the same segment.
 //   overlap-add role (warps 0-7): thread (slab, column j) keeps the last 4m frames of its column in a
 //     32-entry register ring, one packed FFMA2 per tap; columns j < M/2 emit on even frames, j >= M/2 on odd
 //     frames (the upper half keeps its ring one frame behind).
@@ -83,13 +83,6 @@ __device__ __forceinline__ void dft_role(const SmallSynthParams& p, uint32_t sme
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xcol_wr + (2 * n1 + 1) * (kRoleThreads * 8)), "l"(so + T * n1) : "memory");
         }
     };
-    // exchange: the warp's 32 staging columns are an 8 KB scratch once every lane has read its samples; entry
-    // E = 32 k1 + (lane ^ (k1 % T)) lives at row E / 16, 16-byte slot E % 16 of the warp's 256-byte row segment
-    const uint32_t xwarp = smem + (dt & ~31) * 8;
-    auto entry = [&](int k1, int l) {
-        const int E = 32 * k1 + (l ^ (k1 % T));
-        return xwarp + (E >> 4) * (kRoleThreads * 8) + (E & 15) * 16;
-    };
     float2 tw[16];                                            // W_M^{tt k1}
 #pragma unroll
     for (int k = 0; k < 16; k++) tw[k] = __ldg(&p.twid[tt * k]);
@@ -108,30 +101,32 @@ __device__ __forceinline__ void dft_role(const SmallSynthParams& p, uint32_t sme
             v[n1].im = make_float2(e.y, o.y);
         }
         dft16(v);
-        __syncwarp();                                        // every lane has consumed its staged samples
+        __syncwarp();                                        // every lane has consumed its staged samples:
+        if (lb + 1 < nb) fetch_x(lb + 1);                    // refill the columns a whole batch ahead of use
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (lb >= 2) mbar_wait(mb + 8 * (2 + b), (uint32_t)(((lb >> 1) - 1) & 1));      // overlap-add role drained U[b]
+        // The team's own segment of its U row (M entries of 16 bytes) doubles as the exchange tile: entry
+        // (k1, n2) at slot k1 T + (n2 ^ (k1 % T)), conflict-free for the writes (fixed k1) and the gathers.
+        const uint32_t useg = smem + kXStageBytes + b * kUBufBytes + pr * kURowBytes + (s * kM) * 16;
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             C2 z = v[dr4(k)];
             if (k > 0) z = cmulw(z, tw[k].x, tw[k].y);
-            stc2(entry(k, lane), z);
+            stc2(useg + (k * T + (tt ^ (k % T))) * 16, z);
         }
         __syncwarp();
-        // thread tt gathers, for its k1 = tt + T i, the T team-mates' values (lane of team-mate n2 = lane - tt + n2)
+        // thread tt gathers, for its k1 = tt + T i, the T team-mates' values
 #pragma unroll
         for (int i = 0; i < I; i++)
 #pragma unroll
-            for (int n2 = 0; n2 < T; n2++) v[i * T + n2] = ldc2(entry(tt + T * i, (lane - tt) + n2));
-        __syncwarp();                                        // scratch consumed: the columns can be refilled
-        if (lb + 1 < nb) fetch_x(lb + 1);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+            for (int n2 = 0; n2 < T; n2++) v[i * T + n2] = ldc2(useg + ((tt + T * i) * T + (n2 ^ tt)) * 16);
+        __syncwarp();                                        // tile consumed: it can take the final U
 #pragma unroll
         for (int i = 0; i < I; i++) dft_r<T>(&v[i * T]);     // v[i T + k2] = U[tt + T i + 16 k2]
-        if (lb >= 2) mbar_wait(mb + 8 * (2 + b), (uint32_t)(((lb >> 1) - 1) & 1));      // overlap-add role drained U[b]
-        const uint32_t urow = smem + kXStageBytes + b * kUBufBytes + pr * kURowBytes + (s * kM + tt) * 16;
 #pragma unroll
         for (int i = 0; i < I; i++)
 #pragma unroll
-            for (int k2 = 0; k2 < T; k2++) stc2(urow + (T * i + 16 * k2) * 16, v[i * T + k2]);
+            for (int k2 = 0; k2 < T; k2++) stc2(useg + (tt + T * i + 16 * k2) * 16, v[i * T + k2]);
         __syncwarp();
         if (lane == 0) mbar_arrive(mb + 8 * b);
     }
