@@ -164,11 +164,7 @@ constexpr int kFftSmem = kFftWarps * 1024 * 8 + 16 * 8;
 // ---- warp-level transforms.  M = 1024 S (S = 1, 2, 4): one decimation-in-frequency step splits a frame into S
 // interleaved 1024-point transforms, X[S k + r] = DFT1024{ (sum_q x[1024 q + n] W_S^{q r}) W_M^{n r} }[k]; a warp takes
 // one (frame, r) item: 32 x 32 with a radix-32 in registers and one XOR-swizzled 8 KB shared exchange tile.
-// kCg: the source was written by other SMs during this launch (fused kernel) -> read through L2 (ld.global.cg).
-template <bool kCg>
-__device__ __forceinline__ float2 ldv(const float2* p) { return kCg ? __ldcg(p) : *p; }
-
-template <int S, bool kCg>
+template <int S>
 __device__ __forceinline__ void fft_load(float2 (&v)[32], const float2* src, int r, const float2* __restrict__ twid, int lane)
 {
     float2 ws[S];                                                        // W_S^{q r}
@@ -178,11 +174,11 @@ __device__ __forceinline__ void fft_load(float2 (&v)[32], const float2* src, int
 #pragma unroll
     for (int n1 = 0; n1 < 32; n1++) {
         const int n = 32 * n1 + lane;
-        float2 a = ldv<kCg>(src + n);
+        float2 a = src[n];
         if (S > 1) {
 #pragma unroll
             for (int q = 1; q < S; q++) {
-                const float2 z = ldv<kCg>(src + 1024 * q + n);
+                const float2 z = src[1024 * q + n];
                 if (S == 2) a = r ? xsub(a, z) : xadd(a, z);
                 else a = xadd(a, xmul(z, ws[q].x, ws[q].y));
             }
@@ -225,13 +221,12 @@ __device__ __forceinline__ void fft_store(const float2 (&v)[32], float2* fr, int
 
 // M = 512 = 16 x 32: one warp per PAIR of frames.  Pass 1: lane n2 runs the 16-point transforms over n1 of both
 // frames; pass 2: lane (frame, k1) runs one 32-point transform over n2.  Same 8 KB swizzled tile per warp.
-template <bool kCg>
 __device__ __forceinline__ void fft512_load(float2 (&v)[32], const float2* src0, const float2* src1, int lane)
 {
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) v[n1] = ldv<kCg>(src0 + 32 * n1 + lane);
+    for (int n1 = 0; n1 < 16; n1++) v[n1] = src0[32 * n1 + lane];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) v[16 + n1] = ldv<kCg>(src1 + 32 * n1 + lane);
+    for (int n1 = 0; n1 < 16; n1++) v[16 + n1] = src1[32 * n1 + lane];
 }
 
 __device__ __forceinline__ void fft512_compute(float2 (&v)[32], uint32_t tile, const float2* w32, const float2* __restrict__ twid, int lane)
@@ -292,7 +287,7 @@ __global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft(const float2* p
         const long long vi = v0 + f;
         const float2* src = (vi < 0) ? prefix + (32 + vi) * kM : x + vi * kM;
         float2 v[32];
-        fft_load<S, false>(v, src, r, twid, lane);
+        fft_load<S>(v, src, r, twid, lane);
         fft_compute<S>(v, tile, w32, twid, lane);
         if (S > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + wrp / S), "r"(S * 32) : "memory");
         fft_store<S>(v, dst + f * kM, r, lane, streaming_store);
@@ -319,7 +314,7 @@ __global__ void __launch_bounds__(kFftWarps * 32, 2) k_large_fft512(const float2
             src[h] = (vi < 0) ? prefix + (32 + vi) * kM : x + vi * kM;
         }
         float2 v[32];
-        fft512_load<false>(v, src[0], src[1], lane);
+        fft512_load(v, src[0], src[1], lane);
         fft512_compute(v, tile, w32, twid, lane);
         const long long f = 2 * pr + (lane >> 4);
         fft512_store(v, f < n_frames ? dst + f * kM : nullptr, lane, streaming_store);
