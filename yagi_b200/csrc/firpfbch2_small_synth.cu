@@ -3,8 +3,8 @@
 //   y[k M/2 + i] = sum_{l < 4m} h[i + l M/2] u_{k-l}[(i + (k&1) M/2) mod M],   u_k = 1/2 IDFT_unnorm(X_k)
 //
 // A 256-column CTA is too wide for one small-M stream, so every persistent CTA walks S = 256 / M independent
-// time slabs side by side (the firpfbch2_small.cu idea).  Two warp-specialised roles, 8 warps each, meet in a
-// double-buffered shared U batch of 16 frame pairs x 256 columns:
+// time slabs side by side (the firpfbch2_small.cu idea), each with its own mbarriers: M / 32 warps of each of
+// the two roles per slab, meeting in the slab's M columns of a double-buffered shared U batch of 16 frame pairs:
 //
 //   DFT role (warps 8-15): a team of T = M / 16 threads owns one frame pair of one slab per batch.  Its input
 //     (2 x 16 samples per thread) is staged one batch ahead with cp.async.cg, 16 bytes shared by a lane pair.
@@ -34,8 +34,8 @@ constexpr int kPairs = 16;                                   // frame pairs per 
 constexpr int kXStageBytes = kRoleThreads * 32 * 8;          // 64 KB: one pair (2 x 16 samples) per DFT thread column
 constexpr int kURowBytes = kRoleThreads * 16 + 64;           // one pair row of U; +64 keeps two teams of a quarter-warp apart
 constexpr int kUBufBytes = kPairs * kURowBytes;
-constexpr int kMbar = kXStageBytes + 2 * kUBufBytes;         // ufull[2], ufree[2]
-constexpr int kSmemBytes = kMbar + 32;
+constexpr int kMbar = kXStageBytes + 2 * kUBufBytes;         // per slab s < 4: ufull[s][2], ufree[s][2]
+constexpr int kSmemBytes = kMbar + 4 * 32;
 
 struct SmallSynthParams {
     const float2* prefix;     // the 32 input frames preceding x[0]
@@ -55,7 +55,7 @@ __device__ __forceinline__ void slab_range(long long n_batches, int n_slabs, int
 }
 
 template <int kM>
-__device__ __forceinline__ void dft_role(const SmallSynthParams& p, uint32_t smem, long long nb_max)
+__device__ __forceinline__ void dft_role(const SmallSynthParams& p, uint32_t smem)
 {
     constexpr int T = kM / 16, S = kRoleThreads / kM, I = 16 / T;
     const int lane = threadIdx.x & 31;
@@ -65,7 +65,7 @@ __device__ __forceinline__ void dft_role(const SmallSynthParams& p, uint32_t sme
     long long B0, B1;
     slab_range(p.n_batches, (int)gridDim.x * S, (int)blockIdx.x * S + s, B0, B1);
     const long long nb = (B1 > B0) ? B1 - B0 + 1 : 0;         // batches of this slab, warm-up included
-    const uint32_t mb = smem + kMbar;
+    const uint32_t mb = smem + kMbar + s * 32;                // the slab's own barriers: slabs never wait for each other
 
     // staging: row 2 n1 + parity of this thread's column holds sample T n1 + tt of that frame of the pair; a lane
     // pair shares 16-byte copies (even lane: rows 0-15, odd lane: rows 16-31)
@@ -89,7 +89,7 @@ __device__ __forceinline__ void dft_role(const SmallSynthParams& p, uint32_t sme
 
     if (nb > 0) fetch_x(0);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    for (long long lb = 0; lb < nb_max; lb++) {
+    for (long long lb = 0; lb < nb; lb++) {
         const int b = (int)(lb & 1);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();                                        // the partner lane's rows have landed too
@@ -133,7 +133,7 @@ __device__ __forceinline__ void dft_role(const SmallSynthParams& p, uint32_t sme
 }
 
 template <int kM, int kTaps>
-__device__ __forceinline__ void wola_role(const SmallSynthParams& p, uint32_t smem, long long nb_max)
+__device__ __forceinline__ void wola_role(const SmallSynthParams& p, uint32_t smem)
 {
     constexpr int kM2 = kM / 2, S = kRoleThreads / kM;
     const int lane = threadIdx.x & 31;
@@ -143,8 +143,8 @@ __device__ __forceinline__ void wola_role(const SmallSynthParams& p, uint32_t sm
     long long B0, B1;
     slab_range(p.n_batches, (int)gridDim.x * S, (int)blockIdx.x * S + s, B0, B1);
     const long long n_out = 32 * (B1 - B0);
-    const long long nb_own = (B1 > B0) ? B1 - B0 + 1 : 0;       // batches of this slab, warm-up included
-    const uint32_t mb = smem + kMbar;
+    const long long nb = (B1 > B0) ? B1 - B0 + 1 : 0;          // batches of this slab, warm-up included
+    const uint32_t mb = smem + kMbar + s * 32;
 
     float T[kTaps];
 #pragma unroll
@@ -156,9 +156,9 @@ __device__ __forceinline__ void wola_role(const SmallSynthParams& p, uint32_t sm
     float2 carry = make_float2(0.f, 0.f);                     // odd frame of the previous pair (upper half)
     const uint32_t ucol = smem + kXStageBytes + threadIdx.x * 16;
 
-    for (long long lb = 0; lb < nb_max; lb++) {
+    for (long long lb = 0; lb < nb; lb++) {
         const int b = (int)(lb & 1);
-        mbar_wait(mb + 8 * b, (uint32_t)((lb >> 1) & 1));     // the DFT role has written U[b]
+        mbar_wait(mb + 8 * b, (uint32_t)((lb >> 1) & 1));     // the slab's DFT warps have written U[b]
 #pragma unroll
         for (int ss = 0; ss < 16; ss++) {
             const float4 u = lds128(ucol + b * kUBufBytes + ss * kURowBytes);
@@ -178,17 +178,17 @@ __device__ __forceinline__ void wola_role(const SmallSynthParams& p, uint32_t sm
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(mb + 8 * (2 + b));
-        if (hi && lb == nb_own - 1) {                         // last odd frame of THIS slab (a shorter slab keeps looping
-            W[0] = carry;                                     // on padding batches afterwards): window ends at slot 0
-            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+    }
+    if (hi && nb > 0) {                                       // last odd frame of the slab: window ends at slot 0
+        W[0] = carry;
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int l = kTaps - 1; l >= 0; l--) {
-                const float2 w = W[(0 - l) & 31];
-                if (l & 1) a1 = fma2(w, f2(T[l]), a1);
-                else a0 = fma2(w, f2(T[l]), a0);
-            }
-            __stcs(yb + (n_out - 1) * kM2, add2(a0, a1));
+        for (int l = kTaps - 1; l >= 0; l--) {
+            const float2 w = W[(0 - l) & 31];
+            if (l & 1) a1 = fma2(w, f2(T[l]), a1);
+            else a0 = fma2(w, f2(T[l]), a0);
         }
+        __stcs(yb + (n_out - 1) * kM2, add2(a0, a1));
     }
 }
 
@@ -200,20 +200,12 @@ __global__ void __launch_bounds__(2 * kRoleThreads, 1) k_firpfbch2_synthesis_sma
     constexpr int S = kRoleThreads / kM;
     if (threadIdx.x == 0) {
         const uint32_t mb = smem + kMbar;
-        for (int q = 0; q < 4; q++) mbar_init(mb + 8 * q, 8);           // one arrival per warp of the other role
+        for (int q = 0; q < 4 * S; q++) mbar_init(mb + 8 * q, kM / 32);  // per slab: one arrival per warp of the other role
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // every slab of the CTA runs the same number of batches (the longest one's, warm-up included); a shorter
-    // slab pads with suppressed output
-    long long nb_max = 0;
-    for (int s = 0; s < S; s++) {
-        long long B0, B1;
-        slab_range(p.n_batches, (int)gridDim.x * S, (int)blockIdx.x * S + s, B0, B1);
-        if (B1 > B0) nb_max = max(nb_max, B1 - B0 + 1);
-    }
-    if (threadIdx.x < kRoleThreads) wola_role<kM, kTaps>(p, smem, nb_max);
-    else dft_role<kM>(p, smem, nb_max);
+    if (threadIdx.x < kRoleThreads) wola_role<kM, kTaps>(p, smem);
+    else dft_role<kM>(p, smem);
 }
 
 template <int kM, int kTaps>
