@@ -87,6 +87,97 @@ __global__ void k_analysis_generic(const float* __restrict__ h, const float2* __
     }
 }
 
+// Small M (M <= 64, any even M): one frame per block would leave most of a warp idle, so a 256-thread block takes
+// F = 256 / M consecutive frames per pass, thread = (frame slot, branch) for the dot products and (frame slot, bin)
+// for a direct M-point DFT out of shared memory (M complex MACs per bin: cheaper than the passes of a transform
+// at these sizes, and valid for every M).  Shared: F*M samples + M twiddles.
+__global__ void __launch_bounds__(256) k_analysis_generic_small(const float* __restrict__ h, const float2* __restrict__ tw,
+                                                                const float2* __restrict__ hist, long long Hlen,
+                                                                const float2* __restrict__ x, float2* __restrict__ y,
+                                                                uint32_t M, uint32_t P /*2m*/, long long f_begin, long long f_end,
+                                                                int flag0)
+{
+    extern __shared__ float2 sm[];
+    const uint32_t F = 256 / M, M2 = M >> 1;
+    float2* X = sm;
+    float2* T = sm + F * M;
+    const uint32_t fs = threadIdx.x / M, b = threadIdx.x - fs * M;
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) T[i] = __ldg(&tw[i]);
+    const long long n_groups = (f_end - f_begin + F - 1) / F;
+    const float Mf = (float)M;
+    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const long long f = f_begin + g * F + fs;
+        const bool valid = fs < F && f < f_end;
+        __syncthreads();                                     // the previous pass has been read (and T is loaded)
+        if (valid) {
+            const int par = (flag0 + (int)(f & 1)) & 1;
+            const long long tk = (f + 1) * (long long)M2 - 1;
+            float2 acc = make_float2(0.f, 0.f);
+            for (int n = (int)P - 1; n >= 0; n--) {          // oldest sample first (src/dotprod/mod.rs:36-39)
+                const long long t = tk - b - (long long)n * M;
+                const float2 s = (t >= 0) ? __ldg(&x[t]) : __ldg(&hist[Hlen + t]);
+                const float c = __ldg(&h[b + (size_t)n * M]);
+                acc.x = fmaf(c, s.x, acc.x);
+                acc.y = fmaf(c, s.y, acc.y);
+            }
+            uint32_t dst = b + (par ? M2 : 0);
+            if (dst >= M) dst -= M;
+            X[fs * M + dst] = acc;
+        }
+        __syncthreads();
+        if (valid) {
+            const float2* Xf = X + fs * M;
+            float2 acc = make_float2(0.f, 0.f);
+            uint32_t idx = 0;                                // (n * b) mod M, exactly
+            for (uint32_t n = 0; n < M; n++) {
+                acc = cadd(acc, cmul(Xf[n], T[idx]));
+                idx += b;
+                if (idx >= M) idx -= M;
+            }
+            y[f * (long long)M + b] = make_float2(acc.x / Mf, acc.y / Mf);
+        }
+    }
+}
+
+// The synthesiser's stage 1 in the same shape: F frames per pass, direct M-point inverse DFT.
+__global__ void __launch_bounds__(256) k_synth_ifft_small(const float2* __restrict__ tw, const float2* __restrict__ hist,
+                                                          long long hist_frames, const float2* __restrict__ x,
+                                                          float2* __restrict__ U, uint32_t M, long long v_begin, long long v_end)
+{
+    extern __shared__ float2 sm[];
+    const uint32_t F = 256 / M;
+    float2* X = sm;
+    float2* T = sm + F * M;
+    const uint32_t fs = threadIdx.x / M, c = threadIdx.x - fs * M;
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) T[i] = __ldg(&tw[i]);
+    const long long n_groups = (v_end - v_begin + F - 1) / F;
+    const float s0 = 1.0f / (float)M;
+    const float s1 = (float)(M >> 1);
+    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const long long v = v_begin + g * F + fs;
+        const bool valid = fs < F && v < v_end;
+        __syncthreads();
+        if (valid) {
+            const float2* src = (v >= 0) ? x + v * (long long)M : hist + (hist_frames + v) * (long long)M;
+            X[fs * M + c] = __ldg(&src[c]);
+        }
+        __syncthreads();
+        if (valid) {
+            const float2* Xf = X + fs * M;
+            float2 acc = make_float2(0.f, 0.f);
+            uint32_t idx = 0;
+            for (uint32_t n = 0; n < M; n++) {
+                acc = cadd(acc, cmul(Xf[n], T[idx]));
+                idx += c;
+                if (idx >= M) idx -= M;
+            }
+            acc.x *= s0; acc.y *= s0;                        // two f32 multiplies, as upstream
+            acc.x *= s1; acc.y *= s1;
+            U[(v - v_begin) * (long long)M + c] = acc;
+        }
+    }
+}
+
 // new_hist[i] = stream[n_new - Hlen + i], stream = concat(old_hist, x[0..n_new))
 __global__ void k_update_hist(float2* __restrict__ hist_new, const float2* __restrict__ hist_old, long long Hlen,
                               const float2* __restrict__ x, long long n_new)
@@ -184,6 +275,16 @@ int32_t launch_generic_analysis(yg_firpfbch2_crcf q, const float2* hist, const f
                                 size_t f_begin, size_t f_end, cudaStream_t st)
 {
     if (f_end <= f_begin) return YG_OK;
+    if (q->M <= 64) {                        // several frames per block
+        const uint32_t F = 256 / q->M;
+        const size_t smem_s = ((size_t)F * q->M + q->M) * sizeof(float2);
+        const long long groups = ((long long)(f_end - f_begin) + F - 1) / F;
+        const int grid_s = (int)std::min<long long>(groups, 148 * 8);
+        k_analysis_generic_small<<<grid_s, 256, smem_s, st>>>(q->d_h.p, q->d_tw.p, hist, (long long)q->hist_len, x, y, q->M,
+                                                              2 * q->m, (long long)f_begin, (long long)f_end, q->flag);
+        YG_CUDA(cudaGetLastError());
+        return YG_OK;
+    }
     const size_t smem = smem_dft(q->M);
     YG_TRY(set_smem((const void*)k_analysis_generic, smem));
     const int block = (int)std::min<uint32_t>(256, (q->M + 31) / 32 * 32);
@@ -246,8 +347,15 @@ int32_t launch_generic_synthesis(yg_firpfbch2_crcf q, const float2* hist, const 
     const int block = (int)std::min<uint32_t>(256, (M + 31) / 32 * 32);
     for (long long f0 = (long long)f_begin; f0 < (long long)f_end; f0 += chunk) {
         const long long nf = std::min<long long>(chunk, (long long)f_end - f0);
-        const int grid = (int)std::min<long long>(nh + nf, 148 * 16);
-        k_synth_ifft<<<grid, block, smem, st>>>(q->d_tw.p, hist, (long long)(q->hist_len / M), x, U, M, f0 - nh, f0 + nf);
+        if (M <= 64) {                   // several frames per block
+            const uint32_t F = 256 / M;
+            const size_t smem_s = ((size_t)F * M + M) * sizeof(float2);
+            const int grid_s = (int)std::min<long long>((nh + nf + F - 1) / F, 148 * 8);
+            k_synth_ifft_small<<<grid_s, 256, smem_s, st>>>(q->d_tw.p, hist, (long long)(q->hist_len / M), x, U, M, f0 - nh, f0 + nf);
+        } else {
+            const int grid = (int)std::min<long long>(nh + nf, 148 * 16);
+            k_synth_ifft<<<grid, block, smem, st>>>(q->d_tw.p, hist, (long long)(q->hist_len / M), x, U, M, f0 - nh, f0 + nf);
+        }
         YG_CUDA(cudaGetLastError());
         const long long total = nf * q->M2;
         const int grid2 = (int)std::min<long long>((total + 255) / 256, 148 * 32);
