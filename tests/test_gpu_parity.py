@@ -679,3 +679,28 @@ def test_fused_small_M_synthesis(M, m):
     c.set_state(hist, flag)
     v = _rand_c(rng, 700 * M)
     np.testing.assert_array_equal(q.execute_block(v), c.execute_block(v))
+
+
+@pytest.mark.parametrize("M,m", [(16, 5), (16, 1), (16, 8), (8, 3), (8, 7), (32, 4), (32, 7), (32, 1)])
+def test_fused_tiny_M_analysis(M, m):
+    """firpfbch2 analysis M=8 / 16 / 32 on the fused tiny-M kernel (a FIR warp and a DFT warp per unit, 32/M time
+    slabs per warp): several batches per slab, slabs of unequal length inside a warp, a ragged last batch, a call
+    with fewer batches than slabs, odd-parity starts, history from the previous call."""
+    slabs = 148 * 8 * (32 // M)
+    K = 32 * (3 * slabs + slabs // 3) + 22
+    rng = np.random.default_rng(700 + M + m)
+    h = rng.standard_normal(2 * M * m).astype(np.float32)
+    x = _rand_c(rng, K * M // 2)
+    ref = _oracle_analysis(M, m, x, h=h).reshape(K, M)
+    q = yb.FirPfbCh2.new(A, M, m, h)
+    cuts = [0, 2500, 5001, 5002, 9000, 9001 + 40000, K]
+    outs = []
+    for a, b in zip(cuts, cuts[1:]):
+        outs.append(q.execute_block(x[a * M // 2: b * M // 2]))
+        if b - a >= 2100:
+            assert q.last_path() == 2, (a, b)
+    y = np.concatenate(outs).reshape(K, M)
+    scale = max(1.0, np.abs(ref).max())
+    per_frame = np.abs(y - ref).max(axis=1) / scale
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+    assert_parity(y / scale, ref / scale, "tiny-M M=%d m=%d" % (M, m))

@@ -41,7 +41,8 @@ struct yg_firpfbch2_crcf_s {
     Firpfbch2FastPlan fast;       // fused fast path (may be unsupported for this M/m)
     Firpfbch2FastPlan sfast;      // fused synthesis fast path
     Firpfbch2FastPlan large;      // two-stage large-M analysis path (M = 512 .. 4096)
-    Firpfbch2FastPlan small;      // fused small-M analysis kernel (M = 64)
+    Firpfbch2FastPlan small;      // fused small-M analysis kernel (M = 64, 128)
+    Firpfbch2FastPlan tiny;       // fused tiny-M analysis kernel (M = 8, 16, 32)
     Firpfbch2FastPlan slarge;     // two-stage large-M synthesis path (M = 1024)
     DevBuf<yg_cf32> d_Uc;         // its L2-sized U scratch
 };
@@ -310,16 +311,18 @@ int32_t launch_analysis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames
     const bool use_fused = aligned && q->fast.supported && n_frames >= q->fast.min_frames;
     const bool use_large = q->large.supported && n_frames >= q->large.min_frames;
     const bool use_small = aligned && q->small.supported && n_frames >= q->small.min_frames;
-    if (use_fused || use_large || use_small) {
+    const bool use_tiny = q->tiny.supported && n_frames >= q->tiny.min_frames && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    if (use_fused || use_large || use_small || use_tiny) {
         const size_t lead = (q->flag & 1) ? 1 : 0;
         const size_t body = (n_frames - lead) & ~(size_t)1;
         YG_CUDA(cudaEventRecord(q->ev0, st));
         if (use_fused) YG_TRY(firpfbch2_fast_launch(q->fast, hist, (long long)q->hist_len, x, y, lead, body, st));
         else if (use_small) YG_TRY(firpfbch2_small_launch(q->small, hist, (long long)q->hist_len, x, y, lead, body, st));
+        else if (use_tiny) YG_TRY(firpfbch2_tiny_launch(q->tiny, hist, (long long)q->hist_len, x, y, lead, body, st));
         else YG_TRY(firpfbch2_large_launch(q->large, hist, (long long)q->hist_len, x, y, lead, body, st));
         YG_CUDA(cudaEventRecord(q->ev1, st));
         q->timed = true;
-        q->last_path = (use_fused || use_small) ? 2 : 3;
+        q->last_path = (use_fused || use_small || use_tiny) ? 2 : 3;
         YG_TRY(launch_generic_analysis(q, hist, x, y, 0, lead, st));
         YG_TRY(launch_generic_analysis(q, hist, x, y, lead + body, n_frames, st));
         return YG_OK;
@@ -468,6 +471,7 @@ int32_t build(int32_t type, uint32_t M, uint32_t m, const float* h, size_t h_len
     if (type == YG_ANALYZER) TRYQ(firpfbch2_fast_plan(q->fast, M, m, q->h.data()));
     if (type == YG_ANALYZER) TRYQ(firpfbch2_large_plan(q->large, M, m, q->h.data()));
     if (type == YG_ANALYZER) TRYQ(firpfbch2_small_plan(q->small, M, m, q->h.data()));
+    if (type == YG_ANALYZER) TRYQ(firpfbch2_tiny_plan(q->tiny, M, m, q->h.data()));
     else {
         TRYQ(firpfbch2_synth_fast_plan(q->sfast, M, m, q->h.data()));
         if (!q->sfast.supported) TRYQ(firpfbch2_small_synth_plan(q->sfast, M, m, q->h.data()));
@@ -532,6 +536,7 @@ int32_t yg_firpfbch2_crcf_destroy(yg_firpfbch2_crcf q)
     firpfbch2_fast_release(q->sfast);
     firpfbch2_fast_release(q->large);
     firpfbch2_fast_release(q->small);
+    firpfbch2_fast_release(q->tiny);
     firpfbch2_fast_release(q->slarge);
     q->d_Uc.release();
     q->pipe.destroy();
