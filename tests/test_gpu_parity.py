@@ -704,3 +704,28 @@ def test_fused_tiny_M_analysis(M, m):
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
     assert_parity(y / scale, ref / scale, "tiny-M M=%d m=%d" % (M, m))
+
+
+@pytest.mark.parametrize("M,m", [(16, 5), (16, 1), (16, 7), (8, 3), (8, 7), (32, 4), (32, 7), (32, 1)])
+def test_fused_tiny_M_synthesis(M, m):
+    """firpfbch2 synthesis M=8 / 16 / 32 on the fused tiny-M kernel (a DFT warp and an overlap-add warp per unit,
+    32/M time slabs per warp, warm-up batch per slab): several batches per slab, slabs of unequal length inside a
+    warp, a call with fewer batches than slabs, odd-parity starts (a frame pair straddling prefix | x)."""
+    slabs = 148 * 8 * (32 // M)
+    K = 32 * (2 * slabs + slabs // 3) + 22
+    rng = np.random.default_rng(800 + M + m)
+    h = rng.standard_normal(2 * M * m).astype(np.float32)
+    X = _rand_c(rng, K * M)
+    ref = po.FirPfbCh2.new(po.SYNTHESIZER, M, m, h).execute_block(X).reshape(K, M // 2)
+    q = yb.FirPfbCh2.new(S, M, m, h)
+    cuts = [0, 2500, 5001, 5002, 9000, 9001 + 40000, K]
+    outs = []
+    for a, b in zip(cuts, cuts[1:]):
+        outs.append(q.execute_block(X[a * M: b * M]))
+        if b - a >= 2100:
+            assert q.last_path() == 2, (a, b)
+    y = np.concatenate(outs).reshape(K, M // 2)
+    scale = max(1.0, np.abs(ref).max())
+    per_frame = np.abs(y - ref).max(axis=1) / scale
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+    assert_parity(y / scale, ref / scale, "tiny-M synthesis M=%d m=%d" % (M, m))

@@ -387,7 +387,8 @@ int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frame
             YG_TRY(q->d_Uc.reserve((size_t)firpfbch2_large_synth_scratch_frames(q->M) * q->M));
         YG_CUDA(cudaEventRecord(q->ev0, st));
         if (use_fused && q->M == 256) YG_TRY(firpfbch2_synth_fast_launch(q->sfast, hist, x, y, lead, body, st));
-        else if (use_fused) YG_TRY(firpfbch2_small_synth_launch(q->sfast, hist, x, y, lead, body, st));
+        else if (use_fused && q->M >= 64) YG_TRY(firpfbch2_small_synth_launch(q->sfast, hist, x, y, lead, body, st));
+        else if (use_fused) YG_TRY(firpfbch2_tiny_synth_launch(q->sfast, hist, x, y, lead, body, st));
         else YG_TRY(firpfbch2_large_synth_launch(q->slarge, hist, x, y, reinterpret_cast<float2*>(q->d_Uc.p), lead, body, st));
         YG_CUDA(cudaEventRecord(q->ev1, st));
         q->timed = true;
@@ -475,6 +476,7 @@ int32_t build(int32_t type, uint32_t M, uint32_t m, const float* h, size_t h_len
     else {
         TRYQ(firpfbch2_synth_fast_plan(q->sfast, M, m, q->h.data()));
         if (!q->sfast.supported) TRYQ(firpfbch2_small_synth_plan(q->sfast, M, m, q->h.data()));
+        if (!q->sfast.supported) TRYQ(firpfbch2_tiny_synth_plan(q->sfast, M, m, q->h.data()));
         TRYQ(firpfbch2_large_synth_plan(q->slarge, M, m, q->h.data()));
     }
 #undef TRYQ

@@ -48,6 +48,11 @@ int32_t firpfbch2_tiny_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const 
 int32_t firpfbch2_tiny_launch(const Firpfbch2FastPlan& p, const float2* hist, long long Hlen, const float2* x, float2* y,
                               size_t f0, size_t n_frames, cudaStream_t st);
 
+// Tiny-M fused synthesis (firpfbch2_tiny_synth.cu, M = 8 / 16 / 32); same contract as firpfbch2_synth_fast_launch.
+int32_t firpfbch2_tiny_synth_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const float* h);
+int32_t firpfbch2_tiny_synth_launch(const Firpfbch2FastPlan& p, const float2* prefix, const float2* x, float2* y,
+                                    size_t f0, size_t n_frames, cudaStream_t st);
+
 // Large-M analysis (firpfbch2_large.cu, M = 512 / 1024 / 2048 / 4096): one fused cooperative kernel (FIR role -> L2 ring
 // -> DFT teams) for whole 32-frame batches; FIR stage + in-place FFT stage per L2-sized chunk for the rest.
 int32_t firpfbch2_large_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const float* h);
