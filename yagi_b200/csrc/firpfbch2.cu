@@ -311,7 +311,7 @@ int32_t launch_analysis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames
     const bool use_fused = aligned && q->fast.supported && n_frames >= q->fast.min_frames;
     const bool use_large = q->large.supported && n_frames >= q->large.min_frames;
     const bool use_small = aligned && q->small.supported && n_frames >= q->small.min_frames;
-    const bool use_tiny = q->tiny.supported && n_frames >= q->tiny.min_frames && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    const bool use_tiny = aligned && q->tiny.supported && n_frames >= q->tiny.min_frames && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
     if (use_fused || use_large || use_small || use_tiny) {
         const size_t lead = (q->flag & 1) ? 1 : 0;
         const size_t body = (n_frames - lead) & ~(size_t)1;

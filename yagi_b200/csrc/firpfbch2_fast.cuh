@@ -43,7 +43,7 @@ int32_t firpfbch2_small_launch(const Firpfbch2FastPlan& p, const float2* hist, l
                                size_t f0, size_t n_frames, cudaStream_t st);
 
 // Tiny-M fused analysis (firpfbch2_tiny.cu, M = 8 / 16 / 32): eight (FIR warp, DFT warp) units per CTA; needs a
-// 16-byte aligned output pointer, any input alignment.
+// 16-byte aligned input and output pointers.
 int32_t firpfbch2_tiny_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const float* h);
 int32_t firpfbch2_tiny_launch(const Firpfbch2FastPlan& p, const float2* hist, long long Hlen, const float2* x, float2* y,
                               size_t f0, size_t n_frames, cudaStream_t st);

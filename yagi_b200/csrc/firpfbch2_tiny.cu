@@ -4,13 +4,14 @@
 // FIR warp u (32 / M time slabs side by side, one polyphase branch per lane: the register-ring / packed-FFMA2
 // arithmetic of the M = 256 kernel) and DFT warp u, meeting in the unit's own double-buffered 8 KB V tile with
 // the unit's own mbarriers.  A CTA is eight independent units; nothing is shared between them.
-//   input:  every FIR lane copies the 16 samples of its branch for the next batch into its private shared
-//           column with cp.async (zero-filled beyond the end of the call), double-buffered;
+//   input:  the 16 pairs of a slab-batch are one contiguous run of samples: the FIR warp copies its runs for the next
+//           batch cooperatively with 16-byte cp.async.cg (zero-filled past the end of the slab), double-buffered;
 //   V:      packed {re_e, re_o, im_e, im_o} per (frame pair, branch), branch index XOR-swizzled with the pair so
 //           that both the row-wise writes and the column-wise reads are bank-conflict free;
 //   DFT:    M <= 16: ONE thread transforms a frame pair entirely in registers (radix 8 / 16, packed even/odd
 //           lanes); M = 32: two threads (16 x 2: radix 16, twiddle, one shuffle exchange, radix 2);
-//   output: every thread holds 8 or 16 consecutive bins of its two frames: 16-byte streaming stores.
+//   output: every thread holds 8 or 16 consecutive bins of its two frames; they go back through the pair's own region
+//           of the V tile so that the warp writes the batch (one contiguous run per slab) with 512-byte stores.
 #include "firpfbch2_fast.cuh"
 #include "fused_common.cuh"
 
@@ -68,6 +69,7 @@ __device__ __forceinline__ void fir_role(const TinyParams& p, uint32_t smem, int
     slab_range(p.n_pairs, (int)gridDim.x * kUnits * kSPW, ((int)blockIdx.x * kUnits + unit) * kSPW + sw, b0, b1);
     const long long q_end = min(b1 * kPairsPerBatch, p.n_pairs);       // pairs of this slab end here
     const uint32_t mb = smem + kMbar + unit * 32;
+    (void)q_end;
 
     float2 T[kTaps];
 #pragma unroll
@@ -88,17 +90,33 @@ __device__ __forceinline__ void fir_role(const TinyParams& p, uint32_t smem, int
         W[(32 - i) & 31] = v;
     }
 
-    const uint32_t stage0 = smem + threadIdx.x * 8;
-    const float2* xs = p.x + (pos + call_off);
-    auto prefetch = [&](long long lb, int st) {
-        const long long q = q0 + lb * kPairsPerBatch;
+    // input staging, double-buffered: the 16 pairs of a slab-batch are one contiguous run of 16 M samples, so the
+    // warp copies its 32 / M runs cooperatively (16-byte cp.async.cg, 8 per lane and batch, zero-filled past the end
+    // of the slab) and every lane then picks the sample of its branch out of row r
+    constexpr int kChunksPerSlab = kPairsPerBatch * kM / 2;             // 16-byte chunks of one slab-batch
+    const uint32_t stage_w = smem + (threadIdx.x & ~31) * (kPairsPerBatch * 8);          // the warp's 4 KB of a stage
+    const uint32_t stage_rd = stage_w + sw * (kChunksPerSlab * 16) + pos * 8;           // + r * kM * 8
+    long long sq0[kSPW], sqe[kSPW];                                     // per slab of the warp: first pair, end
 #pragma unroll
-        for (int r = 0; r < kPairsPerBatch; r++) {
-            const bool ok = q + r < q_end;                              // beyond the slab / the call: zero-fill
-            const float2* src = ok ? xs + (q + r) * (long long)kM : p.x;
-            const uint32_t bytes = ok ? 8u : 0u;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(stage0 + st * kInStageBytes + r * (kRoleThreads * 8)),
-                         "l"(src), "r"(bytes) : "memory");
+    for (int s2 = 0; s2 < kSPW; s2++) {
+        long long c0, c1;
+        slab_range(p.n_pairs, (int)gridDim.x * kUnits * kSPW, ((int)blockIdx.x * kUnits + unit) * kSPW + s2, c0, c1);
+        sq0[s2] = c0 * kPairsPerBatch;
+        sqe[s2] = min(c1 * kPairsPerBatch, p.n_pairs);
+    }
+    auto prefetch = [&](long long lb, int st) {
+#pragma unroll
+        for (int s2 = 0; s2 < kSPW; s2++) {
+            const long long q = sq0[s2] + lb * kPairsPerBatch;         // first pair of the run
+#pragma unroll
+            for (int c0 = 0; c0 < kChunksPerSlab; c0 += 32) {
+                const int c = c0 + lane;
+                const bool ok = q + c / (kM / 2) < sqe[s2];
+                const float2* src = ok ? p.x + (q * kM + call_off + 2 * c) : p.x;
+                const uint32_t bytes = ok ? 16u : 0u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(stage_w + st * kInStageBytes + s2 * (kChunksPerSlab * 16) + c * 16),
+                             "l"(src), "r"(bytes) : "memory");
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -113,8 +131,9 @@ __device__ __forceinline__ void fir_role(const TinyParams& p, uint32_t smem, int
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
+        __syncwarp();                                                   // every lane's chunks of the stage have landed
 #pragma unroll
-        for (int r = 0; r < kPairsPerBatch; r++) W[16 * PAR + r] = lds64(stage0 + PAR * kInStageBytes + r * (kRoleThreads * 8));
+        for (int r = 0; r < kPairsPerBatch; r++) W[16 * PAR + r] = lds64(stage_rd + PAR * kInStageBytes + r * (kM * 8));
         if (lb >= 2) mbar_wait(mb + 8 * (2 + PAR), (uint32_t)(((lb >> 1) - 1) & 1));    // the DFT warp has drained V[PAR]
         const uint32_t vrow = vrow0 + PAR * (kUnits * kVUnitBytes);
 #pragma unroll
@@ -137,14 +156,15 @@ __device__ __forceinline__ void fir_role(const TinyParams& p, uint32_t smem, int
     }
 }
 
-// 16-byte streaming stores of NB consecutive bins X[0..NB) of both frames of a pair
-template <int NB>
-__device__ __forceinline__ void store_bins(const C2* X, float2* ye, float2* yo)
+// The NB consecutive bins X[0..NB) of both frames of a pair go back into the pair's own region of the V tile as
+// 16-byte chunks (frame e: chunks c0 .., frame o: chunks kM/2 + c0 ..), chunk index XOR-swizzled with the pair.
+template <int kM, int NB>
+__device__ __forceinline__ void stash_bins(const C2* X, uint32_t ptile, int sx, int c0)
 {
 #pragma unroll
     for (int k = 0; k < NB; k += 2) {
-        __stcs(reinterpret_cast<float4*>(ye + k), make_float4(X[k].re.x, X[k].im.x, X[k + 1].re.x, X[k + 1].im.x));
-        __stcs(reinterpret_cast<float4*>(yo + k), make_float4(X[k].re.y, X[k].im.y, X[k + 1].re.y, X[k + 1].im.y));
+        sts128(ptile + (((c0 + k / 2) ^ sx) * 16), make_float4(X[k].re.x, X[k].im.x, X[k + 1].re.x, X[k + 1].im.x));
+        sts128(ptile + (((kM / 2 + c0 + k / 2) ^ sx) * 16), make_float4(X[k].re.y, X[k].im.y, X[k + 1].re.y, X[k + 1].im.y));
     }
 }
 
@@ -162,14 +182,15 @@ __device__ __forceinline__ void dft_role(const TinyParams& p, uint32_t smem, int
     const int n_slabs = (int)gridDim.x * kUnits * kSPW;
 
     int pi[kPPT];                                                       // pair of the unit-batch: slab sw = pi / 16, pair r = pi % 16
-    long long qb[kPPT], qe[kPPT];                                       // first pair of the slab, end of the slab
 #pragma unroll
-    for (int pp = 0; pp < kPPT; pp++) {
-        pi[pp] = (kTPP == 2) ? (lane >> 1) : lane + 32 * pp;
+    for (int pp = 0; pp < kPPT; pp++) pi[pp] = (kTPP == 2) ? (lane >> 1) : lane + 32 * pp;
+    long long sq0[kSPW], sqe[kSPW];                                     // per slab of the warp: first pair, end
+#pragma unroll
+    for (int sw = 0; sw < kSPW; sw++) {
         long long b0, b1;
-        slab_range(p.n_pairs, n_slabs, slab0 + pi[pp] / kPairsPerBatch, b0, b1);
-        qb[pp] = b0 * kPairsPerBatch + (pi[pp] % kPairsPerBatch);
-        qe[pp] = min(b1 * kPairsPerBatch, p.n_pairs);
+        slab_range(p.n_pairs, n_slabs, slab0 + sw, b0, b1);
+        sq0[sw] = b0 * kPairsPerBatch;
+        sqe[sw] = min(b1 * kPairsPerBatch, p.n_pairs);
     }
     float twr[16], twi[16];                                             // M = 32: W_32^{tt k1}
     if (kM == 32) {
@@ -192,19 +213,17 @@ __device__ __forceinline__ void dft_role(const TinyParams& p, uint32_t smem, int
 #pragma unroll
             for (int n = 0; n < kNV; n++) v[pp][n] = ldc2(vtile + (pi[pp] * kM + swz<kM>(kTPP * n + tt, r)) * 16);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(mb + 8 * (2 + b));                   // V[b] may be overwritten
+        __syncwarp();                                                   // (M = 32: the pair's other thread has read too)
 #pragma unroll
         for (int pp = 0; pp < kPPT; pp++) {
-            const long long q = qb[pp] + lb * kPairsPerBatch;
-            const bool ok = q < qe[pp];
-            float2* ye = p.y + (p.f0 + 2 * q) * (long long)kM;
+            const uint32_t ptile = vtile + (pi[pp] * kM) * 16;          // the pair's own region: only its thread(s) read it
+            const int sx = pi[pp] & (kM - 1);
             if constexpr (kM == 8) {
                 dft_r<8>(v[pp]);
-                if (ok) store_bins<8>(v[pp], ye, ye + kM);
+                stash_bins<kM, 8>(v[pp], ptile, sx, 0);
             } else if constexpr (kM == 16) {
                 dft_r<16>(v[pp]);
-                if (ok) store_bins<16>(v[pp], ye, ye + kM);
+                stash_bins<kM, 16>(v[pp], ptile, sx, 0);
             } else {
                 // n = 2 n1 + tt: radix 16 over n1, twiddle W_32^{tt k1}, then X[k1 + 16 k2] = A_0[k1] + (-1)^k2 A_1[k1];
                 // thread tt keeps k2 = tt: bins 16 tt .. 16 tt + 15
@@ -218,9 +237,25 @@ __device__ __forceinline__ void dft_role(const TinyParams& p, uint32_t smem, int
                     o.im.x = __shfl_xor_sync(0xffffffffu, a.im.x, 1); o.im.y = __shfl_xor_sync(0xffffffffu, a.im.y, 1);
                     v[pp][k] = tt ? csub(o, a) : cadd(a, o);
                 }
-                if (ok) store_bins<16>(v[pp], ye + 16 * tt, ye + kM + 16 * tt);
+                stash_bins<kM, 16>(v[pp], ptile, sx, 8 * tt);
             }
         }
+        __syncwarp();
+        // cooperative read-out: the 32 frames of a slab are one contiguous run of output, 512 bytes per warp store
+#pragma unroll
+        for (int g0 = 0; g0 < 32 * kPairsPerBatch; g0 += 32) {
+            const int g = g0 + lane;
+            const int pj = g / kM, c = g % kM;                          // pair of the unit-batch, chunk inside the pair
+            const int sw = pj / kPairsPerBatch;
+            const long long q = sq0[sw] + lb * kPairsPerBatch + (pj % kPairsPerBatch);
+            const float4 z = lds128(vtile + (pj * kM + (c ^ (pj & (kM - 1)))) * 16);
+            if (q < sqe[sw]) {
+                float2* dst = p.y + (p.f0 + 2 * q + (c >= kM / 2 ? 1 : 0)) * (long long)kM + 2 * (c % (kM / 2));
+                __stcs(reinterpret_cast<float4*>(dst), z);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mb + 8 * (2 + b));                   // V[b] may be overwritten
     }
 }
 
