@@ -29,7 +29,7 @@ using namespace yg::dev;
 constexpr int kPairsPerBatch = 16;
 constexpr int kRoleThreads = 256;
 constexpr int kUnits = 8;                                        // (FIR warp, DFT warp) pairs per CTA
-constexpr int kInStageBytes = kRoleThreads * kPairsPerBatch * 8;  // 32 KB: one batch of input, one column per FIR lane
+constexpr int kInStageBytes = kRoleThreads * kPairsPerBatch * 8;  // 32 KB: one batch of input (4 KB per FIR warp)
 constexpr int kVUnitBytes = 32 * kPairsPerBatch * 16;             // 8 KB: one batch of V of one unit
 constexpr int kVOff = 2 * kInStageBytes;
 constexpr int kMbar = kVOff + 2 * kUnits * kVUnitBytes;           // per unit: vfull[2], vfree[2]
@@ -67,9 +67,7 @@ __device__ __forceinline__ void fir_role(const TinyParams& p, uint32_t smem, int
     const int pos = (br < kM2) ? (kM2 - 1 - br) : (kM + kM2 - 1 - br);
     long long b0, b1;
     slab_range(p.n_pairs, (int)gridDim.x * kUnits * kSPW, ((int)blockIdx.x * kUnits + unit) * kSPW + sw, b0, b1);
-    const long long q_end = min(b1 * kPairsPerBatch, p.n_pairs);       // pairs of this slab end here
     const uint32_t mb = smem + kMbar + unit * 32;
-    (void)q_end;
 
     float2 T[kTaps];
 #pragma unroll
