@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""tools/stress_parity.py [seconds] [seed] -- randomized parity stress of every firpfbch2 path on a GPU.
+
+Random geometry (every fused size plus a few generic ones), random semi-length, random sequence of call sizes
+(tiny, odd, ragged, large), now and then a device buffer that starts on an odd sample; the whole stream is
+compared with the CPU oracle (rel-RMS <= 1e-5, per-frame max-abs <= 1e-4 of the output scale).  Complements the
+fixed cases of tests/test_gpu_parity.py; prints one line per case and exits non-zero on the first mismatch.
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+import yagi_b200 as yb
+from oracle import pyoracle as po
+
+
+def rand_c(rng, n):
+    return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+
+
+def main():
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    rng = np.random.default_rng(seed)
+    sizes = [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 6, 24, 48, 100]
+    t0 = time.time()
+    case = 0
+    while time.time() - t0 < budget:
+        case += 1
+        M = int(rng.choice(sizes))
+        synth = bool(rng.integers(0, 2))
+        m = int(rng.integers(1, 8 if synth else 9))
+        # total frames: enough for several batches per slab sometimes, small otherwise; bounded by oracle time
+        total_samples = int(rng.choice([1 << 16, 1 << 18, 1 << 20, 3 << 20]))
+        K = max(40, total_samples // (M // 2))
+        if M >= 1024:
+            K = min(K, 6000)
+        h = rng.standard_normal(2 * M * m).astype(np.float32)
+        nin = M if synth else M // 2
+        nout = M // 2 if synth else M
+        x = rand_c(rng, K * nin)
+        otype, gtype = (po.SYNTHESIZER, yb.SYNTHESIZER) if synth else (po.ANALYZER, yb.ANALYZER)
+        ref = po.FirPfbCh2.new(otype, M, m, h).execute_block(x).reshape(K, nout)
+        q = yb.FirPfbCh2.new(gtype, M, m, h)
+        # random cuts
+        cuts = [0]
+        while cuts[-1] < K:
+            kind = rng.integers(0, 4)
+            step = int([rng.integers(1, 8), rng.integers(30, 300), rng.integers(300, 5000), rng.integers(5000, 200000)][kind])
+            cuts.append(min(K, cuts[-1] + step))
+        outs, paths = [], set()
+        for a, b in zip(cuts, cuts[1:]):
+            seg = x[a * nin: b * nin]
+            if rng.integers(0, 6) == 0:                       # device buffer starting on an odd sample
+                buf = torch.zeros(seg.size + 1, dtype=torch.complex64, device="cuda")
+                buf[1:] = torch.from_numpy(seg).cuda()
+                outs.append(q.execute_block(buf[1:]).cpu().numpy())
+            else:
+                outs.append(q.execute_block(seg))
+            paths.add(q.last_path())
+        y = np.concatenate(outs).reshape(K, nout)
+        scale = max(1.0, float(np.abs(ref).max()))
+        per_frame = np.abs(y - ref).max(axis=1) / scale
+        rel = float(np.linalg.norm(y - ref) / max(np.linalg.norm(ref), 1e-30))
+        ok = per_frame.max() <= 1e-4 and rel <= 1e-5
+        print("case %3d %s M=%4d m=%d K=%6d calls=%3d paths=%s rel-RMS=%.2e max=%.2e %s" % (
+            case, "syn" if synth else "ana", M, m, K, len(cuts) - 1, sorted(paths), rel, float(per_frame.max()),
+            "ok" if ok else "MISMATCH at frame %d" % int(per_frame.argmax())), flush=True)
+        if not ok:
+            sys.exit(1)
+    print("stress ok: %d cases in %.0f s" % (case, time.time() - t0))
+
+
+if __name__ == "__main__":
+    main()
