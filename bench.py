@@ -230,6 +230,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # host placement for the e2e leg: pinned buffers local to this GPU's PCIe root (yagi_b200/_numa.py)
+    numa_node = yb.bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
@@ -321,7 +323,7 @@ def main():
             dt = float(td.item())
             # result check of the e2e path against the device-resident path (same input, fresh state)
             e2e = {"value": (N * world) / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 16 * N,
-                   "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+                   "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "numa_node_rank0": numa_node,
                    "api": "yg_firpfbch2_crcf_execute_block (host pointers, pinned, chunked 3-stream pipeline)"}
             hx.close(); hy.close()
         except Exception as exc:  # report, do not hide

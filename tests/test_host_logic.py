@@ -124,3 +124,16 @@ def test_stream_shards():
     assert [len(r) for r in sh] == [512] * 8
     sh = stream_shards(10, 4)
     assert sum(len(r) for r in sh) == 10 and sh[0].start == 0 and sh[-1].stop == 10
+
+
+def test_numa_helper_parses_cpulists_and_is_a_no_op_without_a_gpu():
+    """yagi_b200/_numa.py: cpulist parsing; without a CUDA device (or without sysfs NUMA data) nothing is changed."""
+    import os
+    from yagi_b200._numa import _parse_cpulist, bind_to_gpu_numa_node
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    import torch
+    if not torch.cuda.is_available():
+        assert bind_to_gpu_numa_node(0) is None
+        assert os.sched_getaffinity(0) == before

@@ -10,9 +10,11 @@ from .filter import FirFilt, fir_design_kaiser
 from .multichannel import ANALYZER, SYNTHESIZER, FirPfbCh, FirPfbCh2, FirPfbChType
 from .gather import all_gather_frames, channel_major
 from .sharding import TimeShard, firpfbch2_time_shards, stream_shards
+from ._numa import bind_to_gpu_numa_node, gpu_numa_node
 
 __all__ = [
     "ANALYZER", "SYNTHESIZER", "FirPfbChType", "FirPfbCh2", "FirPfbCh", "FirFilt", "fir_design_kaiser",
     "PinnedArray", "TimeShard", "firpfbch2_time_shards", "stream_shards", "all_gather_frames", "channel_major",
+    "bind_to_gpu_numa_node", "gpu_numa_node",
     "YagiError", "InternalError", "ConfigError", "ValueError_", "RangeError", "ModeError", "NoConvergenceError",
 ]
