@@ -81,6 +81,9 @@ int32_t yg_firpfbch2_crcf_reset(yg_firpfbch2_crcf q);                       /* z
 int32_t yg_firpfbch2_crcf_execute(yg_firpfbch2_crcf q, const yg_cf32* x, yg_cf32* y);
 /* execute_block(&mut self, x, n, y): n_frames consecutive frames (cf. firdecim.rs:193-205) */
 int32_t yg_firpfbch2_crcf_execute_block(yg_firpfbch2_crcf q, const yg_cf32* x, size_t n_frames, yg_cf32* y);
+/* Same on device pointers, asynchronous on `cuda_stream` (NULL = the CUDA default stream).  Any 8-byte aligned
+ * pointers work; the fused kernels (last_path 2 / 3) additionally want d_x and d_y 16-byte aligned (every
+ * cudaMalloc pointer plus a whole number of frames is) and otherwise hand the call to the generic kernels. */
 int32_t yg_firpfbch2_crcf_execute_block_dev(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames,
                                             yg_cf32* d_y, void* cuda_stream);
 int32_t yg_firpfbch2_crcf_sync(yg_firpfbch2_crcf q);                        /* wait for all work queued on this handle */
@@ -95,7 +98,7 @@ int32_t yg_firpfbch2_crcf_get_taps(yg_firpfbch2_crcf q, float* h /* 2*M*m */);
 int32_t yg_firpfbch2_crcf_state_len(yg_firpfbch2_crcf q, size_t* n_cf32);
 int32_t yg_firpfbch2_crcf_get_state(yg_firpfbch2_crcf q, yg_cf32* hist, int32_t* flag);
 int32_t yg_firpfbch2_crcf_set_state(yg_firpfbch2_crcf q, const yg_cf32* hist, int32_t flag);
-/* which kernel the last execute_block* used: 0 none, 1 generic, 2 fused fast path */
+/* which kernel the last execute_block* used: 0 none, 1 generic, 2 fused (M = 8 .. 256), 3 large-M path (M = 512 .. 4096) */
 int32_t yg_firpfbch2_crcf_last_path(yg_firpfbch2_crcf q, int32_t* path);
 /* device time of the dominant kernel of the last execute_block_dev call, in ms (CUDA events
  * recorded on the launching stream around that kernel only); syncs the stream */
