@@ -419,10 +419,11 @@ def test_fused_round_trip_M256():
     assert np.abs(y[D:] - x[: N - D]).max() < 2e-3
 
 
-@pytest.mark.parametrize("h_len,S_,N", [(63, 3, 10000), (64, 2, 4096 + 17), (1, 4, 5000), (23, 1, 9000), (65, 2, 5000)])
+@pytest.mark.parametrize("h_len,S_,N", [(63, 3, 10000), (64, 2, 4096 + 17), (1, 4, 5000), (23, 1, 9000), (65, 2, 5000),
+                                        (100, 2, 9000), (128, 1, 4096 * 2 + 5), (200, 3, 10000), (256, 2, 8000), (257, 1, 5000)])
 def test_firfilt_fast_kernel_edges(h_len, S_, N):
-    """Register-blocked firfilt kernel (h_len <= 64): ragged tile ends, history across calls, 1..64 taps;
-    h_len = 65 exercises the generic kernel at the same sizes."""
+    """Register-blocked firfilt kernel (tap capacities 64 / 128 / 256): ragged tile ends, history across calls,
+    1..256 taps; h_len = 257 exercises the generic kernel at the same sizes."""
     rng = np.random.default_rng(h_len * 7 + S_)
     h = rng.standard_normal(h_len).astype(np.float32)
     x = _rand_c(rng, S_ * N).reshape(S_, N)

@@ -126,6 +126,11 @@ def main():
         flops = 252.0 * S * n
         report("firfilt_crcf 63 taps, 1024 streams x 2^20", ms, 16.0 * S * n, S * n, "samples",
                {"fp32_TFLOPs": round(flops / (ms * 1e-3) / 1e12, 2)})
+        for taps in (127, 255):                 # the same kernel at tap capacities 128 / 256 (FP32-bound, not a BASELINE config)
+            q = yb.FirFilt.new_kaiser(taps, 0.25, 60.0, 0.0, n_streams=S)
+            ms = timed(lambda: q.execute_block(x, out=y), steps=3)
+            report("firfilt_crcf %d taps, 1024 streams x 2^20" % taps, ms, 16.0 * S * n, S * n, "samples",
+                   {"fp32_TFLOPs": round(4.0 * taps * S * n / (ms * 1e-3) / 1e12, 2)})
 
 
 if __name__ == "__main__":

@@ -1,4 +1,5 @@
-// firfilt_fast.cu -- batched firfilt_crcf for up to 64 taps (BASELINE config #2: 63 taps, 1024 streams).
+// firfilt_fast.cu -- batched firfilt_crcf for up to 256 taps, instantiated for tap capacities 64 (BASELINE config #2:
+// 63 taps, 1024 streams), 128 and 256.
 //
 //   y[s][n] = scale * sum_k h[k] x[s][n-k]                 (src/filter/fir/firfilt.rs:241-245, :267-278)
 //
@@ -21,13 +22,11 @@ namespace yg {
 
 namespace {
 
-constexpr int kH = 64;                       // taps, zero-padded
 constexpr int kR = 16;                       // outputs per thread
 constexpr int kThreads = 256;
 constexpr int kTile = kThreads * kR;         // 4096 outputs per CTA
-constexpr int kIn = kTile + kH - 1;          // samples staged per tile
-constexpr int kPadded = kIn + (kIn >> 4) + 1;
 
+template <int kH>                            // tap capacity (taps are zero-padded up to it)
 struct FirTaps { float h[kH]; };
 
 __device__ __forceinline__ int pad(int g) { return g + (g >> 4); }
@@ -35,8 +34,8 @@ __device__ __forceinline__ int pad(int g) { return g + (g >> 4); }
 // One input sample (relative index II inside the thread's 79-sample span) feeds every output r it
 // belongs to through tap k = r + 63 - II.  Template recursion forces the full static unroll that keeps
 // every tap a constant-bank operand and every accumulator a fixed register.
-template <int II>
-__device__ __forceinline__ void fir_step(float2 (&acc)[kR], const float2* tile, int g0, const FirTaps& taps)
+template <int kH, int II>
+__device__ __forceinline__ void fir_step(float2 (&acc)[kR], const float2* tile, int g0, const FirTaps<kH>& taps)
 {
     const float2 v = tile[pad(g0 + II)];
 #pragma unroll
@@ -45,13 +44,27 @@ __device__ __forceinline__ void fir_step(float2 (&acc)[kR], const float2* tile, 
         const int k = r + kbase;
         if (k >= 0 && k < kH) acc[r] = __ffma2_rn(v, make_float2(taps.h[k], taps.h[k]), acc[r]);
     }
-    if constexpr (II > 0) fir_step<II - 1>(acc, tile, g0, taps);
+}
+// samples II = HI-1 down to LO (newest first), split in halves so that the template depth stays logarithmic
+template <int kH, int LO, int HI>
+__device__ __forceinline__ void fir_steps(float2 (&acc)[kR], const float2* tile, int g0, const FirTaps<kH>& taps)
+{
+    if constexpr (HI - LO == 1) {
+        fir_step<kH, LO>(acc, tile, g0, taps);
+    } else {
+        constexpr int MID = (LO + HI) / 2;
+        fir_steps<kH, MID, HI>(acc, tile, g0, taps);
+        fir_steps<kH, LO, MID>(acc, tile, g0, taps);
+    }
 }
 
+template <int kH>
 __global__ void __launch_bounds__(kThreads, 4)
-k_firfilt_fast(const FirTaps taps, float scale, const float2* __restrict__ hist, int Hlen,
+k_firfilt_fast(const FirTaps<kH> taps, float scale, const float2* __restrict__ hist, int Hlen,
                const float2* __restrict__ x, float2* __restrict__ y, long long n, int tiles_per_stream)
 {
+    constexpr int kIn = kTile + kH - 1;          // samples staged per tile
+    constexpr int kPadded = kIn + (kIn >> 4) + 1;
     __shared__ float2 tile[kPadded];
     const int t = threadIdx.x;
     const long long s = blockIdx.x / tiles_per_stream;
@@ -84,7 +97,7 @@ k_firfilt_fast(const FirTaps taps, float scale, const float2* __restrict__ hist,
     // output r of this thread needs samples g = 16 t + r - k + 63; sample ii = g - 16 t feeds output r
     // through tap k = r + 63 - ii.  Newest sample first => k ascending for every output.
     const int g0 = kR * t;
-    fir_step<kR + kH - 2>(acc, tile, g0, taps);
+    fir_steps<kH, 0, kR + kH - 1>(acc, tile, g0, taps);
     __syncthreads();                                         // everyone is done reading the inputs
 #pragma unroll
     for (int r = 0; r < kR; r++) tile[pad(g0 + r)] = make_float2(acc[r].x * scale, acc[r].y * scale);
@@ -99,19 +112,30 @@ k_firfilt_fast(const FirTaps taps, float scale, const float2* __restrict__ hist,
 
 }  // namespace
 
-bool firfilt_fast_supported(size_t h_len) { return h_len >= 1 && h_len <= (size_t)kH; }
-
-int32_t firfilt_fast_launch(const float* h, size_t h_len, float scale, const float2* hist, long long Hlen, const float2* x,
-                            float2* y, long long n, long long n_streams, cudaStream_t st)
+namespace {
+template <int kH>
+int32_t launch_h(const float* h, size_t h_len, float scale, const float2* hist, long long Hlen, const float2* x,
+                 float2* y, long long n, long long n_streams, cudaStream_t st)
 {
-    FirTaps taps;
+    FirTaps<kH> taps;
     for (int k = 0; k < kH; k++) taps.h[k] = (k < (int)h_len) ? h[k] : 0.0f;
     const long long tiles = (n + kTile - 1) / kTile;
     const long long grid = tiles * n_streams;
     if (grid > 0x7fffffffLL) return fail(YG_ERANGE, "too many tiles for one launch");
-    k_firfilt_fast<<<(unsigned)grid, kThreads, 0, st>>>(taps, scale, hist, (int)Hlen, x, y, n, (int)tiles);
+    k_firfilt_fast<kH><<<(unsigned)grid, kThreads, 0, st>>>(taps, scale, hist, (int)Hlen, x, y, n, (int)tiles);
     YG_CUDA(cudaGetLastError());
     return YG_OK;
+}
+}  // namespace
+
+bool firfilt_fast_supported(size_t h_len) { return h_len >= 1 && h_len <= 256; }
+
+int32_t firfilt_fast_launch(const float* h, size_t h_len, float scale, const float2* hist, long long Hlen, const float2* x,
+                            float2* y, long long n, long long n_streams, cudaStream_t st)
+{
+    if (h_len <= 64) return launch_h<64>(h, h_len, scale, hist, Hlen, x, y, n, n_streams, st);
+    if (h_len <= 128) return launch_h<128>(h, h_len, scale, hist, Hlen, x, y, n, n_streams, st);
+    return launch_h<256>(h, h_len, scale, hist, Hlen, x, y, n, n_streams, st);
 }
 
 }  // namespace yg
