@@ -61,30 +61,40 @@ __device__ __forceinline__ void fir_steps(float2 (&acc)[kR], const float2* tile,
 template <int kH>
 __global__ void __launch_bounds__(kThreads, 4)
 k_firfilt_fast(const FirTaps<kH> taps, float scale, const float2* __restrict__ hist, int Hlen,
-               const float2* __restrict__ x, float2* __restrict__ y, long long n, int tiles_per_stream)
+               const float2* __restrict__ x, float2* __restrict__ y, long long n)
 {
     constexpr int kIn = kTile + kH - 1;          // samples staged per tile
     constexpr int kPadded = kIn + (kIn >> 4) + 1;
     __shared__ float2 tile[kPadded];
     const int t = threadIdx.x;
-    const long long s = blockIdx.x / tiles_per_stream;
-    const long long n0 = (long long)(blockIdx.x - s * tiles_per_stream) * kTile;     // first output of the tile
+    const long long s = blockIdx.y;                                                   // stream
+    const long long n0 = (long long)blockIdx.x * kTile;                               // first output of the tile
     const float2* xs = x + s * n;
     const float2* hs = hist + s * Hlen;
 
-    // stage samples n0 - 63 .. n0 + 4095 (zeros outside the stream, history for negative indices) with
+    // stage samples n0 - (kH-1) .. n0 + 4095 (zeros outside the stream, history for negative indices) with
     // asynchronous 8-byte copies (LDGSTS): all ~17 per thread are in flight at once, no registers held
     const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+    if (n0 >= kH - 1 && n0 + kTile <= n) {                                            // interior tile: no edge logic
+        const float2* src0 = xs + (n0 - (kH - 1));
 #pragma unroll
-    for (int i = 0; i < (kIn + kThreads - 1) / kThreads; i++) {
-        const int g = t + i * kThreads;
-        if (g < kIn) {
-            const long long gi = n0 - (kH - 1) + g;
-            const float2* src = xs;
-            uint32_t bytes = 0;                                   // 0 => the 8 destination bytes are zero-filled
-            if (gi >= 0) { if (gi < n) { src = xs + gi; bytes = 8; } }
-            else if (gi >= -(long long)Hlen) { src = hs + (Hlen + gi); bytes = 8; }
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(tile_s + 8u * (uint32_t)pad(g)), "l"(src), "r"(bytes) : "memory");
+        for (int i = 0; i < (kIn + kThreads - 1) / kThreads; i++) {
+            const int g = t + i * kThreads;
+            if (g < kIn)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_s + 8u * (uint32_t)pad(g)), "l"(src0 + g) : "memory");
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < (kIn + kThreads - 1) / kThreads; i++) {
+            const int g = t + i * kThreads;
+            if (g < kIn) {
+                const long long gi = n0 - (kH - 1) + g;
+                const float2* src = xs;
+                uint32_t bytes = 0;                                   // 0 => the 8 destination bytes are zero-filled
+                if (gi >= 0) { if (gi < n) { src = xs + gi; bytes = 8; } }
+                else if (gi >= -(long long)Hlen) { src = hs + (Hlen + gi); bytes = 8; }
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(tile_s + 8u * (uint32_t)pad(g)), "l"(src), "r"(bytes) : "memory");
+            }
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -120,10 +130,13 @@ int32_t launch_h(const float* h, size_t h_len, float scale, const float2* hist, 
     FirTaps<kH> taps;
     for (int k = 0; k < kH; k++) taps.h[k] = (k < (int)h_len) ? h[k] : 0.0f;
     const long long tiles = (n + kTile - 1) / kTile;
-    const long long grid = tiles * n_streams;
-    if (grid > 0x7fffffffLL) return fail(YG_ERANGE, "too many tiles for one launch");
-    k_firfilt_fast<kH><<<(unsigned)grid, kThreads, 0, st>>>(taps, scale, hist, (int)Hlen, x, y, n, (int)tiles);
-    YG_CUDA(cudaGetLastError());
+    if (tiles > 0x7fffffffLL) return fail(YG_ERANGE, "too many tiles for one launch");
+    for (long long s0 = 0; s0 < n_streams; s0 += 65535) {                  // grid.y carries the stream index
+        const long long ns = std::min<long long>(65535, n_streams - s0);
+        k_firfilt_fast<kH><<<dim3((unsigned)tiles, (unsigned)ns), kThreads, 0, st>>>(taps, scale, hist + s0 * Hlen, (int)Hlen,
+                                                                                    x + s0 * n, y + s0 * n, n);
+        YG_CUDA(cudaGetLastError());
+    }
     return YG_OK;
 }
 }  // namespace
