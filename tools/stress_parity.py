@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""tools/stress_parity.py [seconds] [seed] -- randomized parity stress of every firpfbch2 path on a GPU.
+"""tools/stress_parity.py [seconds] [seed] [streams] -- randomized parity stress of every firpfbch2 path on a GPU
+(with `streams`: of the many-stream objects firpfbch and firfilt instead).
 
 Random geometry (every fused size plus a few generic ones), random semi-length, random sequence of call sizes
 (tiny, odd, ragged, large), now and then a device buffer that starts on an odd sample; the whole stream is
@@ -24,10 +25,58 @@ def rand_c(rng, n):
     return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
 
 
+def check(name, y, ref, rows_axis=1):
+    scale = max(1.0, float(np.abs(ref).max()))
+    worst = np.abs(y - ref).max(axis=rows_axis) / scale
+    rel = float(np.linalg.norm(y - ref) / max(np.linalg.norm(ref), 1e-30))
+    ok = worst.max() <= 1e-4 and rel <= 1e-5
+    print("%s rel-RMS=%.2e max=%.2e %s" % (name, rel, float(worst.max()), "ok" if ok else "MISMATCH at row %d" % int(worst.argmax())), flush=True)
+    if not ok:
+        sys.exit(1)
+
+
+def stream_objects(rng, budget):
+    """firpfbch (critically sampled, many streams) and batched firfilt: random geometry, streams, call cuts."""
+    t0 = time.time()
+    case = 0
+    while time.time() - t0 < budget:
+        case += 1
+        if rng.integers(0, 2):
+            M = int(rng.choice([64, 64, 64, 16, 5, 32]))
+            p = int(rng.integers(1, 17))
+            S_ = int(rng.integers(1, 40)) if M != 64 else int(rng.choice([1, 3, 4, 9, 37, 130, 700]))
+            Q = int(rng.integers(3, 120))                      # frames per stream
+            synth = bool(rng.integers(0, 2))
+            h = rng.standard_normal(M * p).astype(np.float32)
+            x = rand_c(rng, S_ * Q * M).reshape(S_, Q * M)
+            q = yb.FirPfbCh.new(yb.SYNTHESIZER if synth else yb.ANALYZER, M, p, h, n_streams=S_)
+            cuts = sorted(set([0, Q] + [int(c) for c in rng.integers(0, Q + 1, size=int(rng.integers(0, 4)))]))
+            y = np.concatenate([q.execute_block(np.ascontiguousarray(x[:, a * M: b * M])).reshape(S_, -1)
+                                for a, b in zip(cuts, cuts[1:]) if b > a], axis=1)
+            ref = np.stack([po.FirPfbCh.new(po.SYNTHESIZER if synth else po.ANALYZER, M, p, h).execute_block(x[s]) for s in range(S_)])
+            check("stream case %3d firpfbch %s M=%2d p=%2d S=%3d Q=%3d calls=%d" % (case, "syn" if synth else "ana", M, p, S_, Q, len(cuts) - 1), y, ref)
+        else:
+            h_len = int(rng.choice([1, 7, 23, 63, 64, 65, 100, 128, 200, 256, 257, 400]))
+            S_ = int(rng.integers(1, 6))
+            N = int(rng.choice([300, 4096, 5000, 20000, 70000]))
+            h = rng.standard_normal(h_len).astype(np.float32)
+            x = rand_c(rng, S_ * N).reshape(S_, N)
+            q = yb.FirFilt.new(h, n_streams=S_)
+            sc = float(rng.choice([1.0, 0.37]))
+            q.set_scale(sc)
+            cuts = sorted(set([0, N] + [int(c) for c in rng.integers(0, N + 1, size=int(rng.integers(0, 3)))]))
+            y = np.concatenate([q.execute_block(np.ascontiguousarray(x[:, a:b])).reshape(S_, -1) for a, b in zip(cuts, cuts[1:]) if b > a], axis=1)
+            ref = np.stack([po.firfilt_crcf(h, x[s], scale=sc) for s in range(S_)])
+            check("stream case %3d firfilt h_len=%3d S=%d N=%5d calls=%d" % (case, h_len, S_, N, len(cuts) - 1), y, ref)
+    print("stream objects ok: %d cases" % case)
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     rng = np.random.default_rng(seed)
+    if len(sys.argv) > 3 and sys.argv[3] == "streams":
+        return stream_objects(rng, budget)
     sizes = [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 6, 24, 48, 100]
     t0 = time.time()
     case = 0
