@@ -128,6 +128,8 @@ int32_t yg_firpfbch_crcf_get_M(yg_firpfbch_crcf q, uint32_t* M);
 int32_t yg_firpfbch_crcf_get_p(yg_firpfbch_crcf q, uint32_t* p);
 int32_t yg_firpfbch_crcf_get_n_streams(yg_firpfbch_crcf q, uint32_t* n);
 int32_t yg_firpfbch_crcf_get_taps(yg_firpfbch_crcf q, float* h /* M*p */);
+/* which kernel the last execute_block* used for the bulk of the streams: 0 none, 1 generic, 2 fused (M = 8, 16, 32, 64) */
+int32_t yg_firpfbch_crcf_last_path(yg_firpfbch_crcf q, int32_t* path);
 
 /* -------------------------------------------------------------- firfilt_crcf */
 /* Direct-form FIR, real taps x complex samples: FirFilter<Complex32, f32>

@@ -77,6 +77,7 @@ extern "C" {
     pub fn yg_firpfbch_crcf_get_p(q: yg_firpfbch_crcf, p: *mut u32) -> i32;
     pub fn yg_firpfbch_crcf_get_n_streams(q: yg_firpfbch_crcf, n: *mut u32) -> i32;
     pub fn yg_firpfbch_crcf_get_taps(q: yg_firpfbch_crcf, h: *mut f32) -> i32;
+    pub fn yg_firpfbch_crcf_last_path(q: yg_firpfbch_crcf, path: *mut i32) -> i32;
 
     pub fn yg_firfilt_crcf_create(h: *const f32, h_len: size_t, n_streams: u32, out: *mut yg_firfilt_crcf) -> i32;
     pub fn yg_firfilt_crcf_create_kaiser(n: u32, fc: f32, as_: f32, mu: f32, n_streams: u32, out: *mut yg_firfilt_crcf) -> i32;

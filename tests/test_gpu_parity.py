@@ -730,3 +730,25 @@ def test_fused_tiny_M_synthesis(M, m):
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
     assert_parity(y / scale, ref / scale, "tiny-M synthesis M=%d m=%d" % (M, m))
+
+
+@pytest.mark.parametrize("type_,otype", [(A, po.ANALYZER), (S, po.SYNTHESIZER)])
+@pytest.mark.parametrize("M,p,S_,Q", [(16, 14, 9, 50), (16, 2, 4, 16), (16, 16, 700, 40), (8, 14, 13, 47), (8, 6, 4, 33),
+                                      (8, 16, 3000, 20), (32, 14, 5, 100), (32, 4, 1, 17), (32, 16, 400, 37)])
+def test_firpfbch_fused_tiny_M(M, p, S_, Q, type_, otype):
+    """Fused critically sampled channelizers for M = 8 / 16 / 32 (analysis and synthesis): groups of 32/M streams on
+    the fused kernel, the remainder on the generic one; ragged 16-frame batches; history carried across calls; more
+    items than units (ranges that start mid-stream, warm-up items for the synthesiser)."""
+    rng = np.random.default_rng(p * 100 + S_ + M)
+    h = rng.standard_normal(M * p).astype(np.float32)
+    x = _rand_c(rng, S_ * Q * M).reshape(S_, Q * M)
+    q = yb.FirPfbCh.new(type_, M, p, h, n_streams=S_)
+    cuts = [0, Q // 2 + 3, Q // 2 + 4, Q]
+    y = np.concatenate([q.execute_block(np.ascontiguousarray(x[:, a * M: b * M])).reshape(S_, -1) for a, b in zip(cuts, cuts[1:])], axis=1)
+    if S_ >= 32 // M and Q - cuts[2] >= 16:
+        assert q.last_path() == 2
+    ref = np.stack([po.FirPfbCh.new(otype, M, p, h).execute_block(x[s]) for s in range(S_)])
+    scale = max(1.0, np.abs(ref).max())
+    per_stream = np.abs(y - ref).max(axis=1) / scale
+    assert per_stream.max() <= 1e-4, int(per_stream.argmax())
+    assert_parity(y / scale, ref / scale, "tiny firpfbch type=%d M=%d p=%d S=%d" % (int(type_), M, p, S_))

@@ -115,8 +115,16 @@ def main():
         qs = yb.FirPfbCh.new_kaiser(yb.SYNTHESIZER, M, m, 60.0, n_streams=S)
         ms = timed(lambda: qs.execute_block(x, n // M, out=y), steps=5)
         report("firpfbch synthesis M=64 m=7, 512 streams x 2^18", ms, 16.0 * S * n, S * n, "samples_out")
-        del qs
-        del x, y, q
+        del qs, q
+        for M in (8, 16, 32):                   # the same stream-sharded workload on the tiny-M kernels
+            q = yb.FirPfbCh.new_kaiser(yb.ANALYZER, M, m, 60.0, n_streams=S)
+            ms = timed(lambda: q.execute_block(x, n // M, out=y), steps=5)
+            report("firpfbch analysis M=%d m=7, 512 streams x 2^18 (path %d)" % (M, q.last_path()), ms, 16.0 * S * n, S * n, "samples_in")
+            qs = yb.FirPfbCh.new_kaiser(yb.SYNTHESIZER, M, m, 60.0, n_streams=S)
+            ms = timed(lambda: qs.execute_block(x, n // M, out=y), steps=5)
+            report("firpfbch synthesis M=%d m=7, 512 streams x 2^18 (path %d)" % (M, qs.last_path()), ms, 16.0 * S * n, S * n, "samples_out")
+            del q, qs
+        del x, y
     if "firfilt" in which:
         S, n = 1024, 1 << 20                    # BASELINE config #2: 1024 streams x 2^20 samples (8 GiB in, 8 GiB out)
         x = randc(S * n)

@@ -24,7 +24,7 @@ yg_firpfbch2_crcf_kernel_times
 yg_firpfbch_crcf_create yg_firpfbch_crcf_create_kaiser yg_firpfbch_crcf_clone yg_firpfbch_crcf_destroy
 yg_firpfbch_crcf_reset yg_firpfbch_crcf_execute yg_firpfbch_crcf_execute_block yg_firpfbch_crcf_execute_block_dev
 yg_firpfbch_crcf_sync yg_firpfbch_crcf_get_type yg_firpfbch_crcf_get_M yg_firpfbch_crcf_get_p
-yg_firpfbch_crcf_get_n_streams yg_firpfbch_crcf_get_taps
+yg_firpfbch_crcf_get_n_streams yg_firpfbch_crcf_get_taps yg_firpfbch_crcf_last_path
 yg_firfilt_crcf_create yg_firfilt_crcf_create_kaiser yg_firfilt_crcf_clone yg_firfilt_crcf_destroy
 yg_firfilt_crcf_reset yg_firfilt_crcf_set_scale yg_firfilt_crcf_get_scale yg_firfilt_crcf_get_len
 yg_firfilt_crcf_execute_block yg_firfilt_crcf_execute_block_dev yg_firfilt_crcf_sync
@@ -78,7 +78,7 @@ def lib() -> C.CDLL:
     L.yg_firpfbch_crcf_execute_block.argtypes = [vp, vp, sz, vp]
     L.yg_firpfbch_crcf_execute_block_dev.argtypes = [vp, vp, sz, vp, vp]
     L.yg_firpfbch_crcf_sync.argtypes = [vp]
-    for n in ("get_type", "get_M", "get_p", "get_n_streams", "get_taps"):
+    for n in ("get_type", "get_M", "get_p", "get_n_streams", "get_taps", "last_path"):
         getattr(L, "yg_firpfbch_crcf_" + n).argtypes = [vp, vp]
     # firfilt
     L.yg_firfilt_crcf_create.argtypes = [vp, sz, u32, vp]

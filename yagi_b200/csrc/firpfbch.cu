@@ -25,7 +25,8 @@ struct yg_firpfbch_crcf_s {
     int cur = 0;
     DevBuf<yg_cf32> d_U;           // synthesiser scratch [stream][(p-1)+n][M]
     DevBuf<yg_cf32> d_stage_x, d_stage_y;
-    FirpfbchFastPlan fast;         // fused analysis kernel (M = 64)
+    FirpfbchFastPlan fast;         // fused kernels (M = 64)
+    FirpfbchFastPlan tiny;         // fused tiny-M kernels (M = 8, 16, 32)
     int32_t last_path = 0;
 };
 
@@ -165,10 +166,18 @@ int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames
     float2* y = reinterpret_cast<float2*>(d_y);
     const size_t smem = 2 * (size_t)M * sizeof(float2);
     const int block = (int)std::min<uint32_t>(256, (M + 31) / 32 * 32);
+    // tiny-M fused kernels: groups of 32 / M streams, the remaining streams go to the generic kernels below
+    const long long spw = (M <= 32 && M > 0) ? 32 / M : 1;
+    const bool use_tiny = q->tiny.supported && S >= spw && n_frames >= 16 &&
+                          ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     if (q->type == YG_ANALYZER) {
         const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
         long long s_fast = 0;
-        if (q->fast.supported && S >= 4 && n_frames >= 16 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        if (use_tiny) {
+            s_fast = (S / spw) * spw;
+            YG_TRY(firpfbch_tiny_launch(q->tiny, hist, Hlen, x, y, (long long)n_frames, s_fast, st));
+            q->last_path = 2;
+        } else if (q->fast.supported && S >= 4 && n_frames >= 16 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
             // groups of four streams go to the fused kernel, the remaining 0..3 streams to the generic one
             s_fast = (S / 4) * 4;
             YG_TRY(firpfbch_fast_launch(q->fast, hist, Hlen, x, y, (long long)n_frames, s_fast, st));
@@ -189,7 +198,11 @@ int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames
         const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
         const long long hist_frames = Hlen / M;
         long long s_fast = 0;
-        if (q->fast.supported && S >= 4 && n_frames >= 16 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        if (use_tiny) {
+            s_fast = (S / spw) * spw;
+            YG_TRY(firpfbch_tiny_launch(q->tiny, hist, Hlen, x, y, (long long)n_frames, s_fast, st));
+            q->last_path = 2;
+        } else if (q->fast.supported && S >= 4 && n_frames >= 16 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
             s_fast = (S / 4) * 4;
             YG_TRY(firpfbch_fast_synth_launch(q->fast, hist, hist_frames, x, y, (long long)n_frames, s_fast, st));
             q->last_path = 2;
@@ -253,6 +266,7 @@ int32_t build(int32_t type, uint32_t M, uint32_t p, const float* h, size_t h_len
     // analyser: the last p-1 input frames; synthesiser: at least 16 (one warm-up batch of the fused kernel)
     q->state_len = (type == YG_ANALYZER) ? (size_t)(p - 1) * M : (size_t)std::max<uint32_t>(p - 1, 16) * M;
     TRYQ(firpfbch_fast_plan(q->fast, type, M, p, q->h.data()));
+    TRYQ(firpfbch_tiny_plan(q->tiny, type, M, p, q->h.data()));
     for (int b = 0; b < 2; b++) {
         TRYQ(q->d_hist[b].reserve(std::max<size_t>(1, q->state_len * n_streams)));
         CUDAQ(cudaMemset(q->d_hist[b].p, 0, std::max<size_t>(1, q->state_len * n_streams) * sizeof(yg_cf32)));
@@ -312,6 +326,7 @@ int32_t yg_firpfbch_crcf_destroy(yg_firpfbch_crcf q)
     q->d_h.release(); q->d_tw.release(); q->d_hist[0].release(); q->d_hist[1].release(); q->d_U.release();
     q->d_stage_x.release(); q->d_stage_y.release();
     firpfbch_fast_release(q->fast);
+    firpfbch_fast_release(q->tiny);
     if (q->stream) cudaStreamDestroy(q->stream);
     delete q;
     return YG_OK;
@@ -374,6 +389,7 @@ int32_t yg_firpfbch_crcf_get_type(yg_firpfbch_crcf q, int32_t* type) { YG_TRY(ch
 int32_t yg_firpfbch_crcf_get_M(yg_firpfbch_crcf q, uint32_t* M) { YG_TRY(check(q)); *M = q->M; return YG_OK; }
 int32_t yg_firpfbch_crcf_get_p(yg_firpfbch_crcf q, uint32_t* p) { YG_TRY(check(q)); *p = q->p; return YG_OK; }
 int32_t yg_firpfbch_crcf_get_n_streams(yg_firpfbch_crcf q, uint32_t* n) { YG_TRY(check(q)); *n = q->n_streams; return YG_OK; }
+int32_t yg_firpfbch_crcf_last_path(yg_firpfbch_crcf q, int32_t* path) { YG_TRY(check(q)); *path = q->last_path; return YG_OK; }
 int32_t yg_firpfbch_crcf_get_taps(yg_firpfbch_crcf q, float* h)
 {
     YG_TRY(check(q));

@@ -197,6 +197,12 @@ class FirPfbCh:
         _lib.check(_lib.lib().yg_firpfbch_crcf_clone(self._q, C.byref(q)))
         return FirPfbCh(q)
 
+    def last_path(self) -> int:
+        """0 none, 1 generic kernels, 2 fused kernel for the bulk of the streams (for tests / bench bookkeeping)."""
+        p = C.c_int32()
+        _lib.check(_lib.lib().yg_firpfbch_crcf_last_path(self._q, C.byref(p)))
+        return p.value
+
     def __del__(self):
         q = getattr(self, "_q", None)
         if q is not None and q.value:
