@@ -49,6 +49,9 @@ enum { YG_ANALYZER = 0, YG_SYNTHESIZER = 1 };
 int32_t     yg_version(void);                       /* 0xMMmmpp */
 const char* yg_last_error(void);                    /* message of this thread's last non-OK status */
 int32_t     yg_device_count(int32_t* n);
+/* kernels launched by this library in this process so far (every launch is counted; benchmarks take the difference
+ * around their timed region) */
+int32_t     yg_launch_count(uint64_t* n);
 /* page-locked host buffers for the host-pointer entry points (plain malloc'd memory works too, slower) */
 int32_t     yg_host_alloc(void** p, size_t bytes);
 int32_t     yg_host_free(void* p);
@@ -91,6 +94,7 @@ int32_t yg_firpfbch2_crcf_get_type(yg_firpfbch2_crcf q, int32_t* type);
 int32_t yg_firpfbch2_crcf_get_M(yg_firpfbch2_crcf q, uint32_t* M);
 int32_t yg_firpfbch2_crcf_get_m(yg_firpfbch2_crcf q, uint32_t* m);
 int32_t yg_firpfbch2_crcf_get_taps(yg_firpfbch2_crcf q, float* h /* 2*M*m */);
+int32_t yg_firpfbch2_crcf_get_device(yg_firpfbch2_crcf q, int32_t* dev);   /* the CUDA device the handle is bound to */
 /* Stream state as plain data (what Clone copies; also the time-shard hand-off).
  * Both types keep the tail of their INPUT stream, oldest first: analyzer the last (4m-1)*M/2
  * input samples, synthesizer the last 4m-1 input frames (M each; their IFFTs are recomputed, so the
@@ -105,6 +109,9 @@ int32_t yg_firpfbch2_crcf_last_path(yg_firpfbch2_crcf q, int32_t* path);
 int32_t yg_firpfbch2_crcf_last_kernel_ms(yg_firpfbch2_crcf q, float* ms);
 /* the same for up to `cap` most recent calls (at most 64 are kept), oldest first; *n = how many */
 int32_t yg_firpfbch2_crcf_kernel_times(yg_firpfbch2_crcf q, float* ms, size_t cap, size_t* n);
+/* The two timing events per call cost about a microsecond of stream time each; enable = 0 stops recording them
+ * (last_kernel_ms / kernel_times then report Mode errors / nothing), enable != 0 (the default) turns them back on. */
+int32_t yg_firpfbch2_crcf_set_kernel_timing(yg_firpfbch2_crcf q, int32_t enable);
 
 /* ------------------------------------------------------------- firpfbch_crcf */
 /* Critically sampled channelizer (LIQUID_COMPAT.md:1765-1780),
@@ -128,8 +135,15 @@ int32_t yg_firpfbch_crcf_get_M(yg_firpfbch_crcf q, uint32_t* M);
 int32_t yg_firpfbch_crcf_get_p(yg_firpfbch_crcf q, uint32_t* p);
 int32_t yg_firpfbch_crcf_get_n_streams(yg_firpfbch_crcf q, uint32_t* n);
 int32_t yg_firpfbch_crcf_get_taps(yg_firpfbch_crcf q, float* h /* M*p */);
+int32_t yg_firpfbch_crcf_get_device(yg_firpfbch_crcf q, int32_t* dev);
 /* which kernel the last execute_block* used for the bulk of the streams: 0 none, 1 generic, 2 fused (M = 8, 16, 32, 64) */
 int32_t yg_firpfbch_crcf_last_path(yg_firpfbch_crcf q, int32_t* path);
+
+/* ------------------------------------------------------------- output layout */
+/* Frame-major analysis output y[frame][M] -> channel-major out[channel][frame] (one contiguous time series per
+ * channel), device pointers, out of place, asynchronous on `cuda_stream`.  Not on the hot path: the step after it in
+ * an SDR pipeline. */
+int32_t yg_channel_major_dev(const yg_cf32* d_frames, size_t n_frames, uint32_t M, yg_cf32* d_out, void* cuda_stream);
 
 /* -------------------------------------------------------------- firfilt_crcf */
 /* Direct-form FIR, real taps x complex samples: FirFilter<Complex32, f32>
@@ -147,6 +161,7 @@ int32_t yg_firfilt_crcf_reset(yg_firfilt_crcf q);
 int32_t yg_firfilt_crcf_set_scale(yg_firfilt_crcf q, float scale);
 int32_t yg_firfilt_crcf_get_scale(yg_firfilt_crcf q, float* scale);
 int32_t yg_firfilt_crcf_get_len(yg_firfilt_crcf q, size_t* h_len);
+int32_t yg_firfilt_crcf_get_device(yg_firfilt_crcf q, int32_t* dev);
 int32_t yg_firfilt_crcf_execute_block(yg_firfilt_crcf q, const yg_cf32* x, size_t n, yg_cf32* y);
 int32_t yg_firfilt_crcf_execute_block_dev(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf32* d_y,
                                           void* cuda_stream);

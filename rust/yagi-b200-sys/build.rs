@@ -1,7 +1,10 @@
-// build.rs -- compiles the CUDA sources of yagi_b200 with nvcc for sm_100a and links them.
+// build.rs -- compiles EVERY CUDA source of yagi_b200 (yagi_b200/csrc/*.cu) with nvcc for sm_100a and
+// links the objects.  The list is globbed, not written out, so a new kernel file cannot be forgotten
+// (tests/test_host_logic.py::test_rust_sys_crate_tracks_the_c_abi checks this file and src/lib.rs).
 // NOT BUILT IN THE DEVELOPMENT IMAGE (no cargo/rustc there); written to the C ABI in
 // include/yagi_b200.h, which is what the Python mirror and all tests exercise.
 use std::env;
+use std::fs;
 use std::path::PathBuf;
 use std::process::Command;
 
@@ -11,15 +14,28 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
 
+    let mut sources: Vec<PathBuf> = fs::read_dir(&csrc)
+        .expect("yagi_b200/csrc not found")
+        .filter_map(|e| e.ok().map(|e| e.path()))
+        .filter(|p| p.extension().map_or(false, |x| x == "cu"))
+        .collect();
+    sources.sort();
+    assert!(!sources.is_empty(), "no .cu sources under {}", csrc.display());
+    // headers: any change rebuilds everything
+    for e in fs::read_dir(&csrc).unwrap().filter_map(|e| e.ok()) {
+        if e.path().extension().map_or(false, |x| x == "cuh") {
+            println!("cargo:rerun-if-changed={}", e.path().display());
+        }
+    }
+
     let mut objs = Vec::new();
-    for name in ["common", "firpfbch2", "firpfbch2_fast", "firpfbch2_small", "firpfbch2_synth_fast", "firpfbch2_large", "firpfbch", "firpfbch_fast", "firfilt", "firfilt_fast"] {
-        let src = csrc.join(format!("{name}.cu"));
-        let obj = out.join(format!("{name}.o"));
+    for src in &sources {
+        let obj = out.join(src.file_stem().unwrap()).with_extension("o");
         println!("cargo:rerun-if-changed={}", src.display());
         let ok = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17"])
             .args(["-Xcompiler", "-fPIC", "-c"])
-            .arg(&src)
+            .arg(src)
             .arg("-o")
             .arg(&obj)
             .status()

@@ -39,6 +39,8 @@ extern "C" {
     pub fn yg_version() -> i32;
     pub fn yg_last_error() -> *const c_char;
     pub fn yg_device_count(n: *mut i32) -> i32;
+    pub fn yg_launch_count(n: *mut u64) -> i32;
+    pub fn yg_channel_major_dev(d_frames: *const yg_cf32, n_frames: size_t, m_ch: u32, d_out: *mut yg_cf32, cuda_stream: *mut c_void) -> i32;
     pub fn yg_host_alloc(p: *mut *mut c_void, bytes: size_t) -> i32;
     pub fn yg_host_free(p: *mut c_void) -> i32;
     pub fn yg_fir_design_kaiser(n: u32, fc: f32, as_: f32, mu: f32, h: *mut f32) -> i32;
@@ -56,12 +58,14 @@ extern "C" {
     pub fn yg_firpfbch2_crcf_get_M(q: yg_firpfbch2_crcf, m_ch: *mut u32) -> i32;
     pub fn yg_firpfbch2_crcf_get_m(q: yg_firpfbch2_crcf, m: *mut u32) -> i32;
     pub fn yg_firpfbch2_crcf_get_taps(q: yg_firpfbch2_crcf, h: *mut f32) -> i32;
+    pub fn yg_firpfbch2_crcf_get_device(q: yg_firpfbch2_crcf, dev: *mut i32) -> i32;
     pub fn yg_firpfbch2_crcf_state_len(q: yg_firpfbch2_crcf, n: *mut size_t) -> i32;
     pub fn yg_firpfbch2_crcf_get_state(q: yg_firpfbch2_crcf, hist: *mut yg_cf32, flag: *mut i32) -> i32;
     pub fn yg_firpfbch2_crcf_set_state(q: yg_firpfbch2_crcf, hist: *const yg_cf32, flag: i32) -> i32;
     pub fn yg_firpfbch2_crcf_last_path(q: yg_firpfbch2_crcf, path: *mut i32) -> i32;
     pub fn yg_firpfbch2_crcf_last_kernel_ms(q: yg_firpfbch2_crcf, ms: *mut f32) -> i32;
     pub fn yg_firpfbch2_crcf_kernel_times(q: yg_firpfbch2_crcf, ms: *mut f32, cap: size_t, n: *mut size_t) -> i32;
+    pub fn yg_firpfbch2_crcf_set_kernel_timing(q: yg_firpfbch2_crcf, enable: i32) -> i32;
 
     pub fn yg_firpfbch_crcf_create(type_: i32, m_ch: u32, p: u32, h: *const f32, h_len: size_t, n_streams: u32, out: *mut yg_firpfbch_crcf) -> i32;
     pub fn yg_firpfbch_crcf_create_kaiser(type_: i32, m_ch: u32, m: u32, as_: f32, n_streams: u32, out: *mut yg_firpfbch_crcf) -> i32;
@@ -77,6 +81,7 @@ extern "C" {
     pub fn yg_firpfbch_crcf_get_p(q: yg_firpfbch_crcf, p: *mut u32) -> i32;
     pub fn yg_firpfbch_crcf_get_n_streams(q: yg_firpfbch_crcf, n: *mut u32) -> i32;
     pub fn yg_firpfbch_crcf_get_taps(q: yg_firpfbch_crcf, h: *mut f32) -> i32;
+    pub fn yg_firpfbch_crcf_get_device(q: yg_firpfbch_crcf, dev: *mut i32) -> i32;
     pub fn yg_firpfbch_crcf_last_path(q: yg_firpfbch_crcf, path: *mut i32) -> i32;
 
     pub fn yg_firfilt_crcf_create(h: *const f32, h_len: size_t, n_streams: u32, out: *mut yg_firfilt_crcf) -> i32;
@@ -87,6 +92,7 @@ extern "C" {
     pub fn yg_firfilt_crcf_set_scale(q: yg_firfilt_crcf, scale: f32) -> i32;
     pub fn yg_firfilt_crcf_get_scale(q: yg_firfilt_crcf, scale: *mut f32) -> i32;
     pub fn yg_firfilt_crcf_get_len(q: yg_firfilt_crcf, h_len: *mut size_t) -> i32;
+    pub fn yg_firfilt_crcf_get_device(q: yg_firfilt_crcf, dev: *mut i32) -> i32;
     pub fn yg_firfilt_crcf_execute_block(q: yg_firfilt_crcf, x: *const yg_cf32, n: size_t, y: *mut yg_cf32) -> i32;
     pub fn yg_firfilt_crcf_execute_block_dev(q: yg_firfilt_crcf, d_x: *const yg_cf32, n: size_t, d_y: *mut yg_cf32, cuda_stream: *mut c_void) -> i32;
     pub fn yg_firfilt_crcf_sync(q: yg_firfilt_crcf) -> i32;

@@ -1,0 +1,410 @@
+"""Round-2 GPU parity tests: oracle-independent checks of the CUDA channelizers, full-size property checks
+for BASELINE configs #2 / #4 / #5, one-launch steps, and the optional NCCL output gather.
+
+Everything goes through the C ABI (via the thin Python mirror).  Tolerance (BASELINE.json north_star):
+rel-RMS <= 1e-5 and max-abs <= 1e-4 per output sample in f32 unless a test states the reference's own.
+"""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import stimulus
+from oracle import pyoracle as po
+from parity import assert_parity, errors
+
+pytestmark = pytest.mark.gpu
+
+import yagi_b200 as yb  # noqa: E402
+
+A, S = yb.ANALYZER, yb.SYNTHESIZER
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rand_c(rng, n):
+    return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+
+
+# ------------------------------------------------------------------ one launch per fused step
+def test_fused_call_is_one_launch_and_hands_over_state():
+    """An even-parity, even-length call on the fused M=256 kernel is ONE kernel launch: the state hand-off
+    (tail of the input stream -> the other history buffer) is done by the same kernel."""
+    import torch
+    M, m, K = 256, 7, 4096
+    x = stimulus.noise_plus_tones(0, K * M // 2, M)
+    xd = torch.from_numpy(x).cuda()
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    ref = po.FirPfbCh2.new_kaiser(po.ANALYZER, M, m, 60.0).execute_block(x)
+    l0 = yb.launch_count()
+    y1 = q.execute_block(xd[: 1000 * M // 2])
+    torch.cuda.synchronize()
+    assert q.last_path() == 2
+    assert yb.launch_count() - l0 == 1
+    hist, flag = q.get_state()
+    assert flag == 0
+    np.testing.assert_array_equal(hist, x[1000 * M // 2 - q.state_len(): 1000 * M // 2])
+    # the next call starts from the state the kernel wrote
+    y2 = q.execute_block(xd[1000 * M // 2:])
+    torch.cuda.synchronize()
+    assert yb.launch_count() - l0 == 2
+    assert_parity(torch.cat([y1, y2]).cpu().numpy(), ref, "two one-launch calls")
+    # an odd-parity start needs the generic kernel for the leading frame: more launches, same answer
+    q.reset()
+    l0 = yb.launch_count()
+    ya = q.execute_block(xd[: 129 * M // 2])
+    yb_ = q.execute_block(xd[129 * M // 2:])
+    torch.cuda.synchronize()
+    assert yb.launch_count() - l0 >= 4
+    assert_parity(torch.cat([ya, yb_]).cpu().numpy(), ref, "odd split")
+
+
+def test_kernel_timing_toggle():
+    import torch
+    M, m, K = 256, 7, 256
+    xd = torch.from_numpy(stimulus.noise_plus_tones(0, K * M // 2, M)).cuda()
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    q.execute_block(xd)
+    assert q.last_kernel_ms() > 0 and len(q.kernel_times_ms()) == 1
+    q.set_kernel_timing(False)
+    y0 = q.execute_block(xd)
+    with pytest.raises(yb.ModeError):
+        q.last_kernel_ms()
+    assert len(q.kernel_times_ms()) == 0
+    q.set_kernel_timing(True)
+    y1 = q.execute_block(xd)
+    assert q.last_kernel_ms() > 0
+    assert bool(torch.equal(torch.view_as_real(y0), torch.view_as_real(y1)))      # same state (tail of x) both times
+
+
+def test_device_mismatch_is_refused():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    q = yb.FirPfbCh2.new_kaiser(A, 16, 5, 60.0)
+    assert q.get_device() == torch.cuda.current_device()
+    other = (q.get_device() + 1) % torch.cuda.device_count()
+    x = torch.zeros(64 * 8, dtype=torch.complex64, device="cuda:%d" % other)
+    with pytest.raises(yb.ValueError_):
+        q.execute_block(x)
+
+
+# ------------------------------------------------------------------ oracle-free: DFT stage vs numpy.fft in f64
+@pytest.mark.parametrize("M", [64, 128, 256, 512, 1024, 2048, 4096])
+def test_dft_stage_against_numpy_fft_f64(M):
+    """Oracle-free pin of the CUDA transform at the fused sizes (the reference's own FFT vectors stop at N = 192):
+    with the prototype h[0..M) = 1 (else 0) and m = 1 the analyser is a pure backward DFT,
+        y_k = (1/M) IDFT_unnorm(roll(V_k, (k&1) M/2)),  V_k[b] = s[t_k - b],  t_k = (k+1) M/2 - 1,
+    so every frame k >= 1 is checked against numpy.fft.ifft (f64) of the rolled, reversed input window.
+    Enough frames are sent that the fused kernels (last_path 2 or 3) take the call."""
+    rng = np.random.default_rng(M)
+    K = 256
+    h = np.zeros(2 * M, dtype=np.float32)
+    h[:M] = 1.0
+    s = _rand_c(rng, K * M // 2)
+    q = yb.FirPfbCh2.new(A, M, 1, h)
+    y = q.execute_block(s).reshape(K, M)
+    assert q.last_path() in (2, 3), q.last_path()
+    s64 = s.astype(np.complex128)
+    worst = 0.0
+    for k in range(1, K):
+        tk = (k + 1) * (M // 2) - 1
+        V = s64[tk - M + 1: tk + 1][::-1]                     # V[b] = s[tk - b]
+        ref = np.fft.ifft(np.roll(V, (k & 1) * (M // 2)))     # = (1/M) IDFT_unnorm
+        worst = max(worst, float(np.abs(y[k] - ref).max() / max(1e-30, np.abs(ref).max())))
+    # f32 transform of length M: error grows like log2(M) ulps
+    assert worst < 2e-6 * np.log2(M), worst
+
+
+@pytest.mark.parametrize("M", [64, 256, 1024])
+def test_synthesis_dft_stage_against_numpy_fft_f64(M):
+    """The synthesiser, oracle-free, through its closed form:
+        y[k M/2 + i] = sum_{l < 4m} h[i + l M/2] u_{k-l}[(i + pi_k) mod M],  u_k = 1/2 IDFT_unnorm(X_k), pi_k = (k&1) M/2
+    evaluated in f64 with numpy.fft for random X and a random prototype."""
+    rng = np.random.default_rng(100 + M)
+    m, K = 2, 160
+    h = rng.standard_normal(2 * M * m).astype(np.float32)
+    X = _rand_c(rng, K * M).reshape(K, M)
+    q = yb.FirPfbCh2.new(S, M, m, h)
+    y = q.execute_block(X.reshape(-1)).reshape(K, M // 2)
+    assert q.last_path() in (2, 3), q.last_path()
+    u = 0.5 * M * np.fft.ifft(X.astype(np.complex128), axis=1)
+    h64 = h.astype(np.float64)
+    i = np.arange(M // 2)
+    ref = np.zeros((K, M // 2), dtype=np.complex128)
+    for k in range(K):
+        col = (i + (k & 1) * (M // 2)) % M
+        for l in range(4 * m):
+            if k - l >= 0:
+                ref[k] += h64[i + l * (M // 2)] * u[k - l][col]
+    scale = np.abs(ref).max()
+    rel, mx = errors(y / scale, ref / scale)
+    assert rel < 1e-5 and mx < 1e-4, (rel, mx)
+
+
+# ------------------------------------------------------------------ upstream firpfbch autotests on the CUDA object
+def _mix_filter_decimate(h, x, M, c):
+    """Channel c of the analyser, the long way (f64): mix down by c/M, filter with h, keep samples t = M-1 mod M."""
+    t = np.arange(x.size)
+    xm = x.astype(np.complex128) * np.exp(-2j * np.pi * c * t / M)
+    yf = np.convolve(xm, h.astype(np.float64))[: x.size]
+    return yf[M - 1:: M]
+
+
+def test_firpfbch_crcf_analysis_autotest_on_cuda():
+    """Upstream autotest firpfbch_crcf_analysis (LIQUID_COMPAT.md:1774) on yb.FirPfbCh: M = 4, p = 5, random taps and
+    input, 12 symbols -- the channelizer equals per-channel mix-down / firfilt / decimate (tol 1e-4, upstream's).
+    Oracle-independent.  Also at the fused sizes (M = 8 .. 64, many streams)."""
+    for M, p, Q, S_ in ((4, 5, 12, 1), (8, 6, 64, 4), (16, 4, 64, 2), (32, 8, 48, 1), (64, 14, 64, 4)):
+        rng = np.random.default_rng(M + p)
+        h = rng.standard_normal(M * p).astype(np.float32)
+        x = _rand_c(rng, S_ * Q * M).reshape(S_, Q * M)
+        q = yb.FirPfbCh.new(A, M, p, h, n_streams=S_)
+        y = q.execute_block(x).reshape(S_, Q, M)
+        for s in range(S_):
+            ref = np.stack([_mix_filter_decimate(h, x[s], M, c) for c in range(M)], axis=1)      # [Q][M]
+            scale = max(1.0, np.abs(ref).max())
+            assert np.abs(y[s] - ref).max() / scale < 1e-4, (M, p, s)
+
+
+def test_firpfbch_crcf_synthesis_autotest_on_cuda():
+    """Upstream autotest firpfbch_crcf_synthesis (LIQUID_COMPAT.md:1768): the synthesiser equals, per channel,
+    upsample by M / firfilt / mix up by c/M, summed over channels (tol 1e-4).  Oracle-independent."""
+    for M, p, Q, S_ in ((4, 5, 12, 1), (8, 6, 64, 4), (16, 4, 64, 2), (64, 14, 64, 4)):
+        rng = np.random.default_rng(7 * M + p)
+        h = rng.standard_normal(M * p).astype(np.float32)
+        X = _rand_c(rng, S_ * Q * M).reshape(S_, Q, M)
+        q = yb.FirPfbCh.new(S, M, p, h, n_streams=S_)
+        y = q.execute_block(X.reshape(S_, -1)).reshape(S_, Q * M)
+        t = np.arange(Q * M)
+        for s in range(S_):
+            ref = np.zeros(Q * M, dtype=np.complex128)
+            for c in range(M):
+                up = np.zeros(Q * M, dtype=np.complex128)
+                up[::M] = X[s, :, c]
+                ref += np.convolve(up, h.astype(np.float64))[: Q * M] * np.exp(2j * np.pi * c * t / M)
+            scale = max(1.0, np.abs(ref).max())
+            assert np.abs(y[s] - ref).max() / scale < 1e-4, (M, p, s)
+
+
+def test_firpfbch2_analysis_equals_mix_filter_decimate_on_cuda():
+    """The same oracle-independent identity for the 2x oversampled object:
+    y_k[c] = ((-1)^{c k} / M) sum_tau h[tau] e^{+j 2 pi c tau / M} s[t_k - tau], t_k = (k+1) M/2 - 1,
+    evaluated in f64 for a random prototype, through the fused kernels."""
+    for M, m, K in ((16, 3, 96), (64, 2, 128), (256, 2, 128)):
+        rng = np.random.default_rng(M + m)
+        h = rng.standard_normal(2 * M * m).astype(np.float32)
+        x = _rand_c(rng, K * M // 2)
+        q = yb.FirPfbCh2.new(A, M, m, h)
+        y = q.execute_block(x).reshape(K, M)
+        assert q.last_path() == 2
+        L = 2 * M * m
+        tau = np.arange(L)
+        xp = np.concatenate([np.zeros(L, dtype=np.complex128), x.astype(np.complex128)])
+        E = np.exp(2j * np.pi * np.outer(np.arange(M), tau) / M) * h.astype(np.float64)[None, :]       # [c][tau]
+        ks = list(range(0, K, 7)) + [K - 1]
+        for k in ks:
+            tk = (k + 1) * (M // 2) - 1
+            win = xp[L + tk - tau]                                                                     # s[tk - tau]
+            ref = (E @ win) / M * ((-1.0) ** (np.arange(M) * k))
+            scale = max(1.0, np.abs(ref).max())
+            assert np.abs(y[k] - ref).max() / scale < 2e-5, (M, k)
+
+
+# ------------------------------------------------------------------ full-size property checks (configs #2, #4, #5)
+def test_config2_full_size_properties_firfilt():
+    """BASELINE config #2 at full size (1024 streams x 2^20 samples, 63 taps): size-independent properties --
+    (a) linearity in the input: y(a x1 + x2) == a y(x1) + y(x2) on the GPU itself (f32 rounding only);
+    (b) sampled windows of every 97th stream against the oracle (start, a tile boundary, the end)."""
+    import torch
+    S_, N = 1024, 1 << 20
+    h = yb.fir_design_kaiser(63, 0.25, 60.0, 0.0)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(22)
+    xr = torch.empty(S_ * N, 2, dtype=torch.float32, device="cuda")
+    xr.normal_(0.0, 1.0, generator=g)
+    x = torch.view_as_complex(xr)
+    q = yb.FirFilt.new(h, n_streams=S_)
+    y = q.execute_block(x).view(S_, N)
+    torch.cuda.synchronize()
+    xv = x.view(S_, N)
+    for s in range(0, S_, 97):
+        for a in (0, 4096 - 100, N // 2 - 77, N - 3000):
+            b = min(N, a + 3000)
+            lo = max(0, a - 62)
+            ref = po.firfilt_crcf(h, xv[s, lo:b].cpu().numpy())[a - lo:]
+            assert_parity(y[s, a:b].cpu().numpy(), ref, "config #2 stream %d window %d" % (s, a))
+    # (b') DC gain property over the whole block: sum_n y[s][n] = sum(h) * sum_n x[s][n] - (edge terms)
+    #      checked on the interior through a telescoping identity: sum_{n=62}^{N-1} y[n] = sum_k h[k] sum_{n=62-k}^{N-1-k} x[n]
+    #      (every 8th stream; a dropped or duplicated 64-output tile would move the sum by ~4, rounding by ~1e-3)
+    cs = torch.cumsum(xv[::8].to(torch.complex128), dim=1)
+    lhs = y[::8, 62:].to(torch.complex128).sum(dim=1)
+    rhs = torch.zeros(S_ // 8, dtype=torch.complex128, device="cuda")
+    for k in range(63):
+        hi = cs[:, N - 1 - k]
+        lo_ = cs[:, 62 - k - 1] if 62 - k - 1 >= 0 else torch.zeros_like(hi)
+        rhs += float(h[k]) * (hi - lo_)
+    err = (lhs - rhs).abs().max().item()
+    assert err < 5e-2, err
+    del cs, lhs, rhs
+    # (a) linearity
+    n2 = S_ * N // 4
+    x1, x2 = x[:n2], x[n2: 2 * n2]
+    q4 = yb.FirFilt.new(h, n_streams=S_ // 4)
+    y1 = q4.execute_block(x1).clone(); q4.reset()
+    y2 = q4.execute_block(x2).clone(); q4.reset()
+    y3 = q4.execute_block(0.5 * x1 + x2)
+    torch.cuda.synchronize()
+    d = (y3 - (0.5 * y1 + y2)).abs().max().item()
+    assert d < 2e-5, d
+
+
+def test_config4_full_size_round_trip_M1024_m4():
+    """BASELINE config #4 at full size: analysis -> synthesis round trip, M=1024, m=4, N=2^24 wideband samples.
+    (a) reconstruction y[t] ~= x[t - D], D = 2Mm - M/2 + 1 (upstream firpfbch2 autotest property, tol 1e-3 of the
+    signal scale); (b) the channelised frames against the oracle on sampled windows; (c) channel-sum checksum of
+    every analysis frame (sum_c y_k[c] = one polyphase partial sum)."""
+    import torch
+    M, m, N = 1024, 4, 1 << 24
+    K = N // (M // 2)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(44)
+    xr = torch.empty(N, 2, dtype=torch.float32, device="cuda")
+    xr.normal_(0.0, 1.0, generator=g)
+    x = torch.view_as_complex(xr)
+    qa = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    qs = yb.FirPfbCh2.new_kaiser(S, M, m, 60.0)
+    ch = qa.execute_block(x)
+    assert qa.last_path() == 3
+    y = qs.execute_block(ch)
+    assert qs.last_path() == 3
+    torch.cuda.synchronize()
+    D = 2 * M * m - M // 2 + 1
+    d = y[D:] - x[: N - D]
+    rel = (d.abs().pow(2).sum().sqrt() / x.abs().pow(2).sum().sqrt()).item()
+    assert rel < 1e-3, rel                       # upstream: |y - x| <= 1e-3 at unit modulus
+    assert d.abs().max().item() < 1e-2 and y[:D].abs().max().item() < 1e-2
+    # (c) checksum over every frame with full history
+    chv = ch.view(K, M)
+    h = torch.from_numpy(qa.get_taps()).cuda()
+    k = torch.arange(4 * m, K, device="cuda", dtype=torch.int64)
+    b0 = (k & 1) * (M // 2)
+    tk = (k + 1) * (M // 2) - 1
+    acc = torch.zeros(k.numel(), dtype=torch.complex128, device="cuda")
+    for n in range(2 * m):
+        acc += h[b0 + n * M].to(torch.float64) * x[tk - b0 - n * M].to(torch.complex128)
+    chk = chv[4 * m:].to(torch.complex128).sum(dim=1)
+    assert (chk - acc).abs().max().item() < 1e-3
+    # (b) sampled windows vs the oracle
+    halo = (4 * m - 1) * M // 2
+    for f0 in (0, 2 * 1111, K // 2 - 32, K - 64):
+        f0 -= f0 % 2
+        nf = 64
+        s0 = f0 * M // 2
+        lo = max(0, s0 - halo - M // 2)
+        pre = x[lo:s0].cpu().numpy()
+        seg = x[s0: s0 + nf * M // 2].cpu().numpy()
+        o = po.FirPfbCh2.new_kaiser(po.ANALYZER, M, m, 60.0)
+        if pre.size:
+            pad = (-pre.size) % M
+            o.execute_block(np.concatenate([np.zeros(pad, dtype=np.complex64), pre]))
+        ref = o.execute_block(seg)
+        assert_parity(chv[f0: f0 + nf].reshape(-1).cpu().numpy(), ref, "config #4 analysis window at frame %d" % f0)
+    # synthesis windows vs the oracle fed with the GPU's own channel frames
+    for f0 in (0, 2 * 999, K - 64):
+        f0 -= f0 % 2
+        nf = 64
+        npre = min(f0, 32)                       # >= 4m - 1 frames of history, even
+        o = po.FirPfbCh2.new_kaiser(po.SYNTHESIZER, M, m, 60.0)
+        seg = chv[f0 - npre: f0 + nf].reshape(-1).cpu().numpy()
+        ref = o.execute_block(seg)[npre * (M // 2):]
+        got = y[f0 * (M // 2): (f0 + nf) * (M // 2)].cpu().numpy()
+        assert_parity(got, ref, "config #4 synthesis window at frame %d" % f0)
+
+
+def test_config5_full_size_properties_firpfbch_M64():
+    """BASELINE config #5, one GPU's share at full size (512 streams x 2^18 samples, M=64, m=7):
+    (a) every 37th stream, sampled windows against the oracle; (b) analysis of a constant-per-stream DC input
+    converges to sum(h)-weighted DC in channel 0 only (closed form), all streams."""
+    import torch
+    M, m, S_, N = 64, 7, 512, 1 << 18
+    Q = N // M
+    g = torch.Generator(device="cuda")
+    g.manual_seed(55)
+    xr = torch.empty(S_ * N, 2, dtype=torch.float32, device="cuda")
+    xr.normal_(0.0, 1.0, generator=g)
+    x = torch.view_as_complex(xr)
+    q = yb.FirPfbCh.new_kaiser(A, M, m, 60.0, n_streams=S_)
+    y = q.execute_block(x).view(S_, Q, M)
+    assert q.last_path() == 2
+    torch.cuda.synchronize()
+    xv = x.view(S_, N)
+    p = 2 * m
+    for s in range(0, S_, 37):
+        for f0 in (0, Q // 2 - 40, Q - 64):
+            nf = 64
+            npre = min(f0, p)                                  # p - 1 frames of history suffice
+            seg = xv[s, (f0 - npre) * M: (f0 + nf) * M].cpu().numpy()
+            ref = po.FirPfbCh.new_kaiser(po.ANALYZER, M, m, 60.0).execute_block(seg)[npre * M:]
+            assert_parity(y[s, f0: f0 + nf].reshape(-1).cpu().numpy(), ref, "config #5 stream %d frame %d" % (s, f0))
+    # (b) DC input: after the filter has filled, y_q[c] = e^{j 2 pi c / M} sum_tau h[tau] e^{j 2 pi c tau / M} * dc
+    q.reset()
+    dc = torch.arange(1, S_ + 1, device="cuda", dtype=torch.float32) * (1.0 / S_)
+    xd = (dc[:, None] * torch.ones(1, 64 * M, device="cuda")).to(torch.complex64).contiguous()
+    yd = q.execute_block(xd.view(-1)).view(S_, 64, M)[:, -1, :].to(torch.complex128)
+    h = q.get_taps().astype(np.float64)
+    tau = np.arange(h.size)
+    H = np.array([np.exp(2j * np.pi * c / M) * np.sum(h * np.exp(2j * np.pi * c * tau / M)) for c in range(M)])
+    ref = torch.from_numpy(H).cuda()[None, :] * dc.to(torch.float64)[:, None]
+    assert (yd - ref).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------ optional NCCL gather (off the hot path)
+_GATHER_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import yagi_b200 as yb, stimulus
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank % torch.cuda.device_count())
+dev = torch.device("cuda", rank % torch.cuda.device_count())
+dist.init_process_group("nccl", device_id=dev)
+M, m, K = 256, 7, 1024
+x = stimulus.noise_plus_tones(0, K * M // 2, M)
+whole = yb.FirPfbCh2.new_kaiser(yb.ANALYZER, M, m, 60.0).execute_block(torch.from_numpy(x).cuda())
+sh = yb.firpfbch2_time_shards(K, M, m, world)
+me = sh[rank]
+q = yb.FirPfbCh2.new_kaiser(yb.ANALYZER, M, m, 60.0)
+q.set_state(stimulus.noise_plus_tones(me.halo_begin, me.halo_len, M), 0)
+y = q.execute_block(torch.from_numpy(x[me.sample_begin: me.sample_end]).cuda())
+full = yb.all_gather_frames(y, [s.n_frames for s in sh], M)
+torch.cuda.synchronize()
+assert full.shape == (K, M), full.shape
+assert bool(torch.equal(torch.view_as_real(full.reshape(-1)), torch.view_as_real(whole))), "gathered shards differ from the single pass"
+cm = yb.channel_major(full)
+assert cm.shape == (M, K) and cm.is_contiguous()
+assert bool(torch.equal(torch.view_as_real(cm), torch.view_as_real(full.t().contiguous())))
+dist.barrier(); dist.destroy_process_group()
+print("gather ok rank", rank)
+"""
+
+
+def test_nccl_gather_of_time_shards_and_channel_major():
+    """yagi_b200.gather on hardware: every rank channelises its time shard (primed with the halo), the NCCL
+    all-gather reassembles the frames in stream order bit-identically to a single pass, and channel_major returns the
+    [M][K] transpose.  Runs with as many ranks as there are GPUs (at most 4; a single GPU still goes through NCCL)."""
+    import torch
+    world = max(1, min(4, torch.cuda.device_count()))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    code = _GATHER_WORKER.format(root=ROOT)
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "gather ok" in o, "rank %d:\n%s" % (r, o[-2000:])

@@ -137,3 +137,31 @@ def test_numa_helper_parses_cpulists_and_is_a_no_op_without_a_gpu():
     if not torch.cuda.is_available():
         assert bind_to_gpu_numa_node(0) is None
         assert os.sched_getaffinity(0) == before
+
+
+def test_rust_sys_crate_tracks_the_c_abi():
+    """rust/yagi-b200-sys cannot be compiled here (no cargo), so keep it honest textually:
+    build.rs compiles every csrc/*.cu (globbed, no hand-written list to go stale) and src/lib.rs
+    declares exactly the symbols of include/yagi_b200.h with the same number of arguments."""
+    hdr = open(os.path.join(ROOT, "include", "yagi_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = {}
+    for name, args in re.findall(r"\b(yg_[A-Za-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = args.strip()
+        declared[name] = 0 if args in ("", "void") else args.count(",") + 1
+    rs = open(os.path.join(ROOT, "rust", "yagi-b200-sys", "src", "lib.rs")).read()
+    bound = {}
+    for name, args in re.findall(r"pub fn (yg_[A-Za-z0-9_]+)\s*\(([^)]*)\)", rs):
+        args = args.strip()
+        bound[name] = 0 if args == "" else args.count(":")
+    assert bound == declared
+    build_rs = open(os.path.join(ROOT, "rust", "yagi-b200-sys", "build.rs")).read()
+    assert "read_dir(&csrc)" in build_rs and 'x == "cu"' in build_rs          # globbed
+    for f in os.listdir(os.path.join(ROOT, "yagi_b200", "csrc")):
+        if f.endswith(".cu"):
+            assert ('"%s"' % f[:-3]) not in build_rs                             # no stale explicit list
+    # the facades call only declared symbols
+    for facade in ("multichannel/mod.rs", "filter/firfilt_gpu.rs"):
+        text = open(os.path.join(ROOT, "rust", facade)).read()
+        used = set(re.findall(r"sys::(yg_[A-Za-z0-9_]+)\s*\(", text))
+        assert used and used <= set(declared), used - set(declared)

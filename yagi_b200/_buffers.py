@@ -56,6 +56,17 @@ def dev_out(out, n: int, like):
     return out
 
 
+def check_device(x, dev: int, what: str = "input") -> None:
+    """A handle is bound to the CUDA device it was created on; tensors from another device would be
+    dereferenced there (or fail with an opaque CUDA error), so refuse them up front."""
+    idx = x.device.index
+    if idx is None:
+        import torch
+        idx = torch.cuda.current_device()
+    if idx != dev:
+        raise ValueError_("%s lives on cuda:%d but this object is bound to cuda:%d" % (what, idx, dev))
+
+
 def cur_stream(x) -> C.c_void_p:
     import torch
     return C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)

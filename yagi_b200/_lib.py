@@ -14,20 +14,20 @@ from .error import from_status
 _lib = None
 
 SYMBOLS = """
-yg_version yg_last_error yg_device_count yg_host_alloc yg_host_free yg_fir_design_kaiser
+yg_version yg_last_error yg_device_count yg_launch_count yg_channel_major_dev yg_host_alloc yg_host_free yg_fir_design_kaiser
 yg_firpfbch2_crcf_create yg_firpfbch2_crcf_create_kaiser yg_firpfbch2_crcf_clone yg_firpfbch2_crcf_destroy
 yg_firpfbch2_crcf_reset yg_firpfbch2_crcf_execute yg_firpfbch2_crcf_execute_block
 yg_firpfbch2_crcf_execute_block_dev yg_firpfbch2_crcf_sync yg_firpfbch2_crcf_get_type yg_firpfbch2_crcf_get_M
 yg_firpfbch2_crcf_get_m yg_firpfbch2_crcf_get_taps yg_firpfbch2_crcf_state_len yg_firpfbch2_crcf_get_state
 yg_firpfbch2_crcf_set_state yg_firpfbch2_crcf_last_path yg_firpfbch2_crcf_last_kernel_ms
-yg_firpfbch2_crcf_kernel_times
+yg_firpfbch2_crcf_kernel_times yg_firpfbch2_crcf_set_kernel_timing yg_firpfbch2_crcf_get_device
 yg_firpfbch_crcf_create yg_firpfbch_crcf_create_kaiser yg_firpfbch_crcf_clone yg_firpfbch_crcf_destroy
 yg_firpfbch_crcf_reset yg_firpfbch_crcf_execute yg_firpfbch_crcf_execute_block yg_firpfbch_crcf_execute_block_dev
 yg_firpfbch_crcf_sync yg_firpfbch_crcf_get_type yg_firpfbch_crcf_get_M yg_firpfbch_crcf_get_p
-yg_firpfbch_crcf_get_n_streams yg_firpfbch_crcf_get_taps yg_firpfbch_crcf_last_path
+yg_firpfbch_crcf_get_n_streams yg_firpfbch_crcf_get_taps yg_firpfbch_crcf_last_path yg_firpfbch_crcf_get_device
 yg_firfilt_crcf_create yg_firfilt_crcf_create_kaiser yg_firfilt_crcf_clone yg_firfilt_crcf_destroy
 yg_firfilt_crcf_reset yg_firfilt_crcf_set_scale yg_firfilt_crcf_get_scale yg_firfilt_crcf_get_len
-yg_firfilt_crcf_execute_block yg_firfilt_crcf_execute_block_dev yg_firfilt_crcf_sync
+yg_firfilt_crcf_execute_block yg_firfilt_crcf_execute_block_dev yg_firfilt_crcf_sync yg_firfilt_crcf_get_device
 """.split()
 
 
@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
     L.yg_last_error.argtypes = []
     L.yg_version.argtypes = []
     L.yg_device_count.argtypes = [vp]
+    L.yg_launch_count.argtypes = [vp]
+    L.yg_channel_major_dev.argtypes = [vp, sz, u32, vp, vp]
     L.yg_host_alloc.argtypes = [vp, sz]
     L.yg_host_free.argtypes = [vp]
     L.yg_fir_design_kaiser.argtypes = [u32, f32, f32, f32, vp]
@@ -68,6 +70,9 @@ def lib() -> C.CDLL:
     L.yg_firpfbch2_crcf_get_state.argtypes = [vp, vp, vp]
     L.yg_firpfbch2_crcf_set_state.argtypes = [vp, vp, i32]
     L.yg_firpfbch2_crcf_kernel_times.argtypes = [vp, vp, sz, vp]
+    L.yg_firpfbch2_crcf_set_kernel_timing.argtypes = [vp, i32]
+    for n in ("yg_firpfbch2_crcf_get_device", "yg_firpfbch_crcf_get_device", "yg_firfilt_crcf_get_device"):
+        getattr(L, n).argtypes = [vp, vp]
     # firpfbch
     L.yg_firpfbch_crcf_create.argtypes = [i32, u32, u32, vp, sz, u32, vp]
     L.yg_firpfbch_crcf_create_kaiser.argtypes = [i32, u32, u32, f32, u32, vp]
@@ -94,6 +99,13 @@ def lib() -> C.CDLL:
     L.yg_firfilt_crcf_sync.argtypes = [vp]
     _lib = L
     return L
+
+
+def launch_count() -> int:
+    """Kernels launched by libyagi_b200.so in this process so far."""
+    n = C.c_uint64()
+    check(lib().yg_launch_count(C.byref(n)))
+    return n.value
 
 
 def check(status: int) -> None:

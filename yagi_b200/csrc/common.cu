@@ -1,6 +1,7 @@
 // common.cu -- error plumbing, host-side Kaiser design, pinned-memory helpers.
 #include "common.cuh"
 
+#include <atomic>
 #include <cmath>
 
 namespace yg {
@@ -35,6 +36,36 @@ int32_t require_device(int* dev_out)
     YG_CUDA(cudaGetDevice(&dev));
     *dev_out = dev;
     return YG_OK;
+}
+
+int sm_count(int dev)
+{
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = 1;
+    }
+    return n;
+}
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+cudaError_t memcpy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind)
+{
+    if (bytes == 0) return cudaSuccess;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, cudaStreamPerThread);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(cudaStreamPerThread);
+}
+
+cudaError_t memset_sync(void* dst, int value, size_t bytes)
+{
+    if (bytes == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(dst, value, bytes, cudaStreamPerThread);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(cudaStreamPerThread);
 }
 
 int32_t HostPipe::init()
@@ -153,6 +184,13 @@ int32_t yg_device_count(int32_t* n)
     cudaError_t e = cudaGetDeviceCount(&c);
     if (e != cudaSuccess) { cudaGetLastError(); c = 0; }
     *n = c;
+    return YG_OK;
+}
+
+int32_t yg_launch_count(uint64_t* n)
+{
+    if (!n) return yg::fail(YG_EVALUE, "null pointer");
+    *n = (uint64_t)yg::launch_count();
     return YG_OK;
 }
 

@@ -45,7 +45,29 @@ struct DeviceGuard {
     int cur = -1;
 };
 
+#define YG_DEVICE_GUARD(dev)                                                                  \
+    ::yg::DeviceGuard _yg_guard(dev);                                                         \
+    if (!_yg_guard.ok) return ::yg::fail(YG_EINTERNAL, "cannot switch to CUDA device %d", (int)(dev))
+
 int32_t require_device(int* dev_out);
+int sm_count(int dev);                  // multiprocessor count (>= 1)
+
+// Every kernel launch of the library goes through YG_LAUNCH_CHECK() (or count_launch() after a
+// cooperative launch), so callers can ask how many kernels a region launched (yg_launch_count).
+void count_launch();
+unsigned long long launch_count();
+#define YG_LAUNCH_CHECK()                  \
+    do {                                   \
+        ::yg::count_launch();              \
+        YG_CUDA(cudaGetLastError());       \
+    } while (0)
+
+// Host<->device copies and fills that have COMPLETED on the device when they return, whatever
+// stream the next kernel runs on.  (The plain cudaMemset / device-to-device cudaMemcpy are
+// asynchronous on the legacy default stream, which the handles' non-blocking streams do not
+// synchronise with.)
+cudaError_t memcpy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
+cudaError_t memset_sync(void* dst, int value, size_t bytes);
 
 // ---------------------------------------------------------------- design (host)
 int32_t fir_design_kaiser(uint32_t n, float fc, float as, float mu, float* h);
@@ -112,6 +134,12 @@ int32_t run_host_pipe(HostPipe& hp, cudaStream_t s_comp, const yg_cf32* x, yg_cf
 {
     YG_TRY(hp.init());
     if (n_frames == 0) return YG_OK;
+    // On a mid-loop failure the copies already queued still target the caller's x and y: drain the three
+    // streams before reporting it, so the caller may free its buffers as soon as the call returns.
+    struct Drain {
+        HostPipe& hp; cudaStream_t s; bool armed = true;
+        ~Drain() { if (armed) { cudaStreamSynchronize(hp.s_in); cudaStreamSynchronize(s); cudaStreamSynchronize(hp.s_out); } }
+    } drain{hp, s_comp};
     if (frames_per_chunk == 0) frames_per_chunk = 1;
     if (frames_per_chunk > n_frames) frames_per_chunk = n_frames;
     const int nbuf = (n_frames > frames_per_chunk) ? 2 : 1;
@@ -139,6 +167,7 @@ int32_t run_host_pipe(HostPipe& hp, cudaStream_t s_comp, const yg_cf32* x, yg_cf
     }
     YG_CUDA(cudaStreamSynchronize(hp.s_out));
     YG_CUDA(cudaStreamSynchronize(s_comp));
+    drain.armed = false;
     return YG_OK;
 }
 

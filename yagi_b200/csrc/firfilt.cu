@@ -18,6 +18,7 @@ struct yg_firfilt_crcf_s {
     uint32_t n_streams = 1;
     float scale = 1.0f;
     int dev = 0;
+    int n_sm = 1;                  // multiprocessor count of `dev` (grid sizing)
     cudaStream_t stream = nullptr;
     StreamOrder order;
     std::vector<float> h;
@@ -114,7 +115,7 @@ int32_t execute_dev_impl(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf3
                                    reinterpret_cast<const float2*>(d_x), reinterpret_cast<float2*>(d_y), (long long)n, S, st));
     } else {
         const long long tiles = ((long long)n + kOutPerThread - 1) / kOutPerThread;
-        const int grid = (int)std::min<long long>((tiles * S + 127) / 128, 148 * 32);
+        const int grid = (int)std::min<long long>((tiles * S + 127) / 128, q->n_sm * 32);
         const size_t smem = (q->h_len + 2 * (kOutPerThread - 1)) * sizeof(float);
         if (smem > 48 * 1024) return fail(YG_ECONFIG, "filter too long for this kernel (%zu taps)", q->h_len);
         k_firfilt<<<grid, 128, smem, st>>>(q->d_h.p, (int)q->h_len, q->scale,
@@ -122,14 +123,14 @@ int32_t execute_dev_impl(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf3
                                            reinterpret_cast<const float2*>(d_x), reinterpret_cast<float2*>(d_y),
                                            (long long)n, S);
     }
-    YG_CUDA(cudaGetLastError());
+    YG_LAUNCH_CHECK();
     if (Hlen > 0) {
         const int nxt = q->cur ^ 1;
-        const int g2 = (int)std::min<long long>((Hlen * S + 255) / 256, 148 * 8);
+        const int g2 = (int)std::min<long long>((Hlen * S + 255) / 256, q->n_sm * 8);
         k_firfilt_update_hist<<<g2, 256, 0, st>>>(reinterpret_cast<float2*>(q->d_hist[nxt].p),
                                                   reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
                                                   reinterpret_cast<const float2*>(d_x), (long long)n, S);
-        YG_CUDA(cudaGetLastError());
+        YG_LAUNCH_CHECK();
         q->cur = nxt;
     }
     return YG_OK;
@@ -146,18 +147,19 @@ int32_t build(const float* h, size_t h_len, uint32_t n_streams, yg_firfilt_crcf*
     YG_TRY(require_device(&dev));
     auto* q = new yg_firfilt_crcf_s();
     q->h_len = h_len; q->n_streams = n_streams; q->dev = dev;
+    q->n_sm = sm_count(dev);
     q->h.assign(h, h + h_len);
     auto cleanup = [&](int32_t rc) { yg_firfilt_crcf_destroy(q); return rc; };
 #define TRYQ(expr) do { int32_t _rc = (expr); if (_rc != YG_OK) return cleanup(_rc); } while (0)
 #define CUDAQ(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return cleanup(fail(YG_EINTERNAL, "CUDA error %s (%s)", cudaGetErrorString(_e), #expr)); } while (0)
     CUDAQ(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
     TRYQ(q->d_h.reserve(h_len));
-    CUDAQ(cudaMemcpy(q->d_h.p, q->h.data(), h_len * sizeof(float), cudaMemcpyHostToDevice));
+    CUDAQ(yg::memcpy_sync(q->d_h.p, q->h.data(), h_len * sizeof(float), cudaMemcpyHostToDevice));
     q->state_len = h_len - 1;
     for (int b = 0; b < 2; b++) {
         const size_t n = std::max<size_t>(1, q->state_len * n_streams);
         TRYQ(q->d_hist[b].reserve(n));
-        CUDAQ(cudaMemset(q->d_hist[b].p, 0, n * sizeof(yg_cf32)));
+        CUDAQ(yg::memset_sync(q->d_hist[b].p, 0, n * sizeof(yg_cf32)));
     }
 #undef TRYQ
 #undef CUDAQ
@@ -187,14 +189,14 @@ int32_t yg_firfilt_crcf_create_kaiser(uint32_t n, float fc, float as, float mu, 
 int32_t yg_firfilt_crcf_clone(yg_firfilt_crcf q, yg_firfilt_crcf* out)
 {
     YG_TRY(check(q));
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
     YG_TRY(q->order.wait_host());
     yg_firfilt_crcf c = nullptr;
     YG_TRY(build(q->h.data(), q->h_len, q->n_streams, &c));
     c->scale = q->scale;
     if (q->state_len) {
-        cudaError_t e = cudaMemcpy(c->d_hist[c->cur].p, q->d_hist[q->cur].p,
+        cudaError_t e = yg::memcpy_sync(c->d_hist[c->cur].p, q->d_hist[q->cur].p,
                                    q->state_len * q->n_streams * sizeof(yg_cf32), cudaMemcpyDeviceToDevice);
         if (e != cudaSuccess) { yg_firfilt_crcf_destroy(c); return fail(YG_EINTERNAL, "CUDA error %s", cudaGetErrorString(e)); }
     }
@@ -205,7 +207,7 @@ int32_t yg_firfilt_crcf_clone(yg_firfilt_crcf q, yg_firfilt_crcf* out)
 int32_t yg_firfilt_crcf_destroy(yg_firfilt_crcf q)
 {
     if (!q) return YG_OK;
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     if (q->stream) cudaStreamSynchronize(q->stream);
     q->order.wait_host();
     q->order.destroy();
@@ -219,7 +221,7 @@ int32_t yg_firfilt_crcf_destroy(yg_firfilt_crcf q)
 int32_t yg_firfilt_crcf_reset(yg_firfilt_crcf q)
 {
     YG_TRY(check(q));
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     YG_TRY(q->order.wait_host());
     if (q->state_len)
         YG_CUDA(cudaMemsetAsync(q->d_hist[q->cur].p, 0, q->state_len * q->n_streams * sizeof(yg_cf32), q->stream));
@@ -230,13 +232,14 @@ int32_t yg_firfilt_crcf_reset(yg_firfilt_crcf q)
 
 int32_t yg_firfilt_crcf_set_scale(yg_firfilt_crcf q, float scale) { YG_TRY(check(q)); q->scale = scale; return YG_OK; }
 int32_t yg_firfilt_crcf_get_scale(yg_firfilt_crcf q, float* scale) { YG_TRY(check(q)); *scale = q->scale; return YG_OK; }
+int32_t yg_firfilt_crcf_get_device(yg_firfilt_crcf q, int32_t* dev) { YG_TRY(check(q)); *dev = q->dev; return YG_OK; }
 int32_t yg_firfilt_crcf_get_len(yg_firfilt_crcf q, size_t* h_len) { YG_TRY(check(q)); *h_len = q->h_len; return YG_OK; }
 
 int32_t yg_firfilt_crcf_execute_block_dev(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf32* d_y, void* cuda_stream)
 {
     YG_TRY(check(q));
     if (n && (!d_x || !d_y)) return fail(YG_EVALUE, "null buffer");
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     return execute_dev(q, d_x, n, d_y, (cudaStream_t)cuda_stream);
 }
 
@@ -245,7 +248,7 @@ int32_t yg_firfilt_crcf_execute_block(yg_firfilt_crcf q, const yg_cf32* x, size_
     YG_TRY(check(q));
     if (n && (!x || !y)) return fail(YG_EVALUE, "null buffer");
     if (n == 0) return YG_OK;
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     const size_t tot = n * (size_t)q->n_streams;
     YG_TRY(q->d_stage_x.reserve(tot));
     YG_TRY(q->d_stage_y.reserve(tot));
@@ -260,7 +263,7 @@ int32_t yg_firfilt_crcf_execute_block(yg_firfilt_crcf q, const yg_cf32* x, size_
 int32_t yg_firfilt_crcf_sync(yg_firfilt_crcf q)
 {
     YG_TRY(check(q));
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
     YG_TRY(q->order.wait_host());
     return YG_OK;

@@ -135,7 +135,7 @@ int32_t launch_h(const float* h, size_t h_len, float scale, const float2* hist, 
         const long long ns = std::min<long long>(65535, n_streams - s0);
         k_firfilt_fast<kH><<<dim3((unsigned)tiles, (unsigned)ns), kThreads, 0, st>>>(taps, scale, hist + s0 * Hlen, (int)Hlen,
                                                                                     x + s0 * n, y + s0 * n, n);
-        YG_CUDA(cudaGetLastError());
+        YG_LAUNCH_CHECK();
     }
     return YG_OK;
 }

@@ -15,6 +15,7 @@ struct yg_firpfbch_crcf_s {
     uint32_t M = 0, p = 0, n_streams = 1;
     size_t L = 0;                  // M*p
     int dev = 0;
+    int n_sm = 1;                  // multiprocessor count of `dev` (grid sizing)
     cudaStream_t stream = nullptr;
     StreamOrder order;
     std::vector<float> h;
@@ -189,10 +190,10 @@ int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames
             const long long rest = S - s_fast;
             const long long per = (long long)n_frames * M;
             YG_TRY(set_smem((const void*)k_pfbch_analysis, smem));
-            const int g1 = (int)std::min<long long>((long long)n_frames * rest, 148 * 16);
+            const int g1 = (int)std::min<long long>((long long)n_frames * rest, q->n_sm * 16);
             k_pfbch_analysis<<<g1, block, smem, st>>>(q->d_h.p, q->d_tw.p, hist + s_fast * Hlen, Hlen, x + s_fast * per,
                                                       y + s_fast * per, M, p, (long long)n_frames, rest);
-            YG_CUDA(cudaGetLastError());
+            YG_LAUNCH_CHECK();
         }
     } else {
         const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
@@ -216,24 +217,24 @@ int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames
             YG_TRY(q->d_U.reserve((size_t)ftm * rest));
             float2* U = reinterpret_cast<float2*>(q->d_U.p);
             YG_TRY(set_smem((const void*)k_pfbch_synth_ifft, smem));
-            const int g1 = (int)std::min<long long>((long long)(n_frames + p - 1) * rest, 148 * 16);
+            const int g1 = (int)std::min<long long>((long long)(n_frames + p - 1) * rest, q->n_sm * 16);
             k_pfbch_synth_ifft<<<g1, block, smem, st>>>(q->d_tw.p, hist + s_fast * Hlen, hist_frames, x + s_fast * per, U, M, p,
                                                         (long long)n_frames, rest);
-            YG_CUDA(cudaGetLastError());
+            YG_LAUNCH_CHECK();
             const long long total = per * rest;
-            const int g3 = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+            const int g3 = (int)std::min<long long>((total + 255) / 256, q->n_sm * 32);
             k_pfbch_synth_fir<<<g3, 256, 0, st>>>(q->d_h.p, U, y + s_fast * per, M, p, (long long)n_frames, rest);
-            YG_CUDA(cudaGetLastError());
+            YG_LAUNCH_CHECK();
         }
     }
     // both types keep the tail of their INPUT stream as state
     if (Hlen > 0) {
         const int nxt = q->cur ^ 1;
-        const int g2 = (int)std::min<long long>((Hlen * S + 255) / 256, 148 * 8);
+        const int g2 = (int)std::min<long long>((Hlen * S + 255) / 256, q->n_sm * 8);
         k_pfbch_update_hist<<<g2, 256, 0, st>>>(reinterpret_cast<float2*>(q->d_hist[nxt].p),
                                                 reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen, x,
                                                 (long long)n_frames * M, S);
-        YG_CUDA(cudaGetLastError());
+        YG_LAUNCH_CHECK();
         q->cur = nxt;
     }
     return YG_OK;
@@ -252,24 +253,25 @@ int32_t build(int32_t type, uint32_t M, uint32_t p, const float* h, size_t h_len
     YG_TRY(require_device(&dev));
     auto* q = new yg_firpfbch_crcf_s();
     q->type = type; q->M = M; q->p = p; q->n_streams = n_streams; q->L = L; q->dev = dev;
+    q->n_sm = sm_count(dev);
     q->h.assign(h, h + L);
     auto cleanup = [&](int32_t rc) { yg_firpfbch_crcf_destroy(q); return rc; };
 #define TRYQ(expr) do { int32_t _rc = (expr); if (_rc != YG_OK) return cleanup(_rc); } while (0)
 #define CUDAQ(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return cleanup(fail(YG_EINTERNAL, "CUDA error %s (%s)", cudaGetErrorString(_e), #expr)); } while (0)
     CUDAQ(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
     TRYQ(q->d_h.reserve(L));
-    CUDAQ(cudaMemcpy(q->d_h.p, q->h.data(), L * sizeof(float), cudaMemcpyHostToDevice));
+    CUDAQ(yg::memcpy_sync(q->d_h.p, q->h.data(), L * sizeof(float), cudaMemcpyHostToDevice));
     std::vector<float2> tw;
     make_twiddles(M, tw);
     TRYQ(q->d_tw.reserve(M));
-    CUDAQ(cudaMemcpy(q->d_tw.p, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
+    CUDAQ(yg::memcpy_sync(q->d_tw.p, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
     // analyser: the last p-1 input frames; synthesiser: at least 16 (one warm-up batch of the fused kernel)
     q->state_len = (type == YG_ANALYZER) ? (size_t)(p - 1) * M : (size_t)std::max<uint32_t>(p - 1, 16) * M;
     TRYQ(firpfbch_fast_plan(q->fast, type, M, p, q->h.data()));
     TRYQ(firpfbch_tiny_plan(q->tiny, type, M, p, q->h.data()));
     for (int b = 0; b < 2; b++) {
         TRYQ(q->d_hist[b].reserve(std::max<size_t>(1, q->state_len * n_streams)));
-        CUDAQ(cudaMemset(q->d_hist[b].p, 0, std::max<size_t>(1, q->state_len * n_streams) * sizeof(yg_cf32)));
+        CUDAQ(yg::memset_sync(q->d_hist[b].p, 0, std::max<size_t>(1, q->state_len * n_streams) * sizeof(yg_cf32)));
     }
 #undef TRYQ
 #undef CUDAQ
@@ -302,13 +304,13 @@ int32_t yg_firpfbch_crcf_create_kaiser(int32_t type, uint32_t M, uint32_t m, flo
 int32_t yg_firpfbch_crcf_clone(yg_firpfbch_crcf q, yg_firpfbch_crcf* out)
 {
     YG_TRY(check(q));
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
     YG_TRY(q->order.wait_host());
     yg_firpfbch_crcf c = nullptr;
     YG_TRY(build(q->type, q->M, q->p, q->h.data(), q->h.size(), q->n_streams, &c));
     if (q->state_len) {
-        cudaError_t e = cudaMemcpy(c->d_hist[c->cur].p, q->d_hist[q->cur].p,
+        cudaError_t e = yg::memcpy_sync(c->d_hist[c->cur].p, q->d_hist[q->cur].p,
                                    q->state_len * q->n_streams * sizeof(yg_cf32), cudaMemcpyDeviceToDevice);
         if (e != cudaSuccess) { yg_firpfbch_crcf_destroy(c); return fail(YG_EINTERNAL, "CUDA error %s", cudaGetErrorString(e)); }
     }
@@ -319,7 +321,7 @@ int32_t yg_firpfbch_crcf_clone(yg_firpfbch_crcf q, yg_firpfbch_crcf* out)
 int32_t yg_firpfbch_crcf_destroy(yg_firpfbch_crcf q)
 {
     if (!q) return YG_OK;
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     if (q->stream) cudaStreamSynchronize(q->stream);
     q->order.wait_host();
     q->order.destroy();
@@ -335,7 +337,7 @@ int32_t yg_firpfbch_crcf_destroy(yg_firpfbch_crcf q)
 int32_t yg_firpfbch_crcf_reset(yg_firpfbch_crcf q)
 {
     YG_TRY(check(q));
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     YG_TRY(q->order.wait_host());
     if (q->state_len)
         YG_CUDA(cudaMemsetAsync(q->d_hist[q->cur].p, 0, q->state_len * q->n_streams * sizeof(yg_cf32), q->stream));
@@ -349,7 +351,7 @@ int32_t yg_firpfbch_crcf_execute_block_dev(yg_firpfbch_crcf q, const yg_cf32* d_
 {
     YG_TRY(check(q));
     if (n_frames && (!d_x || !d_y)) return fail(YG_EVALUE, "null buffer");
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     return execute_dev(q, d_x, n_frames, d_y, (cudaStream_t)cuda_stream);
 }
 
@@ -358,7 +360,7 @@ int32_t yg_firpfbch_crcf_execute_block(yg_firpfbch_crcf q, const yg_cf32* x, siz
     YG_TRY(check(q));
     if (n_frames && (!x || !y)) return fail(YG_EVALUE, "null buffer");
     if (n_frames == 0) return YG_OK;
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     // stream-major layout makes time-chunking a strided copy; stage the whole block
     const size_t n = n_frames * (size_t)q->M * q->n_streams;
     YG_TRY(q->d_stage_x.reserve(n));
@@ -379,7 +381,7 @@ int32_t yg_firpfbch_crcf_execute(yg_firpfbch_crcf q, const yg_cf32* x, yg_cf32* 
 int32_t yg_firpfbch_crcf_sync(yg_firpfbch_crcf q)
 {
     YG_TRY(check(q));
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
     YG_TRY(q->order.wait_host());
     return YG_OK;
@@ -389,6 +391,7 @@ int32_t yg_firpfbch_crcf_get_type(yg_firpfbch_crcf q, int32_t* type) { YG_TRY(ch
 int32_t yg_firpfbch_crcf_get_M(yg_firpfbch_crcf q, uint32_t* M) { YG_TRY(check(q)); *M = q->M; return YG_OK; }
 int32_t yg_firpfbch_crcf_get_p(yg_firpfbch_crcf q, uint32_t* p) { YG_TRY(check(q)); *p = q->p; return YG_OK; }
 int32_t yg_firpfbch_crcf_get_n_streams(yg_firpfbch_crcf q, uint32_t* n) { YG_TRY(check(q)); *n = q->n_streams; return YG_OK; }
+int32_t yg_firpfbch_crcf_get_device(yg_firpfbch_crcf q, int32_t* dev) { YG_TRY(check(q)); *dev = q->dev; return YG_OK; }
 int32_t yg_firpfbch_crcf_last_path(yg_firpfbch_crcf q, int32_t* path) { YG_TRY(check(q)); *path = q->last_path; return YG_OK; }
 int32_t yg_firpfbch_crcf_get_taps(yg_firpfbch_crcf q, float* h)
 {

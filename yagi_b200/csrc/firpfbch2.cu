@@ -18,6 +18,7 @@ struct yg_firpfbch2_crcf_s {
     uint32_t M = 0, M2 = 0, m = 0;
     size_t L = 0;                 // taps used = 2*M*m
     int dev = 0;
+    int n_sm = 1;                  // multiprocessor count of `dev` (grid sizing)
     cudaStream_t stream = nullptr;
     StreamOrder order;
     std::vector<float> h;         // prototype (L)
@@ -37,6 +38,7 @@ struct yg_firpfbch2_crcf_s {
     unsigned long long n_timed = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // the pair being recorded by the current call
     bool timed = false;
+    bool timing_on = true;        // record CUDA events around the dominant kernel (yg_firpfbch2_crcf_set_kernel_timing)
     void next_events() { ev0 = ev0s[n_timed % kRing]; ev1 = ev1s[n_timed % kRing]; n_timed++; }
     Firpfbch2FastPlan fast;       // fused fast path (may be unsupported for this M/m)
     Firpfbch2FastPlan sfast;      // fused synthesis fast path
@@ -280,23 +282,24 @@ int32_t launch_generic_analysis(yg_firpfbch2_crcf q, const float2* hist, const f
         const uint32_t F = 256 / q->M;
         const size_t smem_s = ((size_t)F * q->M + q->M) * sizeof(float2);
         const long long groups = ((long long)(f_end - f_begin) + F - 1) / F;
-        const int grid_s = (int)std::min<long long>(groups, 148 * 8);
+        const int grid_s = (int)std::min<long long>(groups, q->n_sm * 8);
         k_analysis_generic_small<<<grid_s, 256, smem_s, st>>>(q->d_h.p, q->d_tw.p, hist, (long long)q->hist_len, x, y, q->M,
                                                               2 * q->m, (long long)f_begin, (long long)f_end, q->flag);
-        YG_CUDA(cudaGetLastError());
+        YG_LAUNCH_CHECK();
         return YG_OK;
     }
     const size_t smem = smem_dft(q->M);
     YG_TRY(set_smem((const void*)k_analysis_generic, smem));
     const int block = (int)std::min<uint32_t>(256, (q->M + 31) / 32 * 32);
-    const int grid = (int)std::min<size_t>(f_end - f_begin, 148 * 16);
+    const int grid = (int)std::min<size_t>(f_end - f_begin, q->n_sm * 16);
     k_analysis_generic<<<grid, block, smem, st>>>(q->d_h.p, q->d_tw.p, hist, (long long)q->hist_len, x, y, q->M,
                                                   2 * q->m, (long long)f_begin, (long long)f_end, q->flag);
-    YG_CUDA(cudaGetLastError());
+    YG_LAUNCH_CHECK();
     return YG_OK;
 }
 
-int32_t launch_analysis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
+// *hist_done is set when the kernel that took the call also wrote the next state into d_hist[cur ^ 1]
+int32_t launch_analysis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st, bool* hist_done)
 {
     const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
     const float2* x = reinterpret_cast<const float2*>(d_x);
@@ -305,7 +308,7 @@ int32_t launch_analysis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames
     // The fused kernel handles an even-parity start and an even number of frames; what is
     // left over (a leading odd-parity frame, a trailing single frame) and calls too small to
     // fill the machine go to the generic kernel.
-    q->next_events();
+    if (q->timing_on) q->next_events();
     // the fused kernels read the input with TMA bulk copies, which need 16-byte aligned sources
     const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     const bool use_fused = aligned && q->fast.supported && n_frames >= q->fast.min_frames;
@@ -315,22 +318,26 @@ int32_t launch_analysis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames
     if (use_fused || use_large || use_small || use_tiny) {
         const size_t lead = (q->flag & 1) ? 1 : 0;
         const size_t body = (n_frames - lead) & ~(size_t)1;
-        YG_CUDA(cudaEventRecord(q->ev0, st));
-        if (use_fused) YG_TRY(firpfbch2_fast_launch(q->fast, hist, (long long)q->hist_len, x, y, lead, body, st));
+        if (q->timing_on) YG_CUDA(cudaEventRecord(q->ev0, st));
+        if (use_fused) {
+            YG_TRY(firpfbch2_fast_launch(q->fast, hist, (long long)q->hist_len, x, y, lead, body, st,
+                                         reinterpret_cast<float2*>(q->d_hist[q->cur ^ 1].p), (long long)n_frames * q->M2));
+            *hist_done = true;
+        }
         else if (use_small) YG_TRY(firpfbch2_small_launch(q->small, hist, (long long)q->hist_len, x, y, lead, body, st));
         else if (use_tiny) YG_TRY(firpfbch2_tiny_launch(q->tiny, hist, (long long)q->hist_len, x, y, lead, body, st));
         else YG_TRY(firpfbch2_large_launch(q->large, hist, (long long)q->hist_len, x, y, lead, body, st));
-        YG_CUDA(cudaEventRecord(q->ev1, st));
-        q->timed = true;
+        if (q->timing_on) YG_CUDA(cudaEventRecord(q->ev1, st));
+        q->timed = q->timing_on;
         q->last_path = (use_fused || use_small || use_tiny) ? 2 : 3;
         YG_TRY(launch_generic_analysis(q, hist, x, y, 0, lead, st));
         YG_TRY(launch_generic_analysis(q, hist, x, y, lead + body, n_frames, st));
         return YG_OK;
     }
-    YG_CUDA(cudaEventRecord(q->ev0, st));
+    if (q->timing_on) YG_CUDA(cudaEventRecord(q->ev0, st));
     YG_TRY(launch_generic_analysis(q, hist, x, y, 0, n_frames, st));
-    YG_CUDA(cudaEventRecord(q->ev1, st));
-    q->timed = true;
+    if (q->timing_on) YG_CUDA(cudaEventRecord(q->ev1, st));
+    q->timed = q->timing_on;
     q->last_path = 1;
     return YG_OK;
 }
@@ -353,17 +360,17 @@ int32_t launch_generic_synthesis(yg_firpfbch2_crcf q, const float2* hist, const 
         if (M <= 64) {                   // several frames per block
             const uint32_t F = 256 / M;
             const size_t smem_s = ((size_t)F * M + M) * sizeof(float2);
-            const int grid_s = (int)std::min<long long>((nh + nf + F - 1) / F, 148 * 8);
+            const int grid_s = (int)std::min<long long>((nh + nf + F - 1) / F, q->n_sm * 8);
             k_synth_ifft_small<<<grid_s, 256, smem_s, st>>>(q->d_tw.p, hist, (long long)(q->hist_len / M), x, U, M, f0 - nh, f0 + nf);
         } else {
-            const int grid = (int)std::min<long long>(nh + nf, 148 * 16);
+            const int grid = (int)std::min<long long>(nh + nf, q->n_sm * 16);
             k_synth_ifft<<<grid, block, smem, st>>>(q->d_tw.p, hist, (long long)(q->hist_len / M), x, U, M, f0 - nh, f0 + nf);
         }
-        YG_CUDA(cudaGetLastError());
+        YG_LAUNCH_CHECK();
         const long long total = nf * q->M2;
-        const int grid2 = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+        const int grid2 = (int)std::min<long long>((total + 255) / 256, q->n_sm * 32);
         k_synth_wola<<<grid2, 256, 0, st>>>(q->d_h.p, U + nh * M, y + f0 * q->M2, M, q->m, nf, (q->flag + (int)(f0 & 1)) & 1);
-        YG_CUDA(cudaGetLastError());
+        YG_LAUNCH_CHECK();
     }
     return YG_OK;
 }
@@ -373,7 +380,7 @@ int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frame
     const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
     const float2* x = reinterpret_cast<const float2*>(d_x);
     float2* y = reinterpret_cast<float2*>(d_y);
-    q->next_events();
+    if (q->timing_on) q->next_events();
     // The fused kernel takes an even-parity start and whole rounds of 32 frames; the rest goes to
     // the generic kernels.  All of them read the same (history ++ x) stream and write disjoint
     // output ranges, so their order does not matter.
@@ -385,22 +392,22 @@ int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frame
     if (use_fused || use_large) {
         if (use_large && firpfbch2_large_synth_needs_scratch(q->slarge, hist, x))
             YG_TRY(q->d_Uc.reserve((size_t)firpfbch2_large_synth_scratch_frames(q->M) * q->M));
-        YG_CUDA(cudaEventRecord(q->ev0, st));
+        if (q->timing_on) YG_CUDA(cudaEventRecord(q->ev0, st));
         if (use_fused && q->M == 256) YG_TRY(firpfbch2_synth_fast_launch(q->sfast, hist, x, y, lead, body, st));
         else if (use_fused && q->M >= 64) YG_TRY(firpfbch2_small_synth_launch(q->sfast, hist, x, y, lead, body, st));
         else if (use_fused) YG_TRY(firpfbch2_tiny_synth_launch(q->sfast, hist, x, y, lead, body, st));
         else YG_TRY(firpfbch2_large_synth_launch(q->slarge, hist, x, y, reinterpret_cast<float2*>(q->d_Uc.p), lead, body, st));
-        YG_CUDA(cudaEventRecord(q->ev1, st));
-        q->timed = true;
+        if (q->timing_on) YG_CUDA(cudaEventRecord(q->ev1, st));
+        q->timed = q->timing_on;
         q->last_path = use_fused ? 2 : 3;
         YG_TRY(launch_generic_synthesis(q, hist, x, y, 0, lead, st));
         YG_TRY(launch_generic_synthesis(q, hist, x, y, lead + body, n_frames, st));
         return YG_OK;
     }
-    YG_CUDA(cudaEventRecord(q->ev0, st));
+    if (q->timing_on) YG_CUDA(cudaEventRecord(q->ev0, st));
     YG_TRY(launch_generic_synthesis(q, hist, x, y, 0, n_frames, st));
-    YG_CUDA(cudaEventRecord(q->ev1, st));
-    q->timed = true;
+    if (q->timing_on) YG_CUDA(cudaEventRecord(q->ev1, st));
+    q->timed = q->timing_on;
     q->last_path = 1;
     return YG_OK;
 }
@@ -417,17 +424,20 @@ int32_t execute_dev(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg
 int32_t execute_dev_impl(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
 {
     if (n_frames == 0) return YG_OK;
-    if (q->type == YG_ANALYZER) YG_TRY(launch_analysis(q, d_x, n_frames, d_y, st));
+    bool hist_done = false;
+    if (q->type == YG_ANALYZER) YG_TRY(launch_analysis(q, d_x, n_frames, d_y, st, &hist_done));
     else YG_TRY(launch_synthesis(q, d_x, n_frames, d_y, st));
     // both types keep the tail of their INPUT stream as state
     const long long n_new = (long long)n_frames * (q->type == YG_ANALYZER ? q->M2 : q->M);
     const long long Hlen = (long long)q->hist_len;
     const int nxt = q->cur ^ 1;
-    const int grid = (int)std::min<long long>((Hlen + 255) / 256, 1024);
-    k_update_hist<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(q->d_hist[nxt].p),
-                                        reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
-                                        reinterpret_cast<const float2*>(d_x), n_new);
-    YG_CUDA(cudaGetLastError());
+    if (!hist_done) {
+        const int grid = (int)std::min<long long>((Hlen + 255) / 256, 1024);
+        k_update_hist<<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(q->d_hist[nxt].p),
+                                            reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
+                                            reinterpret_cast<const float2*>(d_x), n_new);
+        YG_LAUNCH_CHECK();
+    }
     q->cur = nxt;
     q->flag = (q->flag + (int)(n_frames & 1)) & 1;
     return YG_OK;
@@ -446,6 +456,7 @@ int32_t build(int32_t type, uint32_t M, uint32_t m, const float* h, size_t h_len
 
     auto* q = new yg_firpfbch2_crcf_s();
     q->type = type; q->M = M; q->M2 = M / 2; q->m = m; q->L = L; q->dev = dev;
+    q->n_sm = sm_count(dev);
     q->h.assign(h, h + L);
     auto cleanup = [&](int32_t rc) { yg_firpfbch2_crcf_destroy(q); return rc; };
 #define TRYQ(expr) do { int32_t _rc = (expr); if (_rc != YG_OK) return cleanup(_rc); } while (0)
@@ -456,18 +467,18 @@ int32_t build(int32_t type, uint32_t M, uint32_t m, const float* h, size_t h_len
         CUDAQ(cudaEventCreate(&q->ev1s[i]));
     }
     TRYQ(q->d_h.reserve(L));
-    CUDAQ(cudaMemcpy(q->d_h.p, q->h.data(), L * sizeof(float), cudaMemcpyHostToDevice));
+    CUDAQ(yg::memcpy_sync(q->d_h.p, q->h.data(), L * sizeof(float), cudaMemcpyHostToDevice));
     std::vector<float2> tw;
     make_twiddles(M, tw);
     TRYQ(q->d_tw.reserve(M));
-    CUDAQ(cudaMemcpy(q->d_tw.p, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
+    CUDAQ(yg::memcpy_sync(q->d_tw.p, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
     const size_t nh = 4 * (size_t)m - 1;
     q->state_len = (type == YG_ANALYZER) ? nh * q->M2 : nh * M;
     // the synthesiser keeps at least 32 input frames so the fused kernel can warm up a whole round
     q->hist_len = (type == YG_ANALYZER) ? q->state_len : std::max<size_t>(nh, 32) * M;
     for (int b = 0; b < 2; b++) {
         TRYQ(q->d_hist[b].reserve(q->hist_len));
-        CUDAQ(cudaMemset(q->d_hist[b].p, 0, q->hist_len * sizeof(yg_cf32)));
+        CUDAQ(yg::memset_sync(q->d_hist[b].p, 0, q->hist_len * sizeof(yg_cf32)));
     }
     if (type == YG_ANALYZER) TRYQ(firpfbch2_fast_plan(q->fast, M, m, q->h.data()));
     if (type == YG_ANALYZER) TRYQ(firpfbch2_large_plan(q->large, M, m, q->h.data()));
@@ -514,12 +525,12 @@ int32_t yg_firpfbch2_crcf_create_kaiser(int32_t type, uint32_t M, uint32_t m, fl
 int32_t yg_firpfbch2_crcf_clone(yg_firpfbch2_crcf q, yg_firpfbch2_crcf* out)
 {
     YG_TRY(check(q));
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
     YG_TRY(q->order.wait_host());
     yg_firpfbch2_crcf c = nullptr;
     YG_TRY(build(q->type, q->M, q->m, q->h.data(), q->h.size(), &c));
-    cudaError_t e = cudaMemcpy(c->d_hist[c->cur].p, q->d_hist[q->cur].p, q->hist_len * sizeof(yg_cf32),
+    cudaError_t e = yg::memcpy_sync(c->d_hist[c->cur].p, q->d_hist[q->cur].p, q->hist_len * sizeof(yg_cf32),
                                cudaMemcpyDeviceToDevice);
     if (e != cudaSuccess) { yg_firpfbch2_crcf_destroy(c); return fail(YG_EINTERNAL, "CUDA error %s", cudaGetErrorString(e)); }
     c->flag = q->flag;
@@ -530,7 +541,7 @@ int32_t yg_firpfbch2_crcf_clone(yg_firpfbch2_crcf q, yg_firpfbch2_crcf* out)
 int32_t yg_firpfbch2_crcf_destroy(yg_firpfbch2_crcf q)
 {
     if (!q) return YG_OK;
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     if (q->stream) cudaStreamSynchronize(q->stream);
     q->order.wait_host();
     q->order.destroy();
@@ -555,7 +566,7 @@ int32_t yg_firpfbch2_crcf_destroy(yg_firpfbch2_crcf q)
 int32_t yg_firpfbch2_crcf_reset(yg_firpfbch2_crcf q)
 {
     YG_TRY(check(q));
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     YG_TRY(q->order.wait_host());
     YG_CUDA(cudaMemsetAsync(q->d_hist[q->cur].p, 0, q->hist_len * sizeof(yg_cf32), q->stream));
     YG_CUDA(cudaStreamSynchronize(q->stream));
@@ -569,7 +580,7 @@ int32_t yg_firpfbch2_crcf_execute_block_dev(yg_firpfbch2_crcf q, const yg_cf32* 
 {
     YG_TRY(check(q));
     if (n_frames && (!d_x || !d_y)) return fail(YG_EVALUE, "null buffer");
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     return execute_dev(q, d_x, n_frames, d_y, st);
 }
@@ -578,7 +589,7 @@ int32_t yg_firpfbch2_crcf_execute_block(yg_firpfbch2_crcf q, const yg_cf32* x, s
 {
     YG_TRY(check(q));
     if (n_frames && (!x || !y)) return fail(YG_EVALUE, "null buffer");
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     const size_t nin = (q->type == YG_ANALYZER) ? q->M2 : q->M;
     const size_t nout = (q->type == YG_ANALYZER) ? q->M : q->M2;
     // ~32 MiB of input per chunk
@@ -598,7 +609,7 @@ int32_t yg_firpfbch2_crcf_execute(yg_firpfbch2_crcf q, const yg_cf32* x, yg_cf32
 int32_t yg_firpfbch2_crcf_sync(yg_firpfbch2_crcf q)
 {
     YG_TRY(check(q));
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
     YG_TRY(q->order.wait_host());
     return YG_OK;
@@ -626,10 +637,10 @@ int32_t yg_firpfbch2_crcf_state_len(yg_firpfbch2_crcf q, size_t* n)
 int32_t yg_firpfbch2_crcf_get_state(yg_firpfbch2_crcf q, yg_cf32* hist, int32_t* flag)
 {
     YG_TRY(check(q));
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
     YG_TRY(q->order.wait_host());
-    if (hist) YG_CUDA(cudaMemcpy(hist, q->d_hist[q->cur].p + (q->hist_len - q->state_len), q->state_len * sizeof(yg_cf32), cudaMemcpyDeviceToHost));
+    if (hist) YG_CUDA(yg::memcpy_sync(hist, q->d_hist[q->cur].p + (q->hist_len - q->state_len), q->state_len * sizeof(yg_cf32), cudaMemcpyDeviceToHost));
     if (flag) *flag = q->flag;
     return YG_OK;
 }
@@ -638,12 +649,12 @@ int32_t yg_firpfbch2_crcf_set_state(yg_firpfbch2_crcf q, const yg_cf32* hist, in
 {
     YG_TRY(check(q));
     if (flag != 0 && flag != 1) return fail(YG_EVALUE, "flag must be 0 or 1");
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     YG_CUDA(cudaStreamSynchronize(q->stream));
     YG_TRY(q->order.wait_host());
     if (hist) {
-        YG_CUDA(cudaMemset(q->d_hist[q->cur].p, 0, q->hist_len * sizeof(yg_cf32)));
-        YG_CUDA(cudaMemcpy(q->d_hist[q->cur].p + (q->hist_len - q->state_len), hist, q->state_len * sizeof(yg_cf32), cudaMemcpyHostToDevice));
+        YG_CUDA(yg::memset_sync(q->d_hist[q->cur].p, 0, q->hist_len * sizeof(yg_cf32)));
+        YG_CUDA(yg::memcpy_sync(q->d_hist[q->cur].p + (q->hist_len - q->state_len), hist, q->state_len * sizeof(yg_cf32), cudaMemcpyHostToDevice));
     }
     q->flag = flag;
     return YG_OK;
@@ -651,11 +662,21 @@ int32_t yg_firpfbch2_crcf_set_state(yg_firpfbch2_crcf q, const yg_cf32* hist, in
 
 int32_t yg_firpfbch2_crcf_last_path(yg_firpfbch2_crcf q, int32_t* path) { YG_TRY(check(q)); *path = q->last_path; return YG_OK; }
 
+int32_t yg_firpfbch2_crcf_get_device(yg_firpfbch2_crcf q, int32_t* dev) { YG_TRY(check(q)); *dev = q->dev; return YG_OK; }
+
+int32_t yg_firpfbch2_crcf_set_kernel_timing(yg_firpfbch2_crcf q, int32_t enable)
+{
+    YG_TRY(check(q));
+    q->timing_on = enable != 0;
+    if (!q->timing_on) { q->timed = false; q->n_timed = 0; }
+    return YG_OK;
+}
+
 int32_t yg_firpfbch2_crcf_last_kernel_ms(yg_firpfbch2_crcf q, float* ms)
 {
     YG_TRY(check(q));
     if (!q->timed) return fail(YG_EMODE, "no timed launch yet");
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     YG_CUDA(cudaEventSynchronize(q->ev1));
     YG_CUDA(cudaEventElapsedTime(ms, q->ev0, q->ev1));
     return YG_OK;
@@ -665,7 +686,7 @@ int32_t yg_firpfbch2_crcf_kernel_times(yg_firpfbch2_crcf q, float* ms, size_t ca
 {
     YG_TRY(check(q));
     if (!ms || !n) return fail(YG_EVALUE, "null pointer");
-    DeviceGuard g(q->dev);
+    YG_DEVICE_GUARD(q->dev);
     const unsigned long long have = std::min<unsigned long long>(q->n_timed, yg_firpfbch2_crcf_s::kRing);
     const size_t take = (size_t)std::min<unsigned long long>(have, cap);
     for (size_t i = 0; i < take; i++) {

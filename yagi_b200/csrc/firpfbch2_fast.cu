@@ -60,6 +60,8 @@ struct FastParams {
     long long n_pairs;        // frame pairs handled here
     const float2* taps;       // [256][kTaps] (even, odd) tap pairs, 1/M folded in
     const float2* twid;       // [16][16] e^{+j 2 pi n2 k1 / 256}
+    float2* hist_new;         // if non-null: receives the last Hlen samples of (hist ++ x[0 .. n_new)), the
+    long long n_new;          //   object's state after the call (folds the k_update_hist launch into this one)
 };
 
 template <int kTaps>                     // 2m + 1
@@ -239,6 +241,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_firpfbch2_analysis_fused(const 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    // State hand-off folded into this launch: the FFT-role threads of the last CTA have nothing to do until
+    // the first V regions are written, so they copy the tail of the input stream into the other history buffer.
+    if (p.hist_new != nullptr && blockIdx.x == gridDim.x - 1 && threadIdx.x >= kFirThreads) {
+        for (long long i = threadIdx.x - kFirThreads; i < p.Hlen; i += kFftThreads) {
+            const long long t = p.n_new - p.Hlen + i;
+            p.hist_new[i] = (t >= 0) ? __ldg(&p.x[t]) : __ldg(&p.hist[p.Hlen + t]);
+        }
+    }
     if (batch_begin >= batch_end) return;
 
     if (threadIdx.x < kFirThreads) fir_role<kTaps>(p, smem, mbar, batch_begin, batch_end);
@@ -253,7 +263,7 @@ int32_t launch_t(const Firpfbch2FastPlan& plan, const FastParams& p, cudaStream_
     const long long n_batches = (p.n_pairs + kPairsPerBatch - 1) / kPairsPerBatch;
     const int grid = (int)std::min<long long>(plan.n_sm, n_batches);
     k_firpfbch2_analysis_fused<kTaps><<<grid, kThreads, kSmemBytes, st>>>(p);
-    YG_CUDA(cudaGetLastError());
+    YG_LAUNCH_CHECK();
     return YG_OK;
 }
 
@@ -299,9 +309,9 @@ int32_t firpfbch2_fast_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const 
             tw[n2 * 16 + k1] = make_float2((float)cos(a), (float)sin(a));
         }
     YG_CUDA(cudaMalloc(&p.d_taps, taps.size() * sizeof(float2)));
-    YG_CUDA(cudaMemcpy(p.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(p.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
     YG_CUDA(cudaMalloc(&p.d_twid, tw.size() * sizeof(float2)));
-    YG_CUDA(cudaMemcpy(p.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(p.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     p.min_frames = 64;
     p.supported = true;
     return YG_OK;
@@ -319,7 +329,7 @@ void firpfbch2_fast_release(Firpfbch2FastPlan& p)
 }
 
 int32_t firpfbch2_fast_launch(const Firpfbch2FastPlan& plan, const float2* hist, long long Hlen, const float2* x,
-                              float2* y, size_t f0, size_t n_frames, cudaStream_t st)
+                              float2* y, size_t f0, size_t n_frames, cudaStream_t st, float2* hist_new, long long n_new)
 {
     if (!plan.supported) return fail(YG_EINTERNAL, "fused kernel not available for this geometry");
     if (n_frames == 0) return YG_OK;
@@ -331,6 +341,8 @@ int32_t firpfbch2_fast_launch(const Firpfbch2FastPlan& plan, const float2* hist,
     p.n_pairs = (long long)(n_frames / 2);
     p.taps = reinterpret_cast<const float2*>(plan.d_taps);
     p.twid = reinterpret_cast<const float2*>(plan.d_twid);
+    p.hist_new = hist_new;
+    p.n_new = n_new;
     switch (plan.m) {
         case 1: return launch_t<3>(plan, p, st);
         case 2: return launch_t<5>(plan, p, st);

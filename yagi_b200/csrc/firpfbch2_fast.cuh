@@ -22,8 +22,11 @@ void firpfbch2_fast_release(Firpfbch2FastPlan& p);
 
 // Frames [f0, f0 + n_frames) of the call (f0 even-parity in the global frame count, n_frames
 // even).  `x` points at the first sample of the call, `hist` holds the Hlen samples before it.
+// With `hist_new` non-null the kernel also writes the object's next state (the last Hlen samples of
+// hist ++ x[0 .. n_new)) there, which saves the separate k_update_hist launch.
 int32_t firpfbch2_fast_launch(const Firpfbch2FastPlan& p, const float2* hist, long long Hlen, const float2* x,
-                              float2* y, size_t f0, size_t n_frames, cudaStream_t st);
+                              float2* y, size_t f0, size_t n_frames, cudaStream_t st, float2* hist_new = nullptr,
+                              long long n_new = 0);
 
 // Fused synthesis (firpfbch2_synth_fast.cu).  `prefix` = the 32 input frames preceding x[0] of the
 // call; frames [f0, f0 + n_frames) of the call, f0 on even global parity, n_frames a multiple of 32.

@@ -604,6 +604,7 @@ int32_t launch_fused(const FusedParams& fp, cudaStream_t st)
     const int G = fp.base.M / kFirThreads;
     YG_CUDA(cudaLaunchCooperativeKernel((const void*)k_large_fused<kTaps>, dim3((unsigned)(G * fp.n_groups)),
                                         dim3(kFirThreads + kFftWarps * 32), args, (size_t)kFusedSmem, st));
+    count_launch();
     return YG_OK;
 }
 
@@ -624,7 +625,7 @@ int32_t launch_fft(const Firpfbch2FastPlan& plan, const float2* prefix, const fl
     } else {
         return fail(YG_EINTERNAL, "large-M path: no transform for M = %u", plan.M);
     }
-    YG_CUDA(cudaGetLastError());
+    YG_LAUNCH_CHECK();
     return YG_OK;
 }
 
@@ -918,6 +919,7 @@ int32_t launch_synth_fused(const SynthFusedParams& p, cudaStream_t st)
     const int G = p.M / kFirThreads;
     YG_CUDA(cudaLaunchCooperativeKernel((const void*)k_large_synth_fused<kTaps>, dim3((unsigned)(G * p.n_groups)),
                                         dim3(kFirThreads + 256), args, (size_t)synth_fused_smem(kTaps), st));
+    count_launch();
     return YG_OK;
 }
 
@@ -926,7 +928,7 @@ int32_t launch_wola(const WolaParams& p, cudaStream_t st)
 {
     dim3 grid((unsigned)p.slabs, (unsigned)(p.M / kFirThreads));
     k_large_wola<kTaps><<<grid, kFirThreads, 0, st>>>(p);
-    YG_CUDA(cudaGetLastError());
+    YG_LAUNCH_CHECK();
     return YG_OK;
 }
 
@@ -935,7 +937,7 @@ int32_t launch_fir(const LargeParams& p, cudaStream_t st)
 {
     dim3 grid((unsigned)p.slabs, (unsigned)(p.M / kFirThreads));
     k_large_fir<kTaps><<<grid, kFirThreads, 0, st>>>(p);
-    YG_CUDA(cudaGetLastError());
+    YG_LAUNCH_CHECK();
     return YG_OK;
 }
 
@@ -959,7 +961,7 @@ int32_t plan_common(Firpfbch2FastPlan& plan, uint32_t M)
         tw[k] = make_float2((float)cos(a), (float)sin(a));
     }
     YG_CUDA(cudaMalloc(&plan.d_twid, tw.size() * sizeof(float2)));
-    YG_CUDA(cudaMemcpy(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     if (M == 1024) YG_CUDA(cudaFuncSetAttribute(k_large_fft<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
     else if (M == 2048) YG_CUDA(cudaFuncSetAttribute(k_large_fft<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
     else if (M == 512) YG_CUDA(cudaFuncSetAttribute(k_large_fft512, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmem));
@@ -1048,7 +1050,7 @@ int32_t firpfbch2_large_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
             taps[(size_t)j * kTaps + i] = make_float2(te * s, to * s);
         }
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float2)));
-    YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(plan.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
     YG_TRY(plan_common(plan, M));
     if (plan.supported) YG_TRY(plan_fused(plan, false));
     return YG_OK;
@@ -1138,7 +1140,7 @@ int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t
     for (int j = 0; j < iM; j++)
         for (int l = 0; l < kTaps; l++) taps[(size_t)j * kTaps + l] = 0.5f * h[(j & (iM2 - 1)) + l * iM2];
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float)));
-    YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
     YG_TRY(plan_common(plan, M));
     if (plan.supported) YG_TRY(plan_fused(plan, true));
     return YG_OK;

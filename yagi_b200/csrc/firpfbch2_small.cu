@@ -324,7 +324,7 @@ int32_t launch_t(const Firpfbch2FastPlan& plan, SmallParams p, cudaStream_t st)
     const int grid = (int)std::min<long long>(plan.n_sm, (n_batches + kSlots - 1) / kSlots);
     p.n_slabs = grid * kSlots;
     k_firpfbch2_analysis_small<kM, kTaps><<<grid, kThreads, kSmemBytes, st>>>(p);
-    YG_CUDA(cudaGetLastError());
+    YG_LAUNCH_CHECK();
     return YG_OK;
 }
 
@@ -365,9 +365,9 @@ int32_t firpfbch2_small_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
             tw[(size_t)n2 * R1 + k1] = make_float2((float)cos(a), (float)sin(a));
         }
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float2)));
-    YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(plan.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
     YG_CUDA(cudaMalloc(&plan.d_twid, tw.size() * sizeof(float2)));
-    YG_CUDA(cudaMemcpy(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     plan.min_frames = 256;
     plan.supported = true;
     return YG_OK;

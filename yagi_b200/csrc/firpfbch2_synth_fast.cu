@@ -265,7 +265,7 @@ int32_t launch_t(const Firpfbch2FastPlan& plan, const SynthParams& p, cudaStream
     YG_CUDA(cudaFuncSetAttribute(k_firpfbch2_synthesis_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     const int grid = (int)std::min<long long>(plan.n_sm, p.n_periods);
     k_firpfbch2_synthesis_fused<kTaps><<<grid, kThreads, kSmemBytes, st>>>(p);
-    YG_CUDA(cudaGetLastError());
+    YG_LAUNCH_CHECK();
     return YG_OK;
 }
 
@@ -296,9 +296,9 @@ int32_t firpfbch2_synth_fast_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, 
             tw[n2 * 16 + k1] = make_float2((float)cos(a), (float)sin(a));
         }
     YG_CUDA(cudaMalloc(&p.d_taps, taps.size() * sizeof(float)));
-    YG_CUDA(cudaMemcpy(p.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(p.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
     YG_CUDA(cudaMalloc(&p.d_twid, tw.size() * sizeof(float2)));
-    YG_CUDA(cudaMemcpy(p.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(p.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     p.min_frames = 64;
     p.supported = true;
     return YG_OK;

@@ -263,7 +263,7 @@ int32_t launch_t(const Firpfbch2FastPlan& plan, const TinySynthParams& p, cudaSt
     YG_CUDA(cudaFuncSetAttribute(k_firpfbch2_synthesis_tiny<kM, kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     const int grid = (int)std::max<long long>(1, std::min<long long>(plan.n_sm, (p.n_batches + kUnits * kSPW - 1) / (kUnits * kSPW)));
     k_firpfbch2_synthesis_tiny<kM, kTaps><<<grid, 2 * kRoleThreads, kSmemBytes, st>>>(p);
-    YG_CUDA(cudaGetLastError());
+    YG_LAUNCH_CHECK();
     return YG_OK;
 }
 
@@ -306,9 +306,9 @@ int32_t firpfbch2_tiny_synth_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t 
         tw[k] = make_float2((float)cos(a), (float)sin(a));
     }
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float)));
-    YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
     YG_CUDA(cudaMalloc(&plan.d_twid, tw.size() * sizeof(float2)));
-    YG_CUDA(cudaMemcpy(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     plan.min_frames = 2048;
     plan.supported = true;
     return YG_OK;

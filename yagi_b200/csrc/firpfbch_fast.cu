@@ -268,7 +268,7 @@ int32_t launch_t(const FirpfbchFastPlan& plan, const PfbParams& p, cudaStream_t 
     const long long n_batches = (long long)p.n_groups * p.batches_per_group;
     const int grid = (int)std::min<long long>(plan.n_sm, n_batches);
     k_firpfbch_analysis_fused<kTaps><<<grid, kThreads, kSmemBytes, st>>>(p);
-    YG_CUDA(cudaGetLastError());
+    YG_LAUNCH_CHECK();
     return YG_OK;
 }
 
@@ -487,7 +487,7 @@ int32_t launch_syn_t(const FirpfbchFastPlan& plan, const PfbSynParams& p, cudaSt
     const long long n_batches = (long long)p.n_groups * p.batches_per_group;
     const int grid = (int)std::min<long long>(plan.n_sm, n_batches);
     k_firpfbch_synthesis_fused<kTaps><<<grid, kThreads, kSynSmemBytes, st>>>(p);
-    YG_CUDA(cudaGetLastError());
+    YG_LAUNCH_CHECK();
     return YG_OK;
 }
 
@@ -517,9 +517,9 @@ int32_t firpfbch_fast_plan(FirpfbchFastPlan& plan, int32_t type, uint32_t M, uin
             tw[n2 * 8 + k1] = make_float2((float)cos(a), (float)sin(a));
         }
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float)));
-    YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
     YG_CUDA(cudaMalloc(&plan.d_twid, tw.size() * sizeof(float2)));
-    YG_CUDA(cudaMemcpy(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     plan.supported = true;
     return YG_OK;
 }

@@ -388,7 +388,7 @@ int32_t launch_t(int n_sm, const TinyPfbParams& p, cudaStream_t st)
     const long long n_items = (long long)p.n_groups * p.batches_per_group;
     const int grid = (int)std::max<long long>(1, std::min<long long>(n_sm, (n_items + kUnits - 1) / kUnits));
     k_firpfbch_tiny<kM, kTaps, kSynth><<<grid, 2 * kRoleThreads, kSmemBytes, st>>>(p);
-    YG_CUDA(cudaGetLastError());
+    YG_LAUNCH_CHECK();
     return YG_OK;
 }
 
@@ -435,9 +435,9 @@ int32_t firpfbch_tiny_plan(FirpfbchFastPlan& plan, int32_t type, uint32_t M, uin
         tw[k] = make_float2((float)cos(a), (float)sin(a));
     }
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float)));
-    YG_CUDA(cudaMemcpy(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
     YG_CUDA(cudaMalloc(&plan.d_twid, tw.size() * sizeof(float2)));
-    YG_CUDA(cudaMemcpy(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    YG_CUDA(yg::memcpy_sync(plan.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     plan.supported = true;
     return YG_OK;
 }

@@ -30,6 +30,9 @@ class FirFilt:
         _lib.check(_lib.lib().yg_firfilt_crcf_get_len(self._q, C.byref(n)))
         self._h_len = n.value
         self._S = None
+        d = C.c_int32()
+        _lib.check(_lib.lib().yg_firfilt_crcf_get_device(self._q, C.byref(d)))
+        self._dev = d.value
 
     @classmethod
     def new(cls, h, n_streams: int = 1) -> "FirFilt":
@@ -78,12 +81,16 @@ class FirFilt:
     def len(self) -> int:
         return self._h_len
 
+    def get_device(self) -> int:
+        return self._dev
+
     def execute_block(self, x, out=None):
         """x[stream][n] -> y[stream][n] (`execute_block(&mut self, x, y)`, firfilt.rs:267-278)."""
         L = _lib.lib()
         if B.is_torch_cuda(x):
             n = _frames(x.numel(), self._S)
             x = B.dev_in(x, n * self._S, "input")
+            B.check_device(x, self._dev)
             y = B.dev_out(out, n * self._S, x)
             _lib.check(L.yg_firfilt_crcf_execute_block_dev(self._q, C.c_void_p(x.data_ptr()), n, C.c_void_p(y.data_ptr()), B.cur_stream(x)))
             return y

@@ -31,6 +31,25 @@ def all_gather_frames(y_local, n_frames_per_rank, M: int, group=None):
     return torch.cat(parts, dim=0)
 
 
-def channel_major(y_frames):
-    """[frames][M] -> [M][frames]: one contiguous time series per channel."""
-    return y_frames.transpose(0, 1).contiguous()
+def channel_major(y_frames, out=None):
+    """[frames][M] -> [M][frames]: one contiguous time series per channel (tiled transpose kernel of
+    libyagi_b200.so, asynchronous on torch's current stream; CPU tensors -- the gloo tests -- are transposed by torch)."""
+    import ctypes as C
+
+    import torch
+
+    from . import _buffers as B
+    from . import _lib
+    K, M = y_frames.shape
+    if not y_frames.is_cuda:
+        return y_frames.transpose(0, 1).contiguous()
+    if y_frames.dtype != torch.complex64 or not y_frames.is_contiguous():
+        raise B.ValueError_("y_frames must be a contiguous complex64 [frames][M] tensor")
+    if out is None:
+        out = torch.empty(M, K, dtype=torch.complex64, device=y_frames.device)
+    elif out.shape != (M, K) or out.dtype != torch.complex64 or not out.is_contiguous() or out.device != y_frames.device:
+        raise B.ValueError_("out must be a contiguous complex64 [M][frames] tensor on the same device")
+    with torch.cuda.device(y_frames.device):
+        _lib.check(_lib.lib().yg_channel_major_dev(C.c_void_p(y_frames.data_ptr()), K, M, C.c_void_p(out.data_ptr()),
+                                                   B.cur_stream(y_frames)))
+    return out

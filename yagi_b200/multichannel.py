@@ -45,6 +45,9 @@ class FirPfbCh2:
         _lib.check(L.yg_firpfbch2_crcf_get_M(self._q, C.byref(M)))
         _lib.check(L.yg_firpfbch2_crcf_get_m(self._q, C.byref(m)))
         self._type, self._M, self._m = FirPfbChType(t.value), M.value, m.value
+        d = C.c_int32()
+        _lib.check(L.yg_firpfbch2_crcf_get_device(self._q, C.byref(d)))
+        self._dev = d.value
 
     # -- constructors ------------------------------------------------------------
     @classmethod
@@ -132,6 +135,7 @@ class FirPfbCh2:
             if n is None:
                 n = _frames(x.numel(), nin)
             x = B.dev_in(x, n * nin, "input")
+            B.check_device(x, self._dev)
             y = B.dev_out(out, n * nout, x)
             _lib.check(L.yg_firpfbch2_crcf_execute_block_dev(self._q, C.c_void_p(x.data_ptr()), n, C.c_void_p(y.data_ptr()), B.cur_stream(x)))
             return y
@@ -147,6 +151,14 @@ class FirPfbCh2:
         p = C.c_int32()
         _lib.check(_lib.lib().yg_firpfbch2_crcf_last_path(self._q, C.byref(p)))
         return p.value
+
+    def get_device(self) -> int:
+        """Index of the CUDA device this object is bound to (the device current at construction)."""
+        return self._dev
+
+    def set_kernel_timing(self, enable: bool) -> None:
+        """Turn the two CUDA events recorded around the dominant kernel of each call off / on (default on)."""
+        _lib.check(_lib.lib().yg_firpfbch2_crcf_set_kernel_timing(self._q, 1 if enable else 0))
 
     def last_kernel_ms(self) -> float:
         ms = C.c_float()
@@ -178,6 +190,9 @@ class FirPfbCh:
         _lib.check(L.yg_firpfbch_crcf_get_p(self._q, C.byref(p)))
         _lib.check(L.yg_firpfbch_crcf_get_n_streams(self._q, C.byref(s)))
         self._type, self._M, self._p, self._S = FirPfbChType(t.value), M.value, p.value, s.value
+        d = C.c_int32()
+        _lib.check(L.yg_firpfbch_crcf_get_device(self._q, C.byref(d)))
+        self._dev = d.value
 
     @classmethod
     def new(cls, type_, num_channels: int, p: int, h, n_streams: int = 1) -> "FirPfbCh":
@@ -224,6 +239,9 @@ class FirPfbCh:
     def get_n_streams(self) -> int:
         return self._S
 
+    def get_device(self) -> int:
+        return self._dev
+
     def get_taps(self) -> np.ndarray:
         h = np.empty(self._M * self._p, dtype=np.float32)
         _lib.check(_lib.lib().yg_firpfbch_crcf_get_taps(self._q, B.ptr(h)))
@@ -242,6 +260,7 @@ class FirPfbCh:
             if n is None:
                 n = _frames(x.numel(), per)
             x = B.dev_in(x, n * per, "input")
+            B.check_device(x, self._dev)
             y = B.dev_out(out, n * per, x)
             _lib.check(L.yg_firpfbch_crcf_execute_block_dev(self._q, C.c_void_p(x.data_ptr()), n, C.c_void_p(y.data_ptr()), B.cur_stream(x)))
             return y
