@@ -124,7 +124,7 @@ def test_synthesis_dft_stage_against_numpy_fft_f64(M):
         y[k M/2 + i] = sum_{l < 4m} h[i + l M/2] u_{k-l}[(i + pi_k) mod M],  u_k = 1/2 IDFT_unnorm(X_k), pi_k = (k&1) M/2
     evaluated in f64 with numpy.fft for random X and a random prototype."""
     rng = np.random.default_rng(100 + M)
-    m, K = 2, 160
+    m, K = 2, 512                    # whole 32-frame rounds, above every fused kernel's minimum call size
     h = rng.standard_normal(2 * M * m).astype(np.float32)
     X = _rand_c(rng, K * M).reshape(K, M)
     q = yb.FirPfbCh2.new(S, M, m, h)
@@ -193,7 +193,7 @@ def test_firpfbch2_analysis_equals_mix_filter_decimate_on_cuda():
     """The same oracle-independent identity for the 2x oversampled object:
     y_k[c] = ((-1)^{c k} / M) sum_tau h[tau] e^{+j 2 pi c tau / M} s[t_k - tau], t_k = (k+1) M/2 - 1,
     evaluated in f64 for a random prototype, through the fused kernels."""
-    for M, m, K in ((16, 3, 96), (64, 2, 128), (256, 2, 128)):
+    for M, m, K in ((16, 3, 2304), (64, 2, 512), (256, 2, 128)):      # K above each fused kernel's minimum call size
         rng = np.random.default_rng(M + m)
         h = rng.standard_normal(2 * M * m).astype(np.float32)
         x = _rand_c(rng, K * M // 2)

@@ -91,29 +91,54 @@ struct DevBuf {
 
 // Keeps a handle's state updates ordered when consecutive calls use different streams
 // (e.g. a device-pointer call on the caller's stream followed by a host-pointer call).
+// After a call on a stream that outlives the handle's use of it (the default streams, the handle's own stream:
+// `own`) nothing is recorded -- an event record between two launches would keep them from overlapping under
+// programmatic dependent launch -- and the event is recorded on that stream later, if and when a call arrives on a
+// different one.  After a call on a caller-created stream, which may be destroyed at any time, it is recorded at once.
 struct StreamOrder {
     cudaEvent_t ev = nullptr;
     cudaStream_t last = nullptr;
+    cudaStream_t own = nullptr;
     bool armed = false;
+    bool pending = false;          // work on `last` since the last record
+    bool permanent(cudaStream_t st) const
+    {
+        return st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread || st == own;
+    }
+    int32_t flush()
+    {
+        if (pending) {
+            if (!ev) YG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            YG_CUDA(cudaEventRecord(ev, last));
+            pending = false;
+        }
+        return YG_OK;
+    }
     int32_t enter(cudaStream_t st)
     {
-        if (armed && st != last) YG_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        if (armed && st != last) {
+            YG_TRY(flush());
+            YG_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        }
         return YG_OK;
     }
     int32_t leave(cudaStream_t st)
     {
-        if (!ev) YG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        YG_CUDA(cudaEventRecord(ev, st));
         last = st;
         armed = true;
+        pending = true;
+        if (!permanent(st)) YG_TRY(flush());
         return YG_OK;
     }
     int32_t wait_host()
     {
-        if (armed) YG_CUDA(cudaEventSynchronize(ev));
+        if (armed) {
+            YG_TRY(flush());
+            YG_CUDA(cudaEventSynchronize(ev));
+        }
         return YG_OK;
     }
-    void destroy() { if (ev) cudaEventDestroy(ev); ev = nullptr; armed = false; }
+    void destroy() { if (ev) cudaEventDestroy(ev); ev = nullptr; armed = false; pending = false; }
 };
 
 // Three-stream chunked host<->device pipeline used by the host-pointer entry points:

@@ -153,6 +153,7 @@ int32_t build(const float* h, size_t h_len, uint32_t n_streams, yg_firfilt_crcf*
 #define TRYQ(expr) do { int32_t _rc = (expr); if (_rc != YG_OK) return cleanup(_rc); } while (0)
 #define CUDAQ(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return cleanup(fail(YG_EINTERNAL, "CUDA error %s (%s)", cudaGetErrorString(_e), #expr)); } while (0)
     CUDAQ(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+    q->order.own = q->stream;
     TRYQ(q->d_h.reserve(h_len));
     CUDAQ(yg::memcpy_sync(q->d_h.p, q->h.data(), h_len * sizeof(float), cudaMemcpyHostToDevice));
     q->state_len = h_len - 1;

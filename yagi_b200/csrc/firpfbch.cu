@@ -259,6 +259,7 @@ int32_t build(int32_t type, uint32_t M, uint32_t p, const float* h, size_t h_len
 #define TRYQ(expr) do { int32_t _rc = (expr); if (_rc != YG_OK) return cleanup(_rc); } while (0)
 #define CUDAQ(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return cleanup(fail(YG_EINTERNAL, "CUDA error %s (%s)", cudaGetErrorString(_e), #expr)); } while (0)
     CUDAQ(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+    q->order.own = q->stream;
     TRYQ(q->d_h.reserve(L));
     CUDAQ(yg::memcpy_sync(q->d_h.p, q->h.data(), L * sizeof(float), cudaMemcpyHostToDevice));
     std::vector<float2> tw;

@@ -462,6 +462,7 @@ int32_t build(int32_t type, uint32_t M, uint32_t m, const float* h, size_t h_len
 #define TRYQ(expr) do { int32_t _rc = (expr); if (_rc != YG_OK) return cleanup(_rc); } while (0)
 #define CUDAQ(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return cleanup(fail(YG_EINTERNAL, "CUDA error %s (%s)", cudaGetErrorString(_e), #expr)); } while (0)
     CUDAQ(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+    q->order.own = q->stream;
     for (int i = 0; i < yg_firpfbch2_crcf_s::kRing; i++) {
         CUDAQ(cudaEventCreate(&q->ev0s[i]));
         CUDAQ(cudaEventCreate(&q->ev1s[i]));

@@ -76,6 +76,7 @@ __device__ __forceinline__ void fir_role(const FastParams& p, uint32_t smem, uin
     float2 T[kTaps];
 #pragma unroll
     for (int i = 0; i < kTaps; i++) T[i] = __ldg(&p.taps[j * kTaps + i]);
+    pdl_wait();                          // the input stream and the history may come from the previous kernel
 
     // register ring of 32 samples: slot (q mod 32) holds u_j[q]
     float2 W[32];
@@ -171,6 +172,15 @@ __device__ __forceinline__ void fft_role(const FastParams& p, uint32_t smem, uin
         twr[k] = w.x;
         twi[k] = w.y;
     }
+    pdl_wait();                          // nothing is written before the previous kernel in the stream has completed
+    // State hand-off folded into this launch: the FFT-role threads of the last CTA have nothing to do until the
+    // first V regions are written, so they copy the tail of the input stream into the other history buffer.
+    if (p.hist_new != nullptr && blockIdx.x == gridDim.x - 1) {
+        for (long long i = tid; i < p.Hlen; i += kFftThreads) {
+            const long long ts = p.n_new - p.Hlen + i;
+            p.hist_new[i] = (ts >= 0) ? __ldg(&p.x[ts]) : __ldg(&p.hist[p.Hlen + ts]);
+        }
+    }
 
     for (long long batch = batch_begin; batch < batch_end; batch++) {
         const int b = (int)((batch - batch_begin) & 1);
@@ -241,15 +251,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_firpfbch2_analysis_fused(const 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    // State hand-off folded into this launch: the FFT-role threads of the last CTA have nothing to do until
-    // the first V regions are written, so they copy the tail of the input stream into the other history buffer.
-    if (p.hist_new != nullptr && blockIdx.x == gridDim.x - 1 && threadIdx.x >= kFirThreads) {
-        for (long long i = threadIdx.x - kFirThreads; i < p.Hlen; i += kFftThreads) {
-            const long long t = p.n_new - p.Hlen + i;
-            p.hist_new[i] = (t >= 0) ? __ldg(&p.x[t]) : __ldg(&p.hist[p.Hlen + t]);
-        }
-    }
-    if (batch_begin >= batch_end) return;
+    pdl_launch_dependents();             // the next kernel in the stream may start its prologue as SMs free up
+    if (batch_begin >= batch_end) return;       // never taken: the grid has at most one CTA per batch
 
     if (threadIdx.x < kFirThreads) fir_role<kTaps>(p, smem, mbar, batch_begin, batch_end);
     else fft_role(p, smem, mbar, batch_begin, batch_end);
@@ -262,8 +265,19 @@ int32_t launch_t(const Firpfbch2FastPlan& plan, const FastParams& p, cudaStream_
     YG_CUDA(cudaFuncSetAttribute(k_firpfbch2_analysis_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     const long long n_batches = (p.n_pairs + kPairsPerBatch - 1) / kPairsPerBatch;
     const int grid = (int)std::min<long long>(plan.n_sm, n_batches);
-    k_firpfbch2_analysis_fused<kTaps><<<grid, kThreads, kSmemBytes, st>>>(p);
-    YG_LAUNCH_CHECK();
+    // programmatic dependent launch: back-to-back calls overlap this kernel's prologue with the previous one's tail
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = plan.pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    YG_CUDA(cudaLaunchKernelEx(&cfg, k_firpfbch2_analysis_fused<kTaps>, p));
+    count_launch();
     return YG_OK;
 }
 
@@ -314,6 +328,8 @@ int32_t firpfbch2_fast_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const 
     YG_CUDA(yg::memcpy_sync(p.d_twid, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     p.min_frames = 64;
     p.supported = true;
+    const char* e = getenv("YG_PDL");     // debugging knob: YG_PDL=0 launches with full stream serialization
+    p.pdl = !(e && e[0] == '0');
     return YG_OK;
 }
 

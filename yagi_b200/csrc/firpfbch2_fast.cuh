@@ -11,6 +11,7 @@ struct Firpfbch2FastPlan {
     void* d_taps = nullptr;       // kernel-specific tap layout (device)
     void* d_twid = nullptr;       // kernel-specific twiddle layout (device)
     int n_sm = 0;
+    bool pdl = true;              // launch with programmatic stream serialization (fused M=256 analysis)
     void* d_scratch = nullptr;    // large-M fused analysis: per-group V ring (device)
     void* d_flags = nullptr;      //   and its counters
     int n_groups = 0;             //   0: fused large-M kernel not available

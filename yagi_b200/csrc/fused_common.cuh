@@ -44,6 +44,15 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still draining; pdl_wait() blocks until that predecessor has completed
+// and its writes are visible (a no-op for a normally launched kernel), pdl_launch_dependents() lets the successor's
+// CTAs be scheduled as soon as SMs free up.  Rule used here: nothing the caller could have produced with the
+// previous kernel (x, the history) is read, and nothing is written, before pdl_wait(); only the prologue (barrier
+// initialisation, plan-time tables -> registers) runs ahead.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // explicit shared-space accesses on 32-bit shared addresses (keeps them LDS/STS, never generic LD/ST)
 __device__ __forceinline__ float2 lds64(uint32_t a)
 {
