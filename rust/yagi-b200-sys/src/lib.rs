@@ -93,6 +93,7 @@ extern "C" {
     pub fn yg_firfilt_crcf_get_scale(q: yg_firfilt_crcf, scale: *mut f32) -> i32;
     pub fn yg_firfilt_crcf_get_len(q: yg_firfilt_crcf, h_len: *mut size_t) -> i32;
     pub fn yg_firfilt_crcf_get_device(q: yg_firfilt_crcf, dev: *mut i32) -> i32;
+    pub fn yg_firfilt_crcf_last_path(q: yg_firfilt_crcf, path: *mut i32) -> i32;
     pub fn yg_firfilt_crcf_execute_block(q: yg_firfilt_crcf, x: *const yg_cf32, n: size_t, y: *mut yg_cf32) -> i32;
     pub fn yg_firfilt_crcf_execute_block_dev(q: yg_firfilt_crcf, d_x: *const yg_cf32, n: size_t, d_y: *mut yg_cf32, cuda_stream: *mut c_void) -> i32;
     pub fn yg_firfilt_crcf_sync(q: yg_firfilt_crcf) -> i32;

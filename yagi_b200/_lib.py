@@ -27,7 +27,7 @@ yg_firpfbch_crcf_sync yg_firpfbch_crcf_get_type yg_firpfbch_crcf_get_M yg_firpfb
 yg_firpfbch_crcf_get_n_streams yg_firpfbch_crcf_get_taps yg_firpfbch_crcf_last_path yg_firpfbch_crcf_get_device
 yg_firfilt_crcf_create yg_firfilt_crcf_create_kaiser yg_firfilt_crcf_clone yg_firfilt_crcf_destroy
 yg_firfilt_crcf_reset yg_firfilt_crcf_set_scale yg_firfilt_crcf_get_scale yg_firfilt_crcf_get_len
-yg_firfilt_crcf_execute_block yg_firfilt_crcf_execute_block_dev yg_firfilt_crcf_sync yg_firfilt_crcf_get_device
+yg_firfilt_crcf_execute_block yg_firfilt_crcf_execute_block_dev yg_firfilt_crcf_sync yg_firfilt_crcf_get_device yg_firfilt_crcf_last_path
 """.split()
 
 
@@ -71,7 +71,7 @@ def lib() -> C.CDLL:
     L.yg_firpfbch2_crcf_set_state.argtypes = [vp, vp, i32]
     L.yg_firpfbch2_crcf_kernel_times.argtypes = [vp, vp, sz, vp]
     L.yg_firpfbch2_crcf_set_kernel_timing.argtypes = [vp, i32]
-    for n in ("yg_firpfbch2_crcf_get_device", "yg_firpfbch_crcf_get_device", "yg_firfilt_crcf_get_device"):
+    for n in ("yg_firpfbch2_crcf_get_device", "yg_firpfbch_crcf_get_device", "yg_firfilt_crcf_get_device", "yg_firfilt_crcf_last_path"):
         getattr(L, n).argtypes = [vp, vp]
     # firpfbch
     L.yg_firpfbch_crcf_create.argtypes = [i32, u32, u32, vp, sz, u32, vp]

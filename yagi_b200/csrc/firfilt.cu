@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 using namespace yg;
 
@@ -11,6 +12,11 @@ namespace yg {
 bool firfilt_fast_supported(size_t h_len);
 int32_t firfilt_fast_launch(const float* h, size_t h_len, float scale, const float2* hist, long long Hlen, const float2* x,
                             float2* y, long long n, long long n_streams, cudaStream_t st);
+// firfilt_tc.cu: tensor-core (tcgen05, 3xTF32 banded Toeplitz) path for <= 65 taps
+bool firfilt_tc_supported(size_t h_len, long long n, long long n_streams, const void* x, const void* y);
+int32_t firfilt_tc_plan(const float* h, size_t h_len, float** d_toep);
+int32_t firfilt_tc_launch(const float* d_toep, float scale, const float2* hist, long long Hlen, const float2* x, float2* y,
+                          long long n, long long n_streams, int n_sm, cudaStream_t st);
 }  // namespace yg
 
 struct yg_firfilt_crcf_s {
@@ -27,11 +33,15 @@ struct yg_firfilt_crcf_s {
     DevBuf<yg_cf32> d_hist[2];
     int cur = 0;
     DevBuf<yg_cf32> d_stage_x, d_stage_y;
+    float* d_toep = nullptr;       // tensor-core path: aliased Toeplitz tables (null: path not planned)
+    int tc_mode = 0;               // 0 never, 1 whenever the geometry allows (YG_FIRFILT_TC)
+    int32_t last_path = 0;         // 0 none, 1 generic, 2 register-blocked FFMA2, 4 tensor cores
 };
 
 namespace {
 
 constexpr int kOutPerThread = 8;
+constexpr int kFirfiltTcDefault = 0;     // see DESIGN.md (K5): off until the A/B says otherwise
 
 // Each thread produces kOutPerThread consecutive outputs of one stream.  Taps are staged in shared
 // memory, zero-padded by kOutPerThread-1 on both sides so the inner loop needs no bounds test.
@@ -109,10 +119,16 @@ int32_t execute_dev_impl(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf3
     if (n == 0) return YG_OK;
     const long long S = q->n_streams;
     const long long Hlen = (long long)q->state_len;
-    if (firfilt_fast_supported(q->h_len) && (long long)n * S >= 4096) {
+    if (q->tc_mode && q->d_toep && firfilt_tc_supported(q->h_len, (long long)n, S, d_x, d_y)) {
+        // tcgen05 3xTF32 Toeplitz GEMM (<= 65 taps, whole calls of aligned, even-length streams)
+        YG_TRY(firfilt_tc_launch(q->d_toep, q->scale, reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
+                                 reinterpret_cast<const float2*>(d_x), reinterpret_cast<float2*>(d_y), (long long)n, S, q->n_sm, st));
+        q->last_path = 4;
+    } else if (firfilt_fast_supported(q->h_len) && (long long)n * S >= 4096) {
         // register-blocked FFMA2 kernel (taps as kernel parameters); generic kernel for long filters / tiny calls
         YG_TRY(firfilt_fast_launch(q->h.data(), q->h_len, q->scale, reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
                                    reinterpret_cast<const float2*>(d_x), reinterpret_cast<float2*>(d_y), (long long)n, S, st));
+        q->last_path = 2;
     } else {
         const long long tiles = ((long long)n + kOutPerThread - 1) / kOutPerThread;
         const int grid = (int)std::min<long long>((tiles * S + 127) / 128, q->n_sm * 32);
@@ -122,8 +138,9 @@ int32_t execute_dev_impl(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf3
                                            reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
                                            reinterpret_cast<const float2*>(d_x), reinterpret_cast<float2*>(d_y),
                                            (long long)n, S);
+        q->last_path = 1;
+        YG_LAUNCH_CHECK();
     }
-    YG_LAUNCH_CHECK();
     if (Hlen > 0) {
         const int nxt = q->cur ^ 1;
         const int g2 = (int)std::min<long long>((Hlen * S + 255) / 256, q->n_sm * 8);
@@ -161,6 +178,14 @@ int32_t build(const float* h, size_t h_len, uint32_t n_streams, yg_firfilt_crcf*
         const size_t n = std::max<size_t>(1, q->state_len * n_streams);
         TRYQ(q->d_hist[b].reserve(n));
         CUDAQ(yg::memset_sync(q->d_hist[b].p, 0, n * sizeof(yg_cf32)));
+    }
+    {   // tensor-core path (firfilt_tc.cu): measured slower or faster than the FFMA2 kernel depending on the tap count;
+        // YG_FIRFILT_TC=1 / 0 forces it on / off, the default is set from the measurements in DESIGN.md
+        const char* e = getenv("YG_FIRFILT_TC");
+        q->tc_mode = e ? (e[0] != '0') : kFirfiltTcDefault;
+        cudaDeviceProp prop;
+        CUDAQ(cudaGetDeviceProperties(&prop, dev));
+        if (q->tc_mode && h_len <= 65 && prop.major == 10) TRYQ(firfilt_tc_plan(q->h.data(), h_len, &q->d_toep));
     }
 #undef TRYQ
 #undef CUDAQ
@@ -214,6 +239,7 @@ int32_t yg_firfilt_crcf_destroy(yg_firfilt_crcf q)
     q->order.destroy();
     q->d_h.release(); q->d_hist[0].release(); q->d_hist[1].release();
     q->d_stage_x.release(); q->d_stage_y.release();
+    if (q->d_toep) cudaFree(q->d_toep);
     if (q->stream) cudaStreamDestroy(q->stream);
     delete q;
     return YG_OK;
@@ -233,6 +259,7 @@ int32_t yg_firfilt_crcf_reset(yg_firfilt_crcf q)
 
 int32_t yg_firfilt_crcf_set_scale(yg_firfilt_crcf q, float scale) { YG_TRY(check(q)); q->scale = scale; return YG_OK; }
 int32_t yg_firfilt_crcf_get_scale(yg_firfilt_crcf q, float* scale) { YG_TRY(check(q)); *scale = q->scale; return YG_OK; }
+int32_t yg_firfilt_crcf_last_path(yg_firfilt_crcf q, int32_t* path) { YG_TRY(check(q)); *path = q->last_path; return YG_OK; }
 int32_t yg_firfilt_crcf_get_device(yg_firfilt_crcf q, int32_t* dev) { YG_TRY(check(q)); *dev = q->dev; return YG_OK; }
 int32_t yg_firfilt_crcf_get_len(yg_firfilt_crcf q, size_t* h_len) { YG_TRY(check(q)); *h_len = q->h_len; return YG_OK; }
 

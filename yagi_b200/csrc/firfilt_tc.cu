@@ -1,0 +1,442 @@
+// firfilt_tc.cu -- batched firfilt_crcf (<= 65 taps) on the 5th-generation tensor cores: 3xTF32 banded-Toeplitz GEMM.
+//
+//   y[s][n] = scale * sum_k h[k] x[s][n-k]                 (src/filter/fir/firfilt.rs:241-245, :267-278)
+//
+// Why: at 63 taps the CUDA-core kernel (firfilt_fast.cu) is FP32-pipe bound -- 126 lane-FMAs per 16 bytes moved, a
+// ceiling of ~0.70 of the HBM roofline -- so the only way up is to take the multiply-adds off the FMA pipe.
+//
+// Formulation (per CTA, M = 128 rows, N = 64 outputs, K = 128 inputs per tile):
+//   rows    : 64 streams x {re, im}                -> the A operand, which lives in TENSOR MEMORY (lane = row);
+//   columns : 64 consecutive output times of a tile, stored reversed (column n' <-> time 63 - n');
+//   K       : the 128 input times [64 tau - 64, 64 tau + 64) = the previous and the current 64-sample block;
+//   B[k][n']: h[127 - (n' + k)] (zero outside 0 .. h_len-1): a Toeplitz band.  Because it depends on n' + k only,
+//             the 8 x 16-byte core matrices of the K-major no-swizzle shared-memory layout at (n'-group I, k-chunk J)
+//             are all the same function of 2I + J: with SBO = 256 B and LBO = 128 B every descriptor of every K step
+//             aliases ONE 5.9 KB table instead of a 32 KB operand per step -- the band never has to be materialised.
+//   3xTF32  : x = x_hi + x_lo, h = h_hi + h_lo (hi = round-to-nearest TF32, lo = exact f32 remainder); the tile is
+//             D = A_hi B_hi + A_lo B_hi + A_hi B_lo accumulated in f32 in TMEM (the dropped lo*lo term and the TF32
+//             truncation of the lo parts are ~2^-22 relative): 48 tcgen05.mma (128 x 64 x 8, kind::tf32) per tile.
+//
+// Pipeline (one persistent CTA per SM, 320 threads, all 512 TMEM columns):
+//   warp 8  TMA producer : cp.async.bulk.tensor 2-D boxes {16 samples, 64 streams} x 4 per 64-sample block into a
+//                          4-stage shared ring, 128-byte swizzle; out-of-range boxes (before the stream start, past
+//                          its end, past the last stream) are zero-filled / clipped by the hardware.
+//   warps 0-3 converter  : thread = row: reads its 64 samples of the block (conflict-free LDS.128 through the swizzle),
+//                          splits them into TF32 hi / lo and writes them to its TMEM lane with tcgen05.st, into a ring
+//                          of three 64-column blocks (hi) + three (lo).
+//   warp 9  MMA issuer   : one thread issues the 48 MMAs of a tile (A from TMEM, B descriptors into the aliased
+//                          table) into one of two 64-column accumulators; tcgen05.commit signals the epilogue and
+//                          hands the oldest A block back to the converter.
+//   warps 4-7 epilogue   : tcgen05.ld the accumulator, scale, write the tile to a swizzled staging buffer and store
+//                          it with cp.async.bulk.tensor (shared -> global).
+// A CTA walks a contiguous range of (stream group, block) items; every run inside a group starts with one priming
+// block (the 64 samples before it: the previous block, or the object's history for the first block of a call).
+#include "common.cuh"
+#include "fused_common.cuh"
+
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace yg {
+
+namespace {
+
+using namespace yg::dev;
+
+constexpr int kBlk = 64;                      // samples per block = outputs per tile (N)
+constexpr int kRows = 128;                    // 64 streams x {re, im} (M)
+constexpr int kStreamsPerGroup = 64;
+constexpr int kStages = 4;                    // input ring
+constexpr int kStageBytes = kBlk * kStreamsPerGroup * 8;      // 32 KB
+constexpr int kSubBytes = kStageBytes / 4;                    // one TMA box: 16 samples x 64 streams
+constexpr int kToepBytes = 23 * 256;                          // aliased Toeplitz table (one of hi / lo)
+constexpr int kThreads = 320;
+constexpr int kSmemIn = 0;
+constexpr int kSmemOut = kSmemIn + kStages * kStageBytes;     // 2 staging buffers
+constexpr int kSmemToep = kSmemOut + 2 * kStageBytes;         // hi table, lo table
+constexpr int kSmemBar = kSmemToep + 2 * kToepBytes;
+constexpr int kSmemBytes = kSmemBar + 256 + 1024;             // + alignment slack
+// mbarrier slots
+constexpr int kBarInFull = 0;                 // [4]
+constexpr int kBarInEmpty = 4;                // [4]
+constexpr int kBarAFull = 8;                  // [3]
+constexpr int kBarAFree = 11;                 // [3]
+constexpr int kBarDFull = 14;                 // [2]
+constexpr int kBarDEmpty = 16;                // [2]
+constexpr int kNumBars = 18;
+// TMEM columns
+constexpr uint32_t kColHi = 0, kColLo = 192, kColD = 384;
+
+struct TcParams {
+    const float2* hist;       // [n_streams][Hlen], oldest first (the object's state), or null
+    int Hlen;
+    long long n;              // samples per stream in this call
+    int n_streams;
+    float scale;
+    const float* toep;        // [2][kToepBytes / 4]: hi table, lo table
+    long long n_blocks;       // ceil(n / 64)
+    int n_groups;             // ceil(n_streams / 64)
+};
+
+// ---- tcgen05 / TMA wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor], 128 x 64 x 8, TF32 inputs, f32 accumulate
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+
+#define YG_R8(v, o) "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
+#define YG_W8(v, o) "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
+// 32 consecutive columns of this thread's TMEM lane  <->  32 registers
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), YG_R8(v, 0), YG_R8(v, 8), YG_R8(v, 16), YG_R8(v, 24) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : YG_W8(v, 0), YG_W8(v, 8), YG_W8(v, 16), YG_W8(v, 24) : "r"(taddr) : "memory");
+}
+#undef YG_R8
+#undef YG_W8
+
+// K-major, no-swizzle shared-memory matrix descriptor: 8 x 16-byte core matrices, LBO = stride between the two
+// 16-byte K chunks of an instruction, SBO = stride between 8-row groups (cute::UMMA::SmemDescriptor bit layout).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);                      // descriptor version 1 (sm_100); base offset 0, layout type 0 = no swizzle
+}
+// kind::tf32, f32 accumulate, A and B K-major, N = 64, M = 128 (cute::UMMA::InstrDescriptor bit layout)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBlk >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+
+// The walk every role performs: the CTA's items [e0, e1) of the (group, block) grid, cut into runs inside one group;
+// a run starts with a priming step for the block before it.  step(group, block, prime) is called in the same order by
+// every role, so running counters (blocks converted, tiles produced) agree across roles.
+template <typename Step>
+__device__ __forceinline__ void walk(long long e0, long long e1, long long n_blocks, Step&& step)
+{
+    long long e = e0;
+    while (e < e1) {
+        const int g = (int)(e / n_blocks);
+        long long b = e - (long long)g * n_blocks;
+        const long long run_end = (e1 < (long long)(g + 1) * n_blocks) ? e1 : (long long)(g + 1) * n_blocks;
+        step(g, b - 1, true);
+        for (; e < run_end; e++, b++) step(g, b, false);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constant__ CUtensorMap tm_in,
+                                                             const __grid_constant__ CUtensorMap tm_out, const TcParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;             // the 128-byte swizzle wants 1024-byte alignment
+    unsigned char* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
+    const uint32_t bar0 = smem + kSmemBar;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kSmemBar + 8 * kNumBars);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const long long total = (long long)p.n_groups * p.n_blocks;
+    const long long e0 = total * blockIdx.x / gridDim.x, e1 = total * (blockIdx.x + 1) / gridDim.x;
+
+    // ---- one-time setup
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; i++) { mbar_init(bar0 + 8 * (kBarInFull + i), 1); mbar_init(bar0 + 8 * (kBarInEmpty + i), 4); }
+        for (int i = 0; i < 3; i++) { mbar_init(bar0 + 8 * (kBarAFull + i), 4); mbar_init(bar0 + 8 * (kBarAFree + i), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(bar0 + 8 * (kBarDFull + i), 1); mbar_init(bar0 + 8 * (kBarDEmpty + i), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {   // Toeplitz tables (hi, lo) -> shared memory; the tensor core reads them through the async proxy
+        float* dst = reinterpret_cast<float*>(smem_gen + kSmemToep);
+        for (int i = threadIdx.x; i < 2 * kToepBytes / 4; i += kThreads) dst[i] = __ldg(&p.toep[i]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ================================================================= TMA producer
+        if (lane == 0) {
+            long long k = 0;
+            walk(e0, e1, p.n_blocks, [&](int g, long long b, bool) {
+                const int st = (int)(k % kStages);
+                if (k >= kStages) mbar_wait(bar0 + 8 * (kBarInEmpty + st), (uint32_t)(((k / kStages) - 1) & 1));
+                const uint32_t full = bar0 + 8 * (kBarInFull + st);
+                mbar_expect_tx(full, kStageBytes);
+                const uint32_t dst = smem + kSmemIn + st * kStageBytes;
+#pragma unroll
+                for (int j = 0; j < 4; j++)      // coordinates: (float index inside the stream, stream); negative = before the start
+                    tma_load_2d(dst + j * kSubBytes, &tm_in, (int)(32 * (4 * b + j)), g * kStreamsPerGroup, full);
+                k++;
+            });
+        }
+    } else if (warp == 9) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            long long k = 0, u = 0;
+            const uint32_t toep_hi = smem + kSmemToep, toep_lo = toep_hi + kToepBytes;
+            walk(e0, e1, p.n_blocks, [&](int, long long, bool prime) {
+                const int slot = (int)(k % 3);
+                mbar_wait(bar0 + 8 * (kBarAFull + slot), (uint32_t)((k / 3) & 1));
+                tc_fence_after();
+                if (!prime) {
+                    const int db = (int)(u & 1);
+                    if (u >= 2) { mbar_wait(bar0 + 8 * (kBarDEmpty + db), (uint32_t)(((u >> 1) - 1) & 1)); tc_fence_after(); }
+                    const uint32_t d = tmem + kColD + kBlk * db;
+                    const int prev = (slot + 2) % 3;
+#pragma unroll
+                    for (int s = 0; s < 16; s++) {
+                        const uint32_t col = (s < 8) ? (uint32_t)(kBlk * prev + 8 * s) : (uint32_t)(kBlk * slot + 8 * (s - 8));
+                        const uint64_t bh = smem_desc(toep_hi + 256 * s, 128, 256), bl = smem_desc(toep_lo + 256 * s, 128, 256);
+                        tc_mma_ts(d, tmem + kColLo + col, bh, kIdesc, s > 0 ? 1u : 0u);      // small terms first
+                        tc_mma_ts(d, tmem + kColHi + col, bl, kIdesc, 1u);
+                        tc_mma_ts(d, tmem + kColHi + col, bh, kIdesc, 1u);
+                    }
+                    tc_commit(bar0 + 8 * (kBarDFull + db));
+                    u++;
+                }
+                if (k >= 1) tc_commit(bar0 + 8 * (kBarAFree + (int)((k - 1) % 3)));     // the block before this one is no longer read
+                k++;
+            });
+        }
+    } else if (warp < 4) {
+        // ================================================================= converter: thread = row (stream, component)
+        const int row = threadIdx.x;
+        const int sl = row >> 1, c = row & 1;                   // stream inside the group, component
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        // byte offset of this stream's 128-byte row inside a box; chunk u of the row sits at ((u ^ (sl & 7)) << 4)
+        const uint32_t row_off = (uint32_t)sl * 128u;
+        long long k = 0;
+        walk(e0, e1, p.n_blocks, [&](int g, long long b, bool) {
+            const int st = (int)(k % kStages);
+            const int slot = (int)(k % 3);
+            mbar_wait(bar0 + 8 * (kBarInFull + st), (uint32_t)((k / kStages) & 1));
+            if (k >= 3) { mbar_wait(bar0 + 8 * (kBarAFree + slot), (uint32_t)(((k / 3) - 1) & 1)); tc_fence_after(); }
+            const uint32_t src = smem + kSmemIn + st * kStageBytes + row_off;
+            const long long s_glob = (long long)g * kStreamsPerGroup + sl;
+            const bool from_hist = (b < 0) && p.hist != nullptr && s_glob < p.n_streams;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                uint32_t hi[32], lo[32];
+                if (!from_hist) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {               // 16-byte chunk = 2 samples (re0, im0, re1, im1)
+                        const int t = 32 * half + 2 * q;         // first sample of the chunk inside the block
+                        const uint32_t a = src + (uint32_t)(t >> 4) * kSubBytes + ((uint32_t)(((t & 15) >> 1) ^ (sl & 7)) << 4);
+                        const float4 v = lds128(a);
+                        const float v0 = c ? v.y : v.x, v1 = c ? v.w : v.z;
+                        uint32_t h0, h1;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0) : "f"(v0));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h1) : "f"(v1));
+                        hi[2 * q] = h0; hi[2 * q + 1] = h1;
+                        lo[2 * q] = __float_as_uint(v0 - __uint_as_float(h0));
+                        lo[2 * q + 1] = __float_as_uint(v1 - __uint_as_float(h1));
+                    }
+                } else {
+                    // first block of the call: the 64 samples before it are the object's history (oldest first, Hlen <= 64)
+                    const float* hp = reinterpret_cast<const float*>(p.hist + s_glob * p.Hlen);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const int idx = p.Hlen - kBlk + 32 * half + i;
+                        const float v = (idx >= 0) ? __ldg(hp + 2 * idx + c) : 0.0f;
+                        uint32_t h0;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0) : "f"(v));
+                        hi[i] = h0;
+                        lo[i] = __float_as_uint(v - __uint_as_float(h0));
+                    }
+                }
+                tmem_st32(lane_base + kColHi + kBlk * slot + 32 * half, hi);
+                tmem_st32(lane_base + kColLo + kBlk * slot + 32 * half, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar0 + 8 * (kBarInEmpty + st));
+                mbar_arrive(bar0 + 8 * (kBarAFull + slot));
+            }
+            k++;
+        });
+    } else {
+        // ================================================================= epilogue: thread = row (stream, component)
+        const int row = threadIdx.x - 128;
+        const int sl = row >> 1, c = row & 1;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t row_off = (uint32_t)sl * 128u + 4u * c;
+        long long u = 0;
+        walk(e0, e1, p.n_blocks, [&](int g, long long b, bool prime) {
+            if (prime) return;
+            const int db = (int)(u & 1);
+            mbar_wait(bar0 + 8 * (kBarDFull + db), (uint32_t)((u >> 1) & 1));
+            tc_fence_after();
+            uint32_t d0[32], d1[32];
+            tmem_ld32(lane_base + kColD + kBlk * db, d0);           // columns n' = 0..31  <-> times 63..32
+            tmem_ld32(lane_base + kColD + kBlk * db + 32, d1);      // columns n' = 32..63 <-> times 31..0
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (kBarDEmpty + db));
+            // the staging buffer was last used two tiles ago: its bulk store must have finished reading it
+            if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const uint32_t dst = smem + kSmemOut + db * kStageBytes + row_off;
+#pragma unroll
+            for (int t = 0; t < kBlk; t++) {
+                const uint32_t bits = (t < 32) ? d1[31 - t] : d0[63 - t];
+                const uint32_t a = dst + (uint32_t)(t >> 4) * kSubBytes + ((uint32_t)(((t & 15) >> 1) ^ (sl & 7)) << 4) + (uint32_t)(t & 1) * 8u;
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(__uint_as_float(bits) * p.scale) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 128) {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    tma_store_2d(&tm_out, (int)(32 * (4 * b + j)), g * kStreamsPerGroup, smem + kSmemOut + db * kStageBytes + j * kSubBytes);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            u++;
+        });
+        if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// x[stream][n] cf32 viewed as f32 [n_streams][2n]; box = 32 floats (16 samples, 128 bytes) x 64 streams, 128-byte swizzle
+int32_t make_map(CUtensorMap* tm, const float2* base, long long n, long long n_streams)
+{
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return fail(YG_EINTERNAL, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[2] = {(cuuint64_t)(2 * n), (cuuint64_t)n_streams};
+    const cuuint64_t gstride[1] = {(cuuint64_t)(8 * n)};
+    const cuuint32_t box[2] = {32, (cuuint32_t)kStreamsPerGroup};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(YG_EINTERNAL, "cuTensorMapEncodeTiled failed (%d) for n = %lld, streams = %lld", (int)r, n, n_streams);
+    return YG_OK;
+}
+
+float tf32_rna(float v)
+{
+    uint32_t b;
+    memcpy(&b, &v, 4);
+    b = (b + 0x1000u) & 0xFFFFE000u;          // round to nearest (ties away), keep 10 mantissa bits
+    float r;
+    memcpy(&r, &b, 4);
+    return r;
+}
+
+}  // namespace
+
+bool firfilt_tc_supported(size_t h_len, long long n, long long n_streams, const void* x, const void* y)
+{
+    if (h_len < 1 || h_len > 65) return false;
+    if (n < 2 * kBlk || (n & 1)) return false;                             // row pitch must be a multiple of 16 bytes
+    if (n >= (1LL << 29) || n_streams > 0x7fffffffLL) return false;        // int32 box coordinates
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return false;
+    if (n * n_streams < (1LL << 16)) return false;                         // tiny calls: not worth 148 persistent CTAs
+    return encode_tiled() != nullptr;
+}
+
+// Builds the aliased Toeplitz tables for taps h (device buffer of 2 * kToepBytes bytes).
+int32_t firfilt_tc_plan(const float* h, size_t h_len, float** d_toep)
+{
+    std::vector<float> t(2 * kToepBytes / 4, 0.0f);
+    for (int A = 0; A < kToepBytes; A += 4) {
+        const int v = 8 * (A >> 8) + 4 * ((A >> 7) & 1) + ((A >> 4) & 7) + ((A >> 2) & 3);      // n' + k
+        const int j = 127 - v;
+        if (j >= 0 && j < (int)h_len) {
+            const float hi = tf32_rna(h[j]);
+            t[A / 4] = hi;
+            t[kToepBytes / 4 + A / 4] = h[j] - hi;
+        }
+    }
+    if (!*d_toep) YG_CUDA(cudaMalloc(d_toep, t.size() * sizeof(float)));
+    YG_CUDA(memcpy_sync(*d_toep, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    YG_CUDA(cudaFuncSetAttribute(k_firfilt_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    return YG_OK;
+}
+
+int32_t firfilt_tc_launch(const float* d_toep, float scale, const float2* hist, long long Hlen, const float2* x, float2* y,
+                          long long n, long long n_streams, int n_sm, cudaStream_t st)
+{
+    CUtensorMap tm_in, tm_out;
+    YG_TRY(make_map(&tm_in, x, n, n_streams));
+    YG_TRY(make_map(&tm_out, y, n, n_streams));
+    TcParams p;
+    p.hist = (Hlen > 0) ? hist : nullptr;
+    p.Hlen = (int)Hlen;
+    p.n = n;
+    p.n_streams = (int)n_streams;
+    p.scale = scale;
+    p.toep = d_toep;
+    p.n_blocks = (n + kBlk - 1) / kBlk;
+    p.n_groups = (int)((n_streams + kStreamsPerGroup - 1) / kStreamsPerGroup);
+    const long long total = p.n_blocks * p.n_groups;
+    const int grid = (int)std::min<long long>(n_sm, total);
+    k_firfilt_tc<<<grid, kThreads, kSmemBytes, st>>>(tm_in, tm_out, p);
+    YG_LAUNCH_CHECK();
+    return YG_OK;
+}
+
+}  // namespace yg

@@ -84,6 +84,12 @@ class FirFilt:
     def get_device(self) -> int:
         return self._dev
 
+    def last_path(self) -> int:
+        """0 none, 1 generic kernel, 2 register-blocked FFMA2 kernel, 4 tensor-core (tcgen05 3xTF32) kernel."""
+        p = C.c_int32()
+        _lib.check(_lib.lib().yg_firfilt_crcf_last_path(self._q, C.byref(p)))
+        return p.value
+
     def execute_block(self, x, out=None):
         """x[stream][n] -> y[stream][n] (`execute_block(&mut self, x, y)`, firfilt.rs:267-278)."""
         L = _lib.lib()
