@@ -408,3 +408,43 @@ def test_nccl_gather_of_time_shards_and_channel_major():
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "gather ok" in o, "rank %d:\n%s" % (r, o[-2000:])
+
+
+# ------------------------------------------------------------------ firfilt on the tensor cores (tcgen05, 3xTF32)
+@pytest.mark.parametrize("S_,N,taps,cuts,scale", [
+    (64, 1024, 63, None, 1.0),                              # 8 stream groups x 1 segment group, 2 blocks per segment
+    (64, 5098, 63, [0, 512, 1000, 1002, 5098], 0.5),        # state carried across calls; short / odd-sized calls fall back
+    (100, 2048, 40, None, 1.0),                             # ragged stream count: 12.5 stream groups
+    (130, 1 << 14, 1, None, 2.0),                           # a single tap
+    (512, 1 << 13, 65, [0, 4096, 8192], 1.0),               # the longest filter the K = 128 window holds
+    (24, 3 << 16, 33, None, 1.0),                           # long streams: 8192-sample segments, 24 of them (3 segment groups)
+    (1024, 1 << 12, 63, None, 1.0),                         # more (tile, block) items than CTAs: runs spanning tiles
+])
+def test_firfilt_tensor_core_path(monkeypatch, S_, N, taps, cuts, scale):
+    """The tcgen05 3xTF32 Toeplitz kernel (last_path 4) against an f64 convolution and against the oracle's f32
+    result, in the tolerance north_star states (rel-RMS <= 1e-5, max-abs <= 1e-4 at unit output scale)."""
+    import torch
+    monkeypatch.setenv("YG_FIRFILT_TC", "1")
+    rng = np.random.default_rng(S_ * 131 + N + taps)
+    h = (rng.standard_normal(taps) / np.sqrt(taps)).astype(np.float32)
+    x = _rand_c(rng, S_ * N).reshape(S_, N)
+    q = yb.FirFilt.new(h, n_streams=S_)
+    q.set_scale(scale)
+    xd = torch.from_numpy(x).cuda()
+    cs = cuts or [0, N]
+    ys, paths = [], []
+    for a, b in zip(cs, cs[1:]):
+        ys.append(q.execute_block(xd[:, a:b].contiguous()).view(S_, b - a))
+        paths.append(q.last_path())
+    torch.cuda.synchronize()
+    assert 4 in paths, paths
+    y = torch.cat(ys, dim=1).cpu().numpy()
+    for s in range(0, S_, max(1, S_ // 16)):
+        ref64 = np.convolve(x[s].astype(np.complex128), h.astype(np.float64))[:N] * scale
+        rel, mx = errors(y[s], ref64)
+        assert rel < 2e-6 and mx < 2e-5, (s, rel, mx)
+        assert_parity(y[s], po.firfilt_crcf(h, x[s], scale=scale), "tensor-core firfilt vs oracle, stream %d" % s)
+    # reset clears the history the next call would otherwise prime the first block with
+    q.reset()
+    y2 = q.execute_block(xd).view(S_, N).cpu().numpy()
+    assert_parity(y2[S_ - 1], po.firfilt_crcf(h, x[S_ - 1], scale=scale), "after reset")

