@@ -1,11 +1,19 @@
 #!/usr/bin/env python
-"""tools/ncu_summary.py REPORT.ncu-rep -- key metrics + stall breakdown + hottest SASS lines (reads with `ncu -i`)."""
+"""tools/ncu_summary.py REPORT.ncu-rep [n_hot_lines] [--traffic KEY] -- key metrics + stall breakdown + hottest SASS lines
+(reads with `ncu -i`).  With --traffic KEY the DRAM bytes of the first kernel of the report are also recorded in
+profiles/ncu_traffic.json under KEY (e.g. "k_firpfbch2_analysis_fused@2^28"), which is where bench.py takes
+`roofline.traffic` from."""
 import csv
 import io
 import subprocess
 import sys
 
 rep = sys.argv[1]
+traffic_key = None
+if "--traffic" in sys.argv:
+    i = sys.argv.index("--traffic")
+    traffic_key = sys.argv[i + 1]
+    del sys.argv[i:i + 2]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
@@ -14,6 +22,23 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "smsp__inst_executed.sum", "sm__cycles_elapsed.avg", "smsp__cycles_elapsed.avg.per_second",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum"]
+def _bytes(val, unit):
+    return float(val) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
+
+
+if traffic_key and len(rows) > 2:
+    import json
+    import os
+    r = rows[2]
+    ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    try:
+        db = json.load(open(path))
+    except Exception:
+        db = {}
+    db[traffic_key] = {"dram_bytes_read": _bytes(r[ir], units[ir]), "dram_bytes_write": _bytes(r[iw], units[iw]),
+                       "kernel": r[hdr.index("Kernel Name")][:120], "source": "ncu --set full, " + os.path.basename(rep)}
+    json.dump(db, open(path, "w"), indent=1, sort_keys=True)
 for r in rows[2:]:
     print("kernel:", r[hdr.index("Kernel Name")][:90])
     for w in want:
