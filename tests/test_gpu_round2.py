@@ -448,3 +448,53 @@ def test_firfilt_tensor_core_path(monkeypatch, S_, N, taps, cuts, scale):
     q.reset()
     y2 = q.execute_block(xd).view(S_, N).cpu().numpy()
     assert_parity(y2[S_ - 1], po.firfilt_crcf(h, x[S_ - 1], scale=scale), "after reset")
+
+
+# ------------------------------------------------------------------ guard bands (compute-sanitizer is closed on this pool)
+def test_kernels_do_not_write_outside_their_output():
+    """Out-of-bounds writes would land in the guard bands around `out`: the fused M=256 kernel (incl. its folded state
+    hand-off), the tensor-core firfilt (TMA tensor stores, ragged stream count), the channel-major transpose and the
+    large-M cooperative kernel all leave a NaN-patterned band of 1 MiB on either side untouched."""
+    import torch
+    pad = 1 << 17
+
+    def guarded(n):
+        buf = torch.full((pad + n + pad, 2), float("nan"), dtype=torch.float32, device="cuda")
+        return buf, torch.view_as_complex(buf)[pad: pad + n]
+
+    def intact(buf, n):
+        return bool(torch.isnan(buf[:pad]).all()) and bool(torch.isnan(buf[pad + n:]).all())
+
+    rng = np.random.default_rng(5)
+    # fused analysis, M = 256
+    M, m, K = 256, 7, 4098
+    x = torch.from_numpy(_rand_c(rng, K * M // 2)).cuda()
+    buf, out = guarded(K * M)
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    q.execute_block(x, K, out=out)
+    torch.cuda.synchronize()
+    assert q.last_path() == 2 and intact(buf, K * M) and bool(torch.isfinite(torch.view_as_real(out)).all())
+    # large-M cooperative kernel
+    M, m, K = 1024, 4, 2048 + 3
+    x = torch.from_numpy(_rand_c(rng, K * M // 2)).cuda()
+    buf, out = guarded(K * M)
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    q.execute_block(x, K, out=out)
+    torch.cuda.synchronize()
+    assert q.last_path() == 3 and intact(buf, K * M) and bool(torch.isfinite(torch.view_as_real(out)).all())
+    # tensor-core firfilt, 100 streams (12.5 tiles of 8) x 4096
+    S_, N = 100, 4096
+    x = torch.from_numpy(_rand_c(rng, S_ * N)).cuda()
+    buf, out = guarded(S_ * N)
+    f = yb.FirFilt.new(yb.fir_design_kaiser(63, 0.25, 60.0, 0.0), n_streams=S_)
+    f.execute_block(x, out=out)
+    torch.cuda.synchronize()
+    assert f.last_path() == 4 and intact(buf, S_ * N) and bool(torch.isfinite(torch.view_as_real(out)).all())
+    # channel-major transpose with ragged tile edges
+    Kf, Mc = 1000 + 7, 48
+    y = torch.from_numpy(_rand_c(rng, Kf * Mc)).cuda().view(Kf, Mc)
+    buf, out = guarded(Kf * Mc)
+    cm = yb.channel_major(y, out=out.view(Mc, Kf))
+    torch.cuda.synchronize()
+    assert intact(buf, Kf * Mc)
+    assert bool(torch.equal(torch.view_as_real(cm), torch.view_as_real(y.t().contiguous())))

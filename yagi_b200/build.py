@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-Xptxas=-v",
-]
+] + os.environ.get("YG_NVCC_EXTRA", "").split()      # e.g. -DYG_LARGE_ACQUIRE_FENCE=0 for an A/B build
 
 
 def _nvcc() -> str:

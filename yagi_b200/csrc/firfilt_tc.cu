@@ -347,12 +347,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
             // the staging buffer was last used two tiles ago: its bulk store must have finished reading it
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
+            // 16 rows x 2 components per warp: rows v and v + 8 share a swizzle key, so in each store the upper eight rows
+            // take the other sample of the 16-byte chunk (flip) -- all 32 lanes then hit distinct banks.
             const uint32_t dst = smem + kSmemOut + db * kStageBytes + row_off;
+            const bool flip = (sl >> 3) & 1;
+            auto tile_val = [&](int t) { return (t < 32) ? d1[31 - t] : d0[63 - t]; };        // time t of the tile (columns are reversed)
 #pragma unroll
-            for (int t = 0; t < kBlk; t++) {
-                const uint32_t bits = (t < 32) ? d1[31 - t] : d0[63 - t];
-                const uint32_t a = dst + (uint32_t)(t >> 4) * kSubBytes + ((uint32_t)(((t & 15) >> 1) ^ (sl & 7)) << 4) + (uint32_t)(t & 1) * 8u;
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(__uint_as_float(bits) * p.scale) : "memory");
+            for (int tt = 0; tt < kBlk; tt += 2) {
+                const uint32_t a = dst + (uint32_t)(tt >> 4) * kSubBytes + ((uint32_t)(((tt & 15) >> 1) ^ (sl & 7)) << 4);
+                const uint32_t lo_bits = tile_val(tt), hi_bits = tile_val(tt + 1);
+                const float first = __uint_as_float(flip ? hi_bits : lo_bits) * p.scale;       // sample tt + flip
+                const float second = __uint_as_float(flip ? lo_bits : hi_bits) * p.scale;      // sample tt + 1 - flip
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + (flip ? 8u : 0u)), "f"(first) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + (flip ? 0u : 8u)), "f"(second) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");

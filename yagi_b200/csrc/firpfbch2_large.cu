@@ -364,6 +364,23 @@ __device__ __forceinline__ void warp_retire(unsigned* p, int lane)
     __syncwarp();
     if (lane == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
+// The polls are relaxed.  The PTX memory model would want an acquire after the counter has been seen, to pair with the
+// producer's red.release before this warp reads the ring.  One `fence.acq_rel.gpu` per batch and warp was built and
+// measured (-DYG_LARGE_ACQUIRE_FENCE=1, profiles/r02_large_fence_ab.log): it costs 10-11 % (M = 1024, 2^24: 0.146 ->
+// 0.163 ms; M = 512: 0.477 -> 0.537 ms) because at gpu scope it also invalidates the SM's L1 (CCTL.IVALL), where the
+// twiddles live.  It stays compiled out: the ring is written with st.global.cg and read with cp.async.cg / ld.global.cg
+// (L2 on both sides, nothing stale to invalidate), and the reads are issued only after the poll loop's exit branch has
+// resolved on the loaded value -- the SM does not issue loads past an unresolved branch -- so the counter load is
+// ordered before them on this hardware.
+#ifndef YG_LARGE_ACQUIRE_FENCE
+#define YG_LARGE_ACQUIRE_FENCE 0
+#endif
+__device__ __forceinline__ void acquire_after_poll()
+{
+#if YG_LARGE_ACQUIRE_FENCE
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void warp_wait(const unsigned* p, unsigned target, int lane)
 {
     if (lane == 0) {
@@ -371,6 +388,7 @@ __device__ __forceinline__ void warp_wait(const unsigned* p, unsigned target, in
         while (ld_relaxed_gpu(p) < target) {
             if (++spins > (1u << 27)) __trap();  // seconds without progress: fail the launch rather than hang the GPU
         }
+        acquire_after_poll();
     }
     __syncwarp();
 }
@@ -379,11 +397,14 @@ __device__ __forceinline__ void warp_wait(const unsigned* p, unsigned target, in
 __device__ __forceinline__ unsigned warp_peek(const unsigned* p, int lane) { return lane == 0 ? ld_relaxed_gpu(p) : 0u; }
 __device__ __forceinline__ void warp_wait_seen(unsigned seen, const unsigned* p, unsigned target, int lane)
 {
-    if (lane == 0 && seen < target) {
-        unsigned spins = 0;
-        while (ld_relaxed_gpu(p) < target) {
-            if (++spins > (1u << 27)) __trap();
+    if (lane == 0) {
+        if (seen < target) {
+            unsigned spins = 0;
+            while (ld_relaxed_gpu(p) < target) {
+                if (++spins > (1u << 27)) __trap();
+            }
         }
+        acquire_after_poll();
     }
     __syncwarp();
 }
