@@ -11,12 +11,12 @@ namespace yg {
 // firfilt_fast.cu
 bool firfilt_fast_supported(size_t h_len);
 int32_t firfilt_fast_launch(const float* h, size_t h_len, float scale, const float2* hist, long long Hlen, const float2* x,
-                            float2* y, long long n, long long n_streams, cudaStream_t st);
+                            float2* y, long long n, long long n_streams, cudaStream_t st, long long t_begin = 0);
 // firfilt_tc.cu: tensor-core (tcgen05, 3xTF32 banded Toeplitz) path for <= 65 taps
-bool firfilt_tc_supported(size_t h_len, long long n, long long n_streams, const void* x, const void* y);
+long long firfilt_tc_prefix(size_t h_len, long long n, long long n_streams, const void* x, const void* y);
 int32_t firfilt_tc_plan(const float* h, size_t h_len, float** d_toep);
 int32_t firfilt_tc_launch(const float* d_toep, float scale, const float2* hist, long long Hlen, const float2* x, float2* y,
-                          long long n, long long n_streams, int n_sm, cudaStream_t st);
+                          long long n, long long pitch, long long n_streams, int n_sm, cudaStream_t st);
 }  // namespace yg
 
 struct yg_firfilt_crcf_s {
@@ -119,10 +119,15 @@ int32_t execute_dev_impl(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf3
     if (n == 0) return YG_OK;
     const long long S = q->n_streams;
     const long long Hlen = (long long)q->state_len;
-    if (q->tc_mode && q->d_toep && firfilt_tc_supported(q->h_len, (long long)n, S, d_x, d_y)) {
-        // tcgen05 3xTF32 Toeplitz GEMM (<= 65 taps, whole calls of aligned, even-length streams)
+    const long long n_main = (q->tc_mode && q->d_toep) ? firfilt_tc_prefix(q->h_len, (long long)n, S, d_x, d_y) : 0;
+    if (n_main > 0) {
+        // tcgen05 3xTF32 Toeplitz GEMM (<= 65 taps) on the longest prefix that is whole segments; the FFMA2 kernel
+        // finishes the remaining < 8192 (< 512 for short streams) samples of every stream, reading its history from x
         YG_TRY(firfilt_tc_launch(q->d_toep, q->scale, reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
-                                 reinterpret_cast<const float2*>(d_x), reinterpret_cast<float2*>(d_y), (long long)n, S, q->n_sm, st));
+                                 reinterpret_cast<const float2*>(d_x), reinterpret_cast<float2*>(d_y), n_main, (long long)n, S,
+                                 q->n_sm, st));
+        YG_TRY(firfilt_fast_launch(q->h.data(), q->h_len, q->scale, reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
+                                   reinterpret_cast<const float2*>(d_x), reinterpret_cast<float2*>(d_y), (long long)n, S, st, n_main));
         q->last_path = 4;
     } else if (firfilt_fast_supported(q->h_len) && (long long)n * S >= 4096) {
         // register-blocked FFMA2 kernel (taps as kernel parameters); generic kernel for long filters / tiny calls

@@ -61,14 +61,14 @@ __device__ __forceinline__ void fir_steps(float2 (&acc)[kR], const float2* tile,
 template <int kH>
 __global__ void __launch_bounds__(kThreads, 4)
 k_firfilt_fast(const FirTaps<kH> taps, float scale, const float2* __restrict__ hist, int Hlen,
-               const float2* __restrict__ x, float2* __restrict__ y, long long n)
+               const float2* __restrict__ x, float2* __restrict__ y, long long n, long long t_begin)
 {
     constexpr int kIn = kTile + kH - 1;          // samples staged per tile
     constexpr int kPadded = kIn + (kIn >> 4) + 1;
     __shared__ float2 tile[kPadded];
     const int t = threadIdx.x;
     const long long s = blockIdx.y;                                                   // stream
-    const long long n0 = (long long)blockIdx.x * kTile;                               // first output of the tile
+    const long long n0 = t_begin + (long long)blockIdx.x * kTile;                     // first output of the tile
     const float2* xs = x + s * n;
     const float2* hs = hist + s * Hlen;
 
@@ -125,16 +125,16 @@ k_firfilt_fast(const FirTaps<kH> taps, float scale, const float2* __restrict__ h
 namespace {
 template <int kH>
 int32_t launch_h(const float* h, size_t h_len, float scale, const float2* hist, long long Hlen, const float2* x,
-                 float2* y, long long n, long long n_streams, cudaStream_t st)
+                 float2* y, long long n, long long n_streams, cudaStream_t st, long long t_begin)
 {
     FirTaps<kH> taps;
     for (int k = 0; k < kH; k++) taps.h[k] = (k < (int)h_len) ? h[k] : 0.0f;
-    const long long tiles = (n + kTile - 1) / kTile;
+    const long long tiles = (n - t_begin + kTile - 1) / kTile;        // outputs [t_begin, n) of every stream
     if (tiles > 0x7fffffffLL) return fail(YG_ERANGE, "too many tiles for one launch");
     for (long long s0 = 0; s0 < n_streams; s0 += 65535) {                  // grid.y carries the stream index
         const long long ns = std::min<long long>(65535, n_streams - s0);
         k_firfilt_fast<kH><<<dim3((unsigned)tiles, (unsigned)ns), kThreads, 0, st>>>(taps, scale, hist + s0 * Hlen, (int)Hlen,
-                                                                                    x + s0 * n, y + s0 * n, n);
+                                                                                    x + s0 * n, y + s0 * n, n, t_begin);
         YG_LAUNCH_CHECK();
     }
     return YG_OK;
@@ -143,12 +143,15 @@ int32_t launch_h(const float* h, size_t h_len, float scale, const float2* hist, 
 
 bool firfilt_fast_supported(size_t h_len) { return h_len >= 1 && h_len <= 256; }
 
+// Outputs [t_begin, n) of every stream (t_begin > 0: the samples before it are read from x itself -- the tail the
+// tensor-core kernel leaves when n is not a whole number of its blocks).
 int32_t firfilt_fast_launch(const float* h, size_t h_len, float scale, const float2* hist, long long Hlen, const float2* x,
-                            float2* y, long long n, long long n_streams, cudaStream_t st)
+                            float2* y, long long n, long long n_streams, cudaStream_t st, long long t_begin)
 {
-    if (h_len <= 64) return launch_h<64>(h, h_len, scale, hist, Hlen, x, y, n, n_streams, st);
-    if (h_len <= 128) return launch_h<128>(h, h_len, scale, hist, Hlen, x, y, n, n_streams, st);
-    return launch_h<256>(h, h_len, scale, hist, Hlen, x, y, n, n_streams, st);
+    if (t_begin >= n) return YG_OK;
+    if (h_len <= 64) return launch_h<64>(h, h_len, scale, hist, Hlen, x, y, n, n_streams, st, t_begin);
+    if (h_len <= 128) return launch_h<128>(h, h_len, scale, hist, Hlen, x, y, n, n_streams, st, t_begin);
+    return launch_h<256>(h, h_len, scale, hist, Hlen, x, y, n, n_streams, st, t_begin);
 }
 
 }  // namespace yg

@@ -407,12 +407,12 @@ EncodeTiledFn encode_tiled()
 // x 8 streams, 128-byte swizzle.  Why segments: with rows = 64 different streams a CTA cycles through 64 + 64 pages that
 // are a power-of-two row pitch apart, which thrashes the TLB (measured: 4.2 TB/s with 8 MiB rows against 5.3 TB/s with
 // 2 MiB rows); 8 streams x 8 adjacent 64 KB segments touch 8 + 8 pages.
-int32_t make_map(CUtensorMap* tm, const float2* base, long long n, long long n_streams, long long Q)
+int32_t make_map(CUtensorMap* tm, const float2* base, long long n, long long pitch, long long n_streams, long long Q)
 {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) return fail(YG_EINTERNAL, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t gdim[3] = {(cuuint64_t)(2 * Q), (cuuint64_t)(n / Q), (cuuint64_t)n_streams};
-    const cuuint64_t gstride[2] = {(cuuint64_t)(8 * Q), (cuuint64_t)(8 * n)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)(8 * Q), (cuuint64_t)(8 * pitch)};
     const cuuint32_t box[3] = {32, (cuuint32_t)kTileSegs, (cuuint32_t)kTileStreams};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float2*>(base), gdim, gstride, box, estr,
@@ -423,7 +423,15 @@ int32_t make_map(CUtensorMap* tm, const float2* base, long long n, long long n_s
 }
 
 // segment length: 8192 samples (64 KB) for long streams, an eighth of the stream for short ones
-long long segment_len(long long n) { return n >= 65536 ? 8192 : n / kTileSegs; }
+long long segment_len(long long n)
+{
+    static const long long q_long = [] {            // YG_TC_SEG: segment length for long streams (tuning knob, default 8192)
+        const char* e = getenv("YG_TC_SEG");
+        const long long v = e ? atoll(e) : 0;
+        return (v >= 64 && v % 64 == 0) ? v : 8192LL;
+    }();
+    return n >= 8 * q_long ? q_long : n / kTileSegs;
+}
 
 float tf32_rna(float v)
 {
@@ -437,16 +445,20 @@ float tf32_rna(float v)
 
 }  // namespace
 
-bool firfilt_tc_supported(size_t h_len, long long n, long long n_streams, const void* x, const void* y)
+// The longest prefix of an n-sample stream the kernel takes: whole 8192-sample segments of long streams, an eighth of the
+// prefix per segment (whole 64-sample blocks) for short ones; 0 if it takes nothing.
+long long firfilt_tc_prefix(size_t h_len, long long n, long long n_streams, const void* x, const void* y)
 {
-    if (h_len < 1 || h_len > 65) return false;
-    if (n < kTileSegs * kBlk) return false;
-    const long long Q = segment_len(n);
-    if (Q % kBlk != 0 || n % Q != 0) return false;                         // whole 64-sample blocks per segment, whole segments per stream
-    if (n >= (1LL << 29) || n_streams > 0x7fffffffLL) return false;        // int32 box coordinates
-    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return false;
-    if (n * n_streams < (1LL << 16)) return false;                         // tiny calls: not worth 148 persistent CTAs
-    return encode_tiled() != nullptr;
+    if (h_len < 1 || h_len > 65) return 0;
+    if (n & 1) return 0;                                                   // row pitch must be a multiple of 16 bytes
+    if (n >= (1LL << 29) || n_streams > 0x7fffffffLL) return 0;            // int32 box coordinates
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return 0;
+    const long long q_long = segment_len(1LL << 40);
+    const long long unit = (n >= kTileSegs * q_long) ? q_long : (long long)kTileSegs * kBlk;
+    const long long n_main = n / unit * unit;
+    if (n_main < kTileSegs * kBlk) return 0;
+    if (n_main * n_streams < (1LL << 16)) return 0;                        // tiny calls: not worth 148 persistent CTAs
+    return encode_tiled() != nullptr ? n_main : 0;
 }
 
 // Builds the aliased Toeplitz tables for taps h (device buffer of 2 * kToepBytes bytes).
@@ -468,13 +480,15 @@ int32_t firfilt_tc_plan(const float* h, size_t h_len, float** d_toep)
     return YG_OK;
 }
 
+// Outputs [0, n) of every stream; rows of x and y are `pitch` samples apart (pitch >= n, even).
 int32_t firfilt_tc_launch(const float* d_toep, float scale, const float2* hist, long long Hlen, const float2* x, float2* y,
-                          long long n, long long n_streams, int n_sm, cudaStream_t st)
+                          long long n, long long pitch, long long n_streams, int n_sm, cudaStream_t st)
 {
     CUtensorMap tm_in, tm_out;
     const long long Q = segment_len(n);
-    YG_TRY(make_map(&tm_in, x, n, n_streams, Q));
-    YG_TRY(make_map(&tm_out, y, n, n_streams, Q));
+    if (Q < kBlk || Q % kBlk != 0 || n % Q != 0) return fail(YG_EINTERNAL, "tensor-core firfilt: %lld samples are not whole segments", n);
+    YG_TRY(make_map(&tm_in, x, n, pitch, n_streams, Q));
+    YG_TRY(make_map(&tm_out, y, n, pitch, n_streams, Q));
     TcParams p;
     p.hist = (Hlen > 0) ? hist : nullptr;
     p.Hlen = (int)Hlen;
