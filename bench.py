@@ -508,10 +508,11 @@ def main():
             line["output_gather"] = gather
         if not args.no_cpu and world == 1:
             threads = cpu_threads()
-            npt = 1 << 22
-            v, secs = run_cpu_path(npt, 2, threads)
+            npt, passes = 1 << 22, 6                      # ~20 core-seconds of CPU work on the 16-core box
+            v, secs = run_cpu_path(npt, passes, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "%d threads x 2 passes x 2^22 samples each of the same workload (%.1f s wall)" % (threads, secs)}
+                                    "sample": "%d threads x %d passes x 2^22 samples each of the same workload (%.1f s wall, %.0f core-seconds)"
+                                              % (threads, passes, secs, secs * threads)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
