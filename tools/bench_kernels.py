@@ -132,12 +132,12 @@ def main():
         q = yb.FirFilt.new_kaiser(63, 0.25, 60.0, 0.0, n_streams=S)
         ms = timed(lambda: q.execute_block(x, out=y), steps=5)
         flops = 252.0 * S * n
-        report("firfilt_crcf 63 taps, 1024 streams x 2^20", ms, 16.0 * S * n, S * n, "samples",
-               {"fp32_TFLOPs": round(flops / (ms * 1e-3) / 1e12, 2)})
+        report("firfilt_crcf 63 taps, 1024 streams x 2^20 (path %d%s)" % (q.last_path(), ", tensor cores" if q.last_path() == 4 else ""),
+               ms, 16.0 * S * n, S * n, "samples", {"useful_f32_TFLOPs": round(flops / (ms * 1e-3) / 1e12, 2)})
         for taps in (127, 255):                 # the same kernel at tap capacities 128 / 256 (FP32-bound, not a BASELINE config)
             q = yb.FirFilt.new_kaiser(taps, 0.25, 60.0, 0.0, n_streams=S)
             ms = timed(lambda: q.execute_block(x, out=y), steps=3)
-            report("firfilt_crcf %d taps, 1024 streams x 2^20" % taps, ms, 16.0 * S * n, S * n, "samples",
+            report("firfilt_crcf %d taps, 1024 streams x 2^20 (path %d)" % (taps, q.last_path()), ms, 16.0 * S * n, S * n, "samples",
                    {"fp32_TFLOPs": round(4.0 * taps * S * n / (ms * 1e-3) / 1e12, 2)})
 
 

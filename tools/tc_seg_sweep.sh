@@ -1,1 +1,1 @@
-for q in 1024 2048 4096 8192 16384 32768 131072; do echo "Q=$q"; YG_TC_SEG=$q python tools/tc_one_time.py; done
+for v in 0 64 128 256; do echo "L2PROMO=$v"; YG_TC_L2PROMO=$v python tools/tc_one_time.py; done
