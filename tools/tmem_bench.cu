@@ -21,6 +21,20 @@ __device__ __forceinline__ void st16(uint32_t a, const uint32_t (&v)[16])
                  ::"r"(a), R16(v) : "memory");
 }
 
+#define W32(v) W16(v), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+// 32 lanes x 32 columns in one instruction
+__device__ __forceinline__ void ld32(uint32_t a, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+                 "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" : W32(v) : "r"(a) : "memory");
+}
+// 16 lanes x 256 bits, repeated 8 times along the columns: 32 registers per thread, 4 KB per warp instruction
+__device__ __forceinline__ void ld16x256(uint32_t a, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+                 "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" : W32(v) : "r"(a) : "memory");
+}
+
 // mode 0: loads only (4 independent x16 loads per iteration, then wait::ld); mode 1: stores only; mode 2: ld + st + 16 FMAs
 __global__ void __launch_bounds__(256, 1) k_tmem(int iters, int mode, unsigned* out, long long* clk)
 {
@@ -51,6 +65,24 @@ __global__ void __launch_bounds__(256, 1) k_tmem(int iters, int mode, unsigned* 
         if (mode == 2)
             for (int q = 0; q < 4; q++)
                 for (int i = 0; i < 16; i++) v[q][i] = v[q][i] * 3u + (unsigned)it;
+        if (mode == 3) {                                   // 2 x (32x32b.x32): the same 64 columns per thread
+            uint32_t w[32];
+            ld32(a, w);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            acc += w[it & 31];
+            ld32(a + 32, w);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            acc += w[(it + 7) & 31];
+        }
+        if (mode == 4) {                                   // 2 x (16x256b.x8): lanes 0-15 and 16-31 of the warp's quadrant, 64 columns
+            uint32_t w[32];
+            ld16x256(a, w);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            acc += w[it & 31];
+            ld16x256(a + (16u << 16), w);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            acc += w[(it + 7) & 31];
+        }
         if (mode == 1 || mode == 2) {
             for (int q = 0; q < 4; q++) st16(a + 16 * q, v[q]);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -76,8 +108,9 @@ int main()
     long long* clk;
     CK(cudaMalloc(&out, grid * 256 * sizeof(unsigned)));
     CK(cudaMalloc(&clk, grid * sizeof(long long)));
-    const char* names[3] = {"tcgen05.ld 4 x (32x32b.x16) per iteration", "tcgen05.st 4 x (32x32b.x16) per iteration", "ld + 64 IMAD + st per iteration"};
-    for (int mode = 0; mode < 3; mode++) {
+    const char* names[5] = {"tcgen05.ld 4 x (32x32b.x16) per iteration", "tcgen05.st 4 x (32x32b.x16) per iteration", "ld + 64 IMAD + st per iteration",
+                            "tcgen05.ld 2 x (32x32b.x32) per iteration", "tcgen05.ld 2 x (16x256b.x8) per iteration"};
+    for (int mode = 0; mode < 5; mode++) {
         k_tmem<<<grid, 256>>>(iters, mode, out, clk);
         CK(cudaDeviceSynchronize());
         long long h[512];

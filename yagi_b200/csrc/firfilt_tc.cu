@@ -157,7 +157,8 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
            (1ull << 46);                      // descriptor version 1 (sm_100); base offset 0, layout type 0 = no swizzle
 }
 // kind::tf32, f32 accumulate, A and B K-major, N = 64, M = 128 (cute::UMMA::InstrDescriptor bit layout)
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBlk >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+constexpr uint32_t idesc_n(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24); }
+constexpr uint32_t kIdesc = idesc_n(kBlk), kIdescHalf = idesc_n(kBlk / 2);
 
 // The walk every role performs: the CTA's items [e0, e1) of the (group, block) grid, cut into runs inside one group;
 // a run starts with a priming step for the block before it.  step(group, block, prime) is called in the same order by
@@ -245,13 +246,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
                 const uint32_t d = tmem + kColD + kBlk * db;
                 const uint32_t col_prev = (uint32_t)(kBlk * ((slot + 2) % 3)), col_cur = (uint32_t)(kBlk * slot);
                 if (elect_one()) {
+                    // B[k][n'] is zero unless 63 <= n' + k <= 127: K steps 0-3 (k < 32) touch only the columns n' >= 32 and
+                    // K steps 12-15 (k >= 96) only n' < 32, so those eight steps are issued at half width (N = 32: half the
+                    // tensor-pipe time); the full-width steps 4-11 come first so that one of them initialises the accumulator.
 #pragma unroll
-                    for (int s = 0; s < 16; s++) {
+                    for (int i = 0; i < 16; i++) {
+                        const int s = (i < 8) ? i + 4 : (i < 12 ? i - 8 : i);              // 4..11, 0..3, 12..15
                         const uint32_t col = (s < 8) ? col_prev + 8 * s : col_cur + 8 * (s - 8);
-                        const uint64_t bh = smem_desc(toep_hi + 256 * s, 128, 256), bl = smem_desc(toep_lo + 256 * s, 128, 256);
-                        tc_mma_ts(d, tmem + kColLo + col, bh, kIdesc, s > 0 ? 1u : 0u);      // small terms first
-                        tc_mma_ts(d, tmem + kColHi + col, bl, kIdesc, 1u);
-                        tc_mma_ts(d, tmem + kColHi + col, bh, kIdesc, 1u);
+                        const bool upper = s < 4, lower = s >= 12;
+                        const uint32_t boff = 256u * s + (upper ? 4u * 256u : 0u);         // n' group 4 = +4 SBO
+                        const uint64_t bh = smem_desc(toep_hi + boff, 128, 256), bl = smem_desc(toep_lo + boff, 128, 256);
+                        const uint32_t dd = d + (upper ? 32u : 0u);
+                        const uint32_t id = (upper || lower) ? kIdescHalf : kIdesc;
+                        tc_mma_ts(dd, tmem + kColLo + col, bh, id, i > 0 ? 1u : 0u);       // small terms first
+                        tc_mma_ts(dd, tmem + kColHi + col, bl, id, 1u);
+                        tc_mma_ts(dd, tmem + kColHi + col, bh, id, 1u);
                     }
                     tc_commit(bar0 + 8 * (kBarDFull + db));
                 }
