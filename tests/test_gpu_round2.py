@@ -500,3 +500,61 @@ def test_kernels_do_not_write_outside_their_output():
     torch.cuda.synchronize()
     assert intact(buf, Kf * Mc)
     assert bool(torch.equal(torch.view_as_real(cm), torch.view_as_real(y.t().contiguous())))
+
+
+# ------------------------------------------------------------------ the reference's own firfilt autotests, on the GPU object
+def _psd_regions_ok(H, regions):
+    """utility/test_helpers.rs validate_psd_spectrum: every bin of a region inside [pmin, pmax] dB on the tested sides."""
+    n = H.size
+    f = np.arange(n) / n - 0.5
+    psd = 20.0 * np.log10(np.maximum(np.abs(np.fft.fftshift(H)), 1e-12))
+    for fmin, fmax, pmin, pmax, test_lo, test_hi in regions:
+        sel = (f >= fmin) & (f <= fmax)
+        if test_lo and not (psd[sel] >= pmin).all():
+            return False
+        if test_hi and not (psd[sel] <= pmax).all():
+            return False
+    return True
+
+
+def test_firfilt_crcf_kaiser_autotest_on_cuda(monkeypatch):
+    """Reference test_firfilt_crcf_kaiser (src/filter/fir/firfilt.rs:354-370): new_kaiser(51, 0.2, 60, 0), scale 0.4;
+    stop bands <= -60 dB, pass band within +-0.1 dB.  The reference reads the response off the taps; here it is MEASURED
+    by pushing an impulse through the GPU filter -- through the tensor-core kernel and through the FFMA2 kernel."""
+    import torch
+    regions = [(-0.5, -0.25, 0.0, -60.0, False, True), (-0.15, 0.15, -0.1, 0.1, True, True), (0.25, 0.5, 0.0, -60.0, False, True)]
+    S_, N = 32, 4096
+    for tc, want in (("1", 4), ("0", 2)):
+        monkeypatch.setenv("YG_FIRFILT_TC", tc)
+        q = yb.FirFilt.new_kaiser(51, 0.2, 60.0, 0.0, n_streams=S_)
+        q.set_scale(0.4)
+        x = np.zeros((S_, N), dtype=np.complex64)
+        for s in range(S_):
+            x[s, 7 * s] = 1.0                                # a different delay per stream
+        y = q.execute_block(torch.from_numpy(x).cuda()).view(S_, N).cpu().numpy()
+        assert q.last_path() == want
+        for s in (0, 5, 31):
+            h_meas = y[s, 7 * s: 7 * s + 1200]               # impulse response (51 taps, zero after)
+            assert np.abs(y[s, : 7 * s]).max(initial=0.0) == 0.0
+            assert _psd_regions_ok(np.fft.fft(h_meas, 1200), regions), (tc, s)
+
+
+def test_firfilt_crcf_copy_autotest_on_cuda(monkeypatch):
+    """Reference test_firfilt_crcf_copy (firfilt.rs:541-583): new_kaiser(21, 0.345, 60, 0), scale 2; run, clone, keep running
+    both: same coefficients, scale, length and outputs.  Sample-sized calls (generic kernel) and block-sized calls
+    (tensor-core kernel)."""
+    import torch
+    rng = np.random.default_rng(21)
+    for S_, n in ((1, 32), (32, 4096)):
+        q = yb.FirFilt.new_kaiser(21, 0.345, 60.0, 0.0, n_streams=S_)
+        q.set_scale(2.0)
+        x1 = torch.from_numpy(_rand_c(rng, S_ * n)).cuda()
+        x2 = torch.from_numpy(_rand_c(rng, S_ * n)).cuda()
+        q.execute_block(x1)
+        c = q.clone()
+        assert c.get_scale() == q.get_scale() == 2.0 and c.len() == q.len() == 21
+        ya, yb_ = q.execute_block(x2), c.execute_block(x2)
+        torch.cuda.synchronize()
+        assert bool(torch.equal(torch.view_as_real(ya), torch.view_as_real(yb_)))
+        ref = po.firfilt_crcf(yb.fir_design_kaiser(21, 0.345, 60.0, 0.0), np.concatenate([x1.view(S_, n)[0].cpu().numpy(), x2.view(S_, n)[0].cpu().numpy()]), scale=2.0)[n:]
+        assert_parity(ya.view(S_, n)[0].cpu().numpy(), ref, "continuation after clone, %d streams" % S_)
