@@ -163,7 +163,7 @@ int32_t yg_firfilt_crcf_get_scale(yg_firfilt_crcf q, float* scale);
 int32_t yg_firfilt_crcf_get_len(yg_firfilt_crcf q, size_t* h_len);
 int32_t yg_firfilt_crcf_get_device(yg_firfilt_crcf q, int32_t* dev);
 /* which kernel the last execute_block* used: 0 none, 1 generic, 2 register-blocked FFMA2 (<= 256 taps),
- * 4 tensor cores (tcgen05 3xTF32 Toeplitz GEMM, <= 65 taps) */
+ * 4 tensor cores (tcgen05 3xTF32 Toeplitz GEMM, <= 161 taps; the FFMA2 kernel finishes a ragged tail) */
 int32_t yg_firfilt_crcf_last_path(yg_firfilt_crcf q, int32_t* path);
 int32_t yg_firfilt_crcf_execute_block(yg_firfilt_crcf q, const yg_cf32* x, size_t n, yg_cf32* y);
 int32_t yg_firfilt_crcf_execute_block_dev(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf32* d_y,

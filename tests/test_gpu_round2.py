@@ -421,6 +421,11 @@ def test_nccl_gather_of_time_shards_and_channel_major():
     (96, 5000, 63, None, 1.0),                              # ragged length: tensor cores on the first 4608 samples, FFMA2 on 392
     (20, 70002, 17, [0, 70002 - 4000, 70002], 0.25),        # long ragged stream: 8 segments + a 4466-sample tail, then a short call
     (1024, 1 << 12, 63, None, 1.0),                         # more (tile, block) items than CTAs: runs spanning tiles
+    (64, 4096, 66, None, 1.0),                              # 66 .. 97 taps: 32-sample blocks, 3 blocks of history
+    (40, 6144 + 100, 97, [0, 2048, 6244], 0.5),             # ... with state across calls and a ragged tail
+    (64, 1 << 13, 127, None, 1.0),                          # 98 .. 161 taps: 32-sample blocks, 5 blocks of history
+    (16, 3 << 16, 161, [0, 1 << 16, 3 << 16], 1.0),         # the longest filter tensor memory has columns for, long streams
+    (300, 2048, 129, None, 1.0),                            # ragged stream count, the shortest call the variant takes
 ])
 def test_firfilt_tensor_core_path(monkeypatch, S_, N, taps, cuts, scale):
     """The tcgen05 3xTF32 Toeplitz kernel (last_path 4) against an f64 convolution and against the oracle's f32

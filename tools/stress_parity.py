@@ -44,7 +44,7 @@ def stream_objects(rng, budget):
         which = int(rng.integers(0, 3))
         if which == 2:
             # firfilt shapes the tensor-core kernel takes (<= 65 taps, whole 64-sample blocks per segment, >= 2^16 samples)
-            h_len = int(rng.choice([1, 2, 17, 33, 62, 63, 64, 65]))
+            h_len = int(rng.choice([1, 2, 17, 33, 62, 63, 64, 65, 66, 96, 97, 98, 127, 128, 160, 161]))
             N = int(rng.choice([4096, 8192, 512 * 37, 65536, 3 * 8192 * 8, 131072]))
             S_ = int(rng.integers(1, max(2, min(300, (1 << 23) // N))))
             h = (rng.standard_normal(h_len) / np.sqrt(h_len)).astype(np.float32)

@@ -15,7 +15,8 @@ int32_t firfilt_fast_launch(const float* h, size_t h_len, float scale, const flo
 // firfilt_tc.cu: tensor-core (tcgen05, 3xTF32 banded Toeplitz) path for <= 65 taps
 long long firfilt_tc_prefix(size_t h_len, long long n, long long n_streams, const void* x, const void* y);
 int32_t firfilt_tc_plan(const float* h, size_t h_len, float** d_toep);
-int32_t firfilt_tc_launch(const float* d_toep, float scale, const float2* hist, long long Hlen, const float2* x, float2* y,
+bool firfilt_tc_taps_ok(size_t h_len);
+int32_t firfilt_tc_launch(const float* d_toep, size_t h_len, float scale, const float2* hist, long long Hlen, const float2* x, float2* y,
                           long long n, long long pitch, long long n_streams, int n_sm, cudaStream_t st);
 }  // namespace yg
 
@@ -123,7 +124,7 @@ int32_t execute_dev_impl(yg_firfilt_crcf q, const yg_cf32* d_x, size_t n, yg_cf3
     if (n_main > 0) {
         // tcgen05 3xTF32 Toeplitz GEMM (<= 65 taps) on the longest prefix that is whole segments; the FFMA2 kernel
         // finishes the remaining < 8192 (< 512 for short streams) samples of every stream, reading its history from x
-        YG_TRY(firfilt_tc_launch(q->d_toep, q->scale, reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
+        YG_TRY(firfilt_tc_launch(q->d_toep, q->h_len, q->scale, reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
                                  reinterpret_cast<const float2*>(d_x), reinterpret_cast<float2*>(d_y), n_main, (long long)n, S,
                                  q->n_sm, st));
         YG_TRY(firfilt_fast_launch(q->h.data(), q->h_len, q->scale, reinterpret_cast<const float2*>(q->d_hist[q->cur].p), Hlen,
@@ -189,7 +190,7 @@ int32_t build(const float* h, size_t h_len, uint32_t n_streams, yg_firfilt_crcf*
         q->tc_mode = e ? (e[0] != '0') : kFirfiltTcDefault;
         cudaDeviceProp prop;
         CUDAQ(cudaGetDeviceProperties(&prop, dev));
-        if (q->tc_mode && h_len <= 65 && prop.major == 10) TRYQ(firfilt_tc_plan(q->h.data(), h_len, &q->d_toep));
+        if (q->tc_mode && firfilt_tc_taps_ok(h_len) && prop.major == 10) TRYQ(firfilt_tc_plan(q->h.data(), h_len, &q->d_toep));
     }
 #undef TRYQ
 #undef CUDAQ

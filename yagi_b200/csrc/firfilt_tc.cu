@@ -1,11 +1,12 @@
-// firfilt_tc.cu -- batched firfilt_crcf (<= 65 taps) on the 5th-generation tensor cores: 3xTF32 banded-Toeplitz GEMM.
+// firfilt_tc.cu -- batched firfilt_crcf (<= 161 taps) on the 5th-generation tensor cores: 3xTF32 banded-Toeplitz GEMM.
 //
 //   y[s][n] = scale * sum_k h[k] x[s][n-k]                 (src/filter/fir/firfilt.rs:241-245, :267-278)
 //
 // Why: at 63 taps the CUDA-core kernel (firfilt_fast.cu) is FP32-pipe bound -- 126 lane-FMAs per 16 bytes moved, a
 // ceiling of ~0.70 of the HBM roofline -- so the only way up is to take the multiply-adds off the FMA pipe.
 //
-// Formulation (per CTA, M = 128 rows, N = 64 outputs, K = 128 inputs per tile):
+// Formulation (per CTA, M = 128 rows, N = 64 outputs, K = 128 inputs per tile; the numbers below are those of the <= 65-tap
+// instance Cfg<64, 1> -- Cfg<32, 3> and Cfg<32, 5> use 32-sample blocks and 3 / 5 blocks of history for up to 97 / 161 taps):
 //   rows    : 64 streams x {re, im}                -> the A operand, which lives in TENSOR MEMORY (lane = row);
 //   columns : 64 consecutive output times of a tile, stored reversed (column n' <-> time 63 - n');
 //   K       : the 128 input times [64 tau - 64, 64 tau + 64) = the previous and the current 64-sample block;
@@ -47,30 +48,38 @@ namespace {
 
 using namespace yg::dev;
 
-constexpr int kBlk = 64;                      // samples per block = outputs per tile (N)
-constexpr int kRows = 128;                    // 64 streams x {re, im} (M)
-constexpr int kStreamsPerGroup = 64;           // rows / 2 of a tile: 8 streams x 8 time segments
+constexpr int kRows = 128;                    // 64 (stream, segment) rows x {re, im} (M of the MMA)
 constexpr int kTileStreams = 8, kTileSegs = 8;
-constexpr int kStages = 4;                    // input ring
-constexpr int kStageBytes = kBlk * kStreamsPerGroup * 8;      // 32 KB
-constexpr int kSubBytes = kStageBytes / 4;                    // one TMA box: 16 samples x 64 streams
-constexpr int kToepBytes = 23 * 256;                          // aliased Toeplitz table (one of hi / lo)
+constexpr int kSubBytes = 16 * 64 * 8;        // one TMA box: 16 samples x 64 rows = 8 KB
 constexpr int kThreads = 320;
-constexpr int kSmemIn = 0;
-constexpr int kSmemOut = kSmemIn + kStages * kStageBytes;     // 2 staging buffers
-constexpr int kSmemToep = kSmemOut + 2 * kStageBytes;         // hi table, lo table
-constexpr int kSmemBar = kSmemToep + 2 * kToepBytes;
-constexpr int kSmemBytes = kSmemBar + 256 + 1024;             // + alignment slack
-// mbarrier slots
-constexpr int kBarInFull = 0;                 // [4]
-constexpr int kBarInEmpty = 4;                // [4]
-constexpr int kBarAFull = 8;                  // [3]
-constexpr int kBarAFree = 11;                 // [3]
-constexpr int kBarDFull = 14;                 // [2]
-constexpr int kBarDEmpty = 16;                // [2]
-constexpr int kNumBars = 18;
-// TMEM columns
-constexpr uint32_t kColHi = 0, kColLo = 192, kColD = 384;
+
+// Geometry of one instantiation: blocks of kBlk samples (= outputs per tile, N of the MMA) and kHB blocks of history, so the
+// K window is (kHB + 1) kBlk samples and filters of up to kHB kBlk + 1 taps fit.  TMEM holds kHB + 2 blocks of A (hi) + as
+// many (lo) + two accumulators: 2 (kHB + 2) kBlk + 2 kBlk <= 512 columns.
+//   <64, 1>: up to  65 taps, K = 128 (BASELINE config #2)        <32, 3>: up to 97 taps, K = 128        <32, 5>: up to 161 taps, K = 192
+template <int kBlk_, int kHB_>
+struct Cfg {
+    static constexpr int kBlk = kBlk_, kHB = kHB_;
+    static constexpr int kSlots = kHB + 2;                               // ring of A blocks
+    static constexpr int kKSteps = (kHB + 1) * kBlk / 8;                 // MMAs (x 3) per tile
+    static constexpr int kSub = kBlk / 16;                               // TMA boxes per block
+    static constexpr int kStageBytes = kBlk * 64 * 8;
+    static constexpr int kStages = 131072 / kStageBytes;                 // 128 KB of input ring
+    static constexpr int kToepBytes = (kBlk / 8 + kKSteps - 1) * 256;    // aliased Toeplitz table (one of hi / lo)
+    static constexpr int kSmemIn = 0;
+    static constexpr int kSmemOut = kSmemIn + kStages * kStageBytes;     // 2 staging buffers
+    static constexpr int kSmemToep = kSmemOut + 2 * kStageBytes;         // hi table, lo table
+    static constexpr int kSmemBar = kSmemToep + 2 * kToepBytes;
+    // mbarrier slots
+    static constexpr int kBarInFull = 0, kBarInEmpty = kStages, kBarAFull = 2 * kStages, kBarAFree = kBarAFull + kSlots,
+                         kBarDFull = kBarAFree + kSlots, kBarDEmpty = kBarDFull + 2, kNumBars = kBarDEmpty + 2;
+    static constexpr int kSmemBytes = kSmemBar + 8 * kNumBars + 64 + 1024;          // + TMEM slot + alignment slack
+    // TMEM columns
+    static constexpr uint32_t kColHi = 0, kColLo = kSlots * kBlk, kColD = 2 * kSlots * kBlk;
+    static_assert(kColD + 2 * kBlk <= 512, "tensor memory holds 512 columns");
+    static_assert(kBlk == 32 || kBlk == 64, "blocks of 32 or 64 samples");
+    static constexpr int kMaxTaps = kHB * kBlk + 1;
+};
 
 struct TcParams {
     const float2* hist;       // [n_streams][Hlen], oldest first (the object's state), or null
@@ -157,13 +166,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
            (1ull << 46);                      // descriptor version 1 (sm_100); base offset 0, layout type 0 = no swizzle
 }
 // kind::tf32, f32 accumulate, A and B K-major, N = 64, M = 128 (cute::UMMA::InstrDescriptor bit layout)
-constexpr uint32_t idesc_n(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24); }
-constexpr uint32_t kIdesc = idesc_n(kBlk), kIdescHalf = idesc_n(kBlk / 2);
+__host__ __device__ constexpr uint32_t idesc_n(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24); }
 
-// The walk every role performs: the CTA's items [e0, e1) of the (group, block) grid, cut into runs inside one group;
-// a run starts with a priming step for the block before it.  step(group, block, prime) is called in the same order by
+// The walk every role performs: the CTA's items [e0, e1) of the (tile, block) grid, cut into runs inside one tile;
+// a run starts with kHB priming steps for the blocks before it.  step(tile, block, prime) is called in the same order by
 // every role, so running counters (blocks converted, tiles produced) agree across roles.
-template <typename Step>
+template <int kHB, typename Step>
 __device__ __forceinline__ void walk(long long e0, long long e1, long long n_blocks, Step&& step)
 {
     long long e = e0;
@@ -171,19 +179,22 @@ __device__ __forceinline__ void walk(long long e0, long long e1, long long n_blo
         const int g = (int)(e / n_blocks);
         long long b = e - (long long)g * n_blocks;
         const long long run_end = (e1 < (long long)(g + 1) * n_blocks) ? e1 : (long long)(g + 1) * n_blocks;
-        step(g, b - 1, true);
+#pragma unroll
+        for (int i = kHB; i >= 1; i--) step(g, b - i, true);
         for (; e < run_end; e++, b++) step(g, b, false);
     }
 }
 
+template <class C>
 __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constant__ CUtensorMap tm_in,
                                                              const __grid_constant__ CUtensorMap tm_out, const TcParams p)
 {
+    constexpr int kBlk = C::kBlk, kHB = C::kHB, kSlots = C::kSlots, kStages = C::kStages, kStageBytes = C::kStageBytes;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;             // the 128-byte swizzle wants 1024-byte alignment
     unsigned char* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
-    const uint32_t bar0 = smem + kSmemBar;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kSmemBar + 8 * kNumBars);
+    const uint32_t bar0 = smem + C::kSmemBar;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + C::kSmemBar + 8 * C::kNumBars);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // warp index, provably uniform
 
     const long long total = (long long)p.n_groups * p.n_blocks;
@@ -191,14 +202,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; i++) { mbar_init(bar0 + 8 * (kBarInFull + i), 1); mbar_init(bar0 + 8 * (kBarInEmpty + i), 4); }
-        for (int i = 0; i < 3; i++) { mbar_init(bar0 + 8 * (kBarAFull + i), 4); mbar_init(bar0 + 8 * (kBarAFree + i), 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(bar0 + 8 * (kBarDFull + i), 1); mbar_init(bar0 + 8 * (kBarDEmpty + i), 4); }
+        for (int i = 0; i < kStages; i++) { mbar_init(bar0 + 8 * (C::kBarInFull + i), 1); mbar_init(bar0 + 8 * (C::kBarInEmpty + i), 4); }
+        for (int i = 0; i < kSlots; i++) { mbar_init(bar0 + 8 * (C::kBarAFull + i), 4); mbar_init(bar0 + 8 * (C::kBarAFree + i), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(bar0 + 8 * (C::kBarDFull + i), 1); mbar_init(bar0 + 8 * (C::kBarDEmpty + i), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {   // Toeplitz tables (hi, lo) -> shared memory; the tensor core reads them through the async proxy
-        float* dst = reinterpret_cast<float*>(smem_gen + kSmemToep);
-        for (int i = threadIdx.x; i < 2 * kToepBytes / 4; i += kThreads) dst[i] = __ldg(&p.toep[i]);
+        float* dst = reinterpret_cast<float*>(smem_gen + C::kSmemToep);
+        for (int i = threadIdx.x; i < 2 * C::kToepBytes / 4; i += kThreads) dst[i] = __ldg(&p.toep[i]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 9) {
@@ -213,21 +224,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
     if (warp == 8) {
         // ================================================================= TMA producer (warp-uniform loop, one elected lane issues)
         long long k = 0;
-        walk(e0, e1, p.n_blocks, [&](int g, long long b, bool) {
+        walk<kHB>(e0, e1, p.n_blocks, [&](int g, long long b, bool) {
             const int st = (int)(k % kStages);
-            const uint32_t full = bar0 + 8 * (kBarInFull + st);
-            if (k >= kStages) mbar_wait(bar0 + 8 * (kBarInEmpty + st), (uint32_t)(((k / kStages) - 1) & 1));
+            const uint32_t full = bar0 + 8 * (C::kBarInFull + st);
+            if (k >= kStages) mbar_wait(bar0 + 8 * (C::kBarInEmpty + st), (uint32_t)(((k / kStages) - 1) & 1));
             if (elect_one()) {
                 mbar_expect_tx(full, kStageBytes);
-                const uint32_t dst = smem + kSmemIn + st * kStageBytes;
-#pragma unroll
-                // coordinates: (float inside the segment, segment of the stream, stream).  The block before a segment's first
-                // one is the last block of the segment before it (segment -1 does not exist: zero-filled by the hardware).
+                const uint32_t dst = smem + C::kSmemIn + st * kStageBytes;
+                // coordinates: (float inside the segment, segment of the stream, stream).  The blocks before a segment's first
+                // one are the last blocks of the segment before it (segment -1 does not exist: zero-filled by the hardware).
                 const int c2 = (g / p.seg_groups) * kTileStreams;
                 const int c1 = (g % p.seg_groups) * kTileSegs - (b < 0 ? 1 : 0);
-                const int c0 = (b < 0) ? p.q_floats - 2 * kBlk : (int)(2 * kBlk * b);
+                const int c0 = (b < 0 ? p.q_floats : 0) + (int)(2 * kBlk * b);
 #pragma unroll
-                for (int j = 0; j < 4; j++) tma_load_3d(dst + j * kSubBytes, &tm_in, c0 + 32 * j, c1, c2, full);
+                for (int j = 0; j < C::kSub; j++) tma_load_3d(dst + j * kSubBytes, &tm_in, c0 + 32 * j, c1, c2, full);
             }
             __syncwarp();
             k++;
@@ -235,63 +245,78 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
     } else if (warp == 9) {
         // ================================================================= MMA issuer (warp-uniform loop, one elected lane issues)
         long long k = 0, u = 0;
-        const uint32_t toep_hi = smem + kSmemToep, toep_lo = toep_hi + kToepBytes;
-        walk(e0, e1, p.n_blocks, [&](int, long long, bool prime) {
-            const int slot = (int)(k % 3);
-            mbar_wait(bar0 + 8 * (kBarAFull + slot), (uint32_t)((k / 3) & 1));
+        const uint32_t toep_hi = smem + C::kSmemToep, toep_lo = toep_hi + C::kToepBytes;
+        walk<kHB>(e0, e1, p.n_blocks, [&](int, long long, bool prime) {
+            const int slot = (int)(k % kSlots);
+            mbar_wait(bar0 + 8 * (C::kBarAFull + slot), (uint32_t)((k / kSlots) & 1));
             tc_fence_after();
             if (!prime) {
                 const int db = (int)(u & 1);
-                if (u >= 2) { mbar_wait(bar0 + 8 * (kBarDEmpty + db), (uint32_t)(((u >> 1) - 1) & 1)); tc_fence_after(); }
-                const uint32_t d = tmem + kColD + kBlk * db;
-                const uint32_t col_prev = (uint32_t)(kBlk * ((slot + 2) % 3)), col_cur = (uint32_t)(kBlk * slot);
+                if (u >= 2) { mbar_wait(bar0 + 8 * (C::kBarDEmpty + db), (uint32_t)(((u >> 1) - 1) & 1)); tc_fence_after(); }
+                const uint32_t d = tmem + C::kColD + kBlk * db;
+                const int oldest = (slot + 2) % kSlots;                    // slot of block k - kHB (kSlots = kHB + 2)
                 if (elect_one()) {
-                    // B[k][n'] is zero unless 63 <= n' + k <= 127: K steps 0-3 (k < 32) touch only the columns n' >= 32 and
-                    // K steps 12-15 (k >= 96) only n' < 32, so those eight steps are issued at half width (N = 32: half the
-                    // tensor-pipe time); the full-width steps 4-11 come first so that one of them initialises the accumulator.
+                    if constexpr (kBlk == 64 && kHB == 1) {
+                        // B[k][n'] is zero unless 63 <= n' + k <= 127: K steps 0-3 (k < 32) touch only the columns n' >= 32 and
+                        // K steps 12-15 (k >= 96) only n' < 32, so those eight steps are issued at half width (N = 32: half the
+                        // tensor-pipe time); the full-width steps 4-11 come first so that one of them initialises the accumulator.
+                        const uint32_t col_prev = (uint32_t)(kBlk * oldest), col_cur = (uint32_t)(kBlk * slot);
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const int s = (i < 8) ? i + 4 : (i < 12 ? i - 8 : i);              // 4..11, 0..3, 12..15
-                        const uint32_t col = (s < 8) ? col_prev + 8 * s : col_cur + 8 * (s - 8);
-                        const bool upper = s < 4, lower = s >= 12;
-                        const uint32_t boff = 256u * s + (upper ? 4u * 256u : 0u);         // n' group 4 = +4 SBO
-                        const uint64_t bh = smem_desc(toep_hi + boff, 128, 256), bl = smem_desc(toep_lo + boff, 128, 256);
-                        const uint32_t dd = d + (upper ? 32u : 0u);
-                        const uint32_t id = (upper || lower) ? kIdescHalf : kIdesc;
-                        tc_mma_ts(dd, tmem + kColLo + col, bh, id, i > 0 ? 1u : 0u);       // small terms first
-                        tc_mma_ts(dd, tmem + kColHi + col, bl, id, 1u);
-                        tc_mma_ts(dd, tmem + kColHi + col, bh, id, 1u);
+                        for (int i = 0; i < 16; i++) {
+                            const int s = (i < 8) ? i + 4 : (i < 12 ? i - 8 : i);              // 4..11, 0..3, 12..15
+                            const uint32_t col = (s < 8) ? col_prev + 8 * s : col_cur + 8 * (s - 8);
+                            const bool upper = s < 4, lower = s >= 12;
+                            const uint32_t boff = 256u * s + (upper ? 4u * 256u : 0u);         // n' group 4 = +4 SBO
+                            const uint64_t bh = smem_desc(toep_hi + boff, 128, 256), bl = smem_desc(toep_lo + boff, 128, 256);
+                            const uint32_t dd = d + (upper ? 32u : 0u);
+                            const uint32_t id = (upper || lower) ? idesc_n(kBlk / 2) : idesc_n(kBlk);
+                            tc_mma_ts(dd, tmem + C::kColLo + col, bh, id, i > 0 ? 1u : 0u);    // small terms first
+                            tc_mma_ts(dd, tmem + C::kColHi + col, bl, id, 1u);
+                            tc_mma_ts(dd, tmem + C::kColHi + col, bh, id, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < C::kKSteps; s++) {
+                            constexpr int kPerBlock = kBlk / 8;                                // K steps per block of A
+                            int sl = oldest + s / kPerBlock;                                   // ring slot of the block this step reads
+                            if (sl >= kSlots) sl -= kSlots;
+                            const uint32_t col = (uint32_t)(kBlk * sl + 8 * (s % kPerBlock));
+                            const uint64_t bh = smem_desc(toep_hi + 256u * s, 128, 256), bl = smem_desc(toep_lo + 256u * s, 128, 256);
+                            tc_mma_ts(d, tmem + C::kColLo + col, bh, idesc_n(kBlk), s > 0 ? 1u : 0u);
+                            tc_mma_ts(d, tmem + C::kColHi + col, bl, idesc_n(kBlk), 1u);
+                            tc_mma_ts(d, tmem + C::kColHi + col, bh, idesc_n(kBlk), 1u);
+                        }
                     }
-                    tc_commit(bar0 + 8 * (kBarDFull + db));
+                    tc_commit(bar0 + 8 * (C::kBarDFull + db));
                 }
                 __syncwarp();
                 u++;
             }
-            if (k >= 1) {
-                if (elect_one()) tc_commit(bar0 + 8 * (kBarAFree + (int)((k - 1) % 3)));     // the block before this one is no longer read
+            if (k >= kHB) {                                                // block k - kHB is no longer read by any later tile
+                if (elect_one()) tc_commit(bar0 + 8 * (C::kBarAFree + (int)((k - kHB) % kSlots)));
                 __syncwarp();
             }
             k++;
         });
     } else if (warp < 4) {
-        // ================================================================= converter: thread = row (stream, component)
+        // ================================================================= converter: thread = row (stream, segment, component)
         const int row = threadIdx.x;
-        const int sl = row >> 1, c = row & 1;                   // stream inside the group, component
+        const int sl = row >> 1, c = row & 1;                   // (stream, segment) row inside the tile, component
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        // byte offset of this stream's 128-byte row inside a box; chunk u of the row sits at ((u ^ (sl & 7)) << 4)
+        // byte offset of this row's 128-byte line inside a box; chunk u of the line sits at ((u ^ (sl & 7)) << 4)
         const uint32_t row_off = (uint32_t)sl * 128u;
         long long k = 0;
-        walk(e0, e1, p.n_blocks, [&](int g, long long b, bool) {
+        walk<kHB>(e0, e1, p.n_blocks, [&](int g, long long b, bool) {
             const int st = (int)(k % kStages);
-            const int slot = (int)(k % 3);
-            mbar_wait(bar0 + 8 * (kBarInFull + st), (uint32_t)((k / kStages) & 1));
-            const uint32_t src = smem + kSmemIn + st * kStageBytes + row_off;
+            const int slot = (int)(k % kSlots);
+            mbar_wait(bar0 + 8 * (C::kBarInFull + st), (uint32_t)((k / kStages) & 1));
+            const uint32_t src = smem + C::kSmemIn + st * kStageBytes + row_off;
             // row sl of the tile = (stream sl / 8, segment sl % 8) of the tile's 8 x 8 patch
             const long long s_glob = (long long)(g / p.seg_groups) * kTileStreams + (sl >> 3);
             const int seg_glob = (g % p.seg_groups) * kTileSegs + (sl & 7);
             const bool from_hist = (b < 0) && seg_glob == 0 && p.hist != nullptr && s_glob < p.n_streams;
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
+            for (int half = 0; half < kBlk / 32; half++) {
                 uint32_t hi[32], lo[32];
                 if (!from_hist) {
 #pragma unroll
@@ -306,61 +331,62 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
                         lo[2 * q + 1] = __float_as_uint(v1 - __uint_as_float(h1));
                     }
                 } else {
-                    // first block of the call: the 64 samples before it are the object's history (oldest first, Hlen <= 64)
+                    // blocks before the first one of the call: the object's history (oldest first, Hlen <= kHB kBlk samples)
                     const float* hp = reinterpret_cast<const float*>(p.hist + s_glob * p.Hlen);
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
-                        const int idx = p.Hlen - kBlk + 32 * half + i;
+                        const int idx = p.Hlen + (int)b * kBlk + 32 * half + i;          // b < 0
                         const float v = (idx >= 0) ? __ldg(hp + 2 * idx + c) : 0.0f;
                         const uint32_t h0 = tf32_hi(v);
                         hi[i] = h0;
                         lo[i] = __float_as_uint(v - __uint_as_float(h0));
                     }
                 }
-                if (half == 0 && k >= 3) {       // the MMAs that read this ring slot's previous block have completed
-                    mbar_wait(bar0 + 8 * (kBarAFree + slot), (uint32_t)(((k / 3) - 1) & 1));
+                if (half == 0 && k >= kSlots) {  // the MMAs that read this ring slot's previous block have completed
+                    mbar_wait(bar0 + 8 * (C::kBarAFree + slot), (uint32_t)(((k / kSlots) - 1) & 1));
                     tc_fence_after();
                 }
                 __syncwarp();
-                tmem_st32(lane_base + kColHi + kBlk * slot + 32 * half, hi);
-                tmem_st32(lane_base + kColLo + kBlk * slot + 32 * half, lo);
+                tmem_st32(lane_base + C::kColHi + kBlk * slot + 32 * half, hi);
+                tmem_st32(lane_base + C::kColLo + kBlk * slot + 32 * half, lo);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(bar0 + 8 * (kBarInEmpty + st));
-                mbar_arrive(bar0 + 8 * (kBarAFull + slot));
+                mbar_arrive(bar0 + 8 * (C::kBarInEmpty + st));
+                mbar_arrive(bar0 + 8 * (C::kBarAFull + slot));
             }
             k++;
         });
     } else {
-        // ================================================================= epilogue: thread = row (stream, component)
+        // ================================================================= epilogue: thread = row (stream, segment, component)
         const int row = threadIdx.x - 128;
         const int sl = row >> 1, c = row & 1;
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t row_off = (uint32_t)sl * 128u + 4u * c;
+        const bool issuer = lane == 0 && (warp & 3) < C::kSub;      // one box per epilogue warp, issued (and its bulk group owned) by lane 0
         long long u = 0;
-        walk(e0, e1, p.n_blocks, [&](int g, long long b, bool prime) {
+        walk<kHB>(e0, e1, p.n_blocks, [&](int g, long long b, bool prime) {
             if (prime) return;
             const int db = (int)(u & 1);
-            mbar_wait(bar0 + 8 * (kBarDFull + db), (uint32_t)((u >> 1) & 1));
+            mbar_wait(bar0 + 8 * (C::kBarDFull + db), (uint32_t)((u >> 1) & 1));
             tc_fence_after();
-            uint32_t d0[32], d1[32];
-            tmem_ld32(lane_base + kColD + kBlk * db, d0);           // columns n' = 0..31  <-> times 63..32
-            tmem_ld32(lane_base + kColD + kBlk * db + 32, d1);      // columns n' = 32..63 <-> times 31..0
+            uint32_t dv[kBlk / 32][32];                             // column n' of the tile <-> time kBlk - 1 - n'
+#pragma unroll
+            for (int h = 0; h < kBlk / 32; h++) tmem_ld32(lane_base + C::kColD + kBlk * db + 32 * h, dv[h]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar0 + 8 * (kBarDEmpty + db));
+            if (lane == 0) mbar_arrive(bar0 + 8 * (C::kBarDEmpty + db));
             // the staging buffer was last used two tiles ago: its bulk store must have finished reading it
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
             // 16 rows x 2 components per warp: rows v and v + 8 share a swizzle key, so in each store the upper eight rows
             // take the other sample of the 16-byte chunk (flip) -- all 32 lanes then hit distinct banks.
-            const uint32_t dst = smem + kSmemOut + db * kStageBytes + row_off;
+            const uint32_t dst = smem + C::kSmemOut + db * kStageBytes + row_off;
             const bool flip = (sl >> 3) & 1;
-            auto tile_val = [&](int t) { return (t < 32) ? d1[31 - t] : d0[63 - t]; };        // time t of the tile (columns are reversed)
+            auto tile_val = [&](int t) { return dv[(kBlk - 1 - t) >> 5][(kBlk - 1 - t) & 31]; };
 #pragma unroll
             for (int tt = 0; tt < kBlk; tt += 2) {
                 const uint32_t a = dst + (uint32_t)(tt >> 4) * kSubBytes + ((uint32_t)(((tt & 15) >> 1) ^ (sl & 7)) << 4);
@@ -372,11 +398,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            {                                // one box per epilogue warp, issued by its lane 0 (which also owns the bulk group)
+            {
                 const int j = warp & 3;
-                const uint32_t src = smem + kSmemOut + db * kStageBytes + j * kSubBytes;
+                const uint32_t src = smem + C::kSmemOut + db * kStageBytes + j * kSubBytes;
                 const int c0 = (int)(2 * kBlk * b) + 32 * j, c1 = (g % p.seg_groups) * kTileSegs, c2 = (g / p.seg_groups) * kTileStreams;
-                if (lane == 0) {
+                if (issuer) {
                     tma_store_3d(&tm_out, c0, c1, c2, src);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
@@ -384,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
             }
             u++;
         });
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     // ---- teardown
@@ -452,50 +478,51 @@ float tf32_rna(float v)
     return r;
 }
 
-}  // namespace
+using Cfg65 = Cfg<64, 1>;       // up to 65 taps (BASELINE config #2)
+using Cfg97 = Cfg<32, 3>;       // up to 97 taps
+using Cfg161 = Cfg<32, 5>;      // up to 161 taps
 
-// The longest prefix of an n-sample stream the kernel takes: whole 8192-sample segments of long streams, an eighth of the
-// prefix per segment (whole 64-sample blocks) for short ones; 0 if it takes nothing.
-long long firfilt_tc_prefix(size_t h_len, long long n, long long n_streams, const void* x, const void* y)
+// shortest segment a variant accepts: whole blocks, and the kHB blocks of history must lie inside the previous segment
+template <class C> constexpr long long min_segment() { return C::kBlk == 64 ? 64 : 256; }
+
+template <class C>
+long long prefix_t(long long n)
 {
-    if (h_len < 1 || h_len > 65) return 0;
-    if (n & 1) return 0;                                                   // row pitch must be a multiple of 16 bytes
-    if (n >= (1LL << 29) || n_streams > 0x7fffffffLL) return 0;            // int32 box coordinates
-    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return 0;
     const long long q_long = segment_len(1LL << 40);
-    const long long unit = (n >= kTileSegs * q_long) ? q_long : (long long)kTileSegs * kBlk;
+    const long long unit = (n >= kTileSegs * q_long) ? q_long : (long long)kTileSegs * min_segment<C>();
     const long long n_main = n / unit * unit;
-    if (n_main < kTileSegs * kBlk) return 0;
-    if (n_main * n_streams < (1LL << 16)) return 0;                        // tiny calls: not worth 148 persistent CTAs
-    return encode_tiled() != nullptr ? n_main : 0;
+    return n_main >= kTileSegs * min_segment<C>() ? n_main : 0;
 }
 
-// Builds the aliased Toeplitz tables for taps h (device buffer of 2 * kToepBytes bytes).
-int32_t firfilt_tc_plan(const float* h, size_t h_len, float** d_toep)
+// Aliased Toeplitz tables (hi, lo) for taps h: the entry at byte A of a table is B at n' + k = 8 (A >> 8) + 4 (A >> 7 & 1)
+// + (A >> 4 & 7) + (A >> 2 & 3), i.e. tap (kHB + 1) kBlk - 1 - (n' + k).
+template <class C>
+int32_t plan_t(const float* h, size_t h_len, float** d_toep)
 {
-    std::vector<float> t(2 * kToepBytes / 4, 0.0f);
-    for (int A = 0; A < kToepBytes; A += 4) {
+    std::vector<float> t(2 * C::kToepBytes / 4, 0.0f);
+    for (int A = 0; A < C::kToepBytes; A += 4) {
         const int v = 8 * (A >> 8) + 4 * ((A >> 7) & 1) + ((A >> 4) & 7) + ((A >> 2) & 3);      // n' + k
-        const int j = 127 - v;
+        const int j = (C::kHB + 1) * C::kBlk - 1 - v;
         if (j >= 0 && j < (int)h_len) {
             const float hi = tf32_rna(h[j]);
             t[A / 4] = hi;
-            t[kToepBytes / 4 + A / 4] = h[j] - hi;
+            t[C::kToepBytes / 4 + A / 4] = h[j] - hi;
         }
     }
     if (!*d_toep) YG_CUDA(cudaMalloc(d_toep, t.size() * sizeof(float)));
     YG_CUDA(memcpy_sync(*d_toep, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
-    YG_CUDA(cudaFuncSetAttribute(k_firfilt_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    YG_CUDA(cudaFuncSetAttribute(k_firfilt_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     return YG_OK;
 }
 
-// Outputs [0, n) of every stream; rows of x and y are `pitch` samples apart (pitch >= n, even).
-int32_t firfilt_tc_launch(const float* d_toep, float scale, const float2* hist, long long Hlen, const float2* x, float2* y,
-                          long long n, long long pitch, long long n_streams, int n_sm, cudaStream_t st)
+template <class C>
+int32_t launch_t(const float* d_toep, float scale, const float2* hist, long long Hlen, const float2* x, float2* y,
+                 long long n, long long pitch, long long n_streams, int n_sm, cudaStream_t st)
 {
     CUtensorMap tm_in, tm_out;
     const long long Q = segment_len(n);
-    if (Q < kBlk || Q % kBlk != 0 || n % Q != 0) return fail(YG_EINTERNAL, "tensor-core firfilt: %lld samples are not whole segments", n);
+    if (Q < min_segment<C>() || Q % C::kBlk != 0 || n % Q != 0)
+        return fail(YG_EINTERNAL, "tensor-core firfilt: %lld samples are not whole segments", n);
     YG_TRY(make_map(&tm_in, x, n, pitch, n_streams, Q));
     YG_TRY(make_map(&tm_out, y, n, pitch, n_streams, Q));
     TcParams p;
@@ -505,15 +532,48 @@ int32_t firfilt_tc_launch(const float* d_toep, float scale, const float2* hist, 
     p.n_streams = (int)n_streams;
     p.scale = scale;
     p.toep = d_toep;
-    p.n_blocks = Q / kBlk;
+    p.n_blocks = Q / C::kBlk;
     p.seg_groups = (int)((n / Q + kTileSegs - 1) / kTileSegs);
     p.n_groups = (int)((n_streams + kTileStreams - 1) / kTileStreams) * p.seg_groups;
     p.q_floats = (int)(2 * Q);
     const long long total = p.n_blocks * p.n_groups;
     const int grid = (int)std::min<long long>(n_sm, total);
-    k_firfilt_tc<<<grid, kThreads, kSmemBytes, st>>>(tm_in, tm_out, p);
+    k_firfilt_tc<C><<<grid, kThreads, C::kSmemBytes, st>>>(tm_in, tm_out, p);
     YG_LAUNCH_CHECK();
     return YG_OK;
+}
+
+}  // namespace
+
+bool firfilt_tc_taps_ok(size_t h_len) { return h_len >= 1 && h_len <= (size_t)Cfg161::kMaxTaps; }
+
+// The longest prefix of an n-sample stream the kernel takes: whole 8192-sample segments of long streams, an eighth of the
+// prefix per segment (whole blocks, history inside the previous segment) for short ones; 0 if it takes nothing.
+long long firfilt_tc_prefix(size_t h_len, long long n, long long n_streams, const void* x, const void* y)
+{
+    if (!firfilt_tc_taps_ok(h_len)) return 0;
+    if (n & 1) return 0;                                                   // row pitch must be a multiple of 16 bytes
+    if (n >= (1LL << 29) || n_streams > 0x7fffffffLL) return 0;            // int32 box coordinates
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return 0;
+    const long long n_main = h_len <= (size_t)Cfg65::kMaxTaps ? prefix_t<Cfg65>(n) : h_len <= (size_t)Cfg97::kMaxTaps ? prefix_t<Cfg97>(n) : prefix_t<Cfg161>(n);
+    if (n_main * n_streams < (1LL << 16)) return 0;                        // tiny calls: not worth 148 persistent CTAs
+    return encode_tiled() != nullptr ? n_main : 0;
+}
+
+int32_t firfilt_tc_plan(const float* h, size_t h_len, float** d_toep)
+{
+    if (h_len <= (size_t)Cfg65::kMaxTaps) return plan_t<Cfg65>(h, h_len, d_toep);
+    if (h_len <= (size_t)Cfg97::kMaxTaps) return plan_t<Cfg97>(h, h_len, d_toep);
+    return plan_t<Cfg161>(h, h_len, d_toep);
+}
+
+// Outputs [0, n) of every stream; rows of x and y are `pitch` samples apart (pitch >= n, even).
+int32_t firfilt_tc_launch(const float* d_toep, size_t h_len, float scale, const float2* hist, long long Hlen, const float2* x, float2* y,
+                          long long n, long long pitch, long long n_streams, int n_sm, cudaStream_t st)
+{
+    if (h_len <= (size_t)Cfg65::kMaxTaps) return launch_t<Cfg65>(d_toep, scale, hist, Hlen, x, y, n, pitch, n_streams, n_sm, st);
+    if (h_len <= (size_t)Cfg97::kMaxTaps) return launch_t<Cfg97>(d_toep, scale, hist, Hlen, x, y, n, pitch, n_streams, n_sm, st);
+    return launch_t<Cfg161>(d_toep, scale, hist, Hlen, x, y, n, pitch, n_streams, n_sm, st);
 }
 
 }  // namespace yg
