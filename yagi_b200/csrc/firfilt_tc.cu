@@ -7,7 +7,8 @@
 //
 // Formulation (per CTA, M = 128 rows, N = 64 outputs, K = 128 inputs per tile; the numbers below are those of the <= 65-tap
 // instance Cfg<64, 1> -- Cfg<32, 3> and Cfg<32, 5> use 32-sample blocks and 3 / 5 blocks of history for up to 97 / 161 taps):
-//   rows    : 64 streams x {re, im}                -> the A operand, which lives in TENSOR MEMORY (lane = row);
+//   rows    : 8 streams x 8 adjacent time segments of each (independent rows, each primed with the block before it)
+//             x {re, im}                           -> the A operand, which lives in TENSOR MEMORY (lane = row);
 //   columns : 64 consecutive output times of a tile, stored reversed (column n' <-> time 63 - n');
 //   K       : the 128 input times [64 tau - 64, 64 tau + 64) = the previous and the current 64-sample block;
 //   B[k][n']: h[127 - (n' + k)] (zero outside 0 .. h_len-1): a Toeplitz band.  Because it depends on n' + k only,
@@ -19,19 +20,19 @@
 //             truncation of the lo parts are ~2^-22 relative): 48 tcgen05.mma (128 x 64 x 8, kind::tf32) per tile.
 //
 // Pipeline (one persistent CTA per SM, 320 threads, all 512 TMEM columns):
-//   warp 8  TMA producer : cp.async.bulk.tensor 2-D boxes {16 samples, 64 streams} x 4 per 64-sample block into a
-//                          4-stage shared ring, 128-byte swizzle; out-of-range boxes (before the stream start, past
-//                          its end, past the last stream) are zero-filled / clipped by the hardware.
+//   warp 8  TMA producer : cp.async.bulk.tensor 3-D boxes {16 samples, 8 segments, 8 streams} x 4 per 64-sample block
+//                          into a 4-stage shared ring, 128-byte swizzle; out-of-range boxes (before the stream start,
+//                          past the last segment or stream) are zero-filled / clipped by the hardware.
 //   warps 0-3 converter  : thread = row: reads its 64 samples of the block (conflict-free LDS.128 through the swizzle),
 //                          splits them into TF32 hi / lo and writes them to its TMEM lane with tcgen05.st, into a ring
 //                          of three 64-column blocks (hi) + three (lo).
-//   warp 9  MMA issuer   : one thread issues the 48 MMAs of a tile (A from TMEM, B descriptors into the aliased
-//                          table) into one of two 64-column accumulators; tcgen05.commit signals the epilogue and
-//                          hands the oldest A block back to the converter.
+//   warp 9  MMA issuer   : one elected lane (warp-uniform control flow, so the operands are provably uniform) issues the 48
+//                          MMAs of a tile (A from TMEM, B descriptors into the aliased table) into one of two 64-column
+//                          accumulators; tcgen05.commit signals the epilogue and hands the oldest A block back to the converter.
 //   warps 4-7 epilogue   : tcgen05.ld the accumulator, scale, write the tile to a swizzled staging buffer and store
 //                          it with cp.async.bulk.tensor (shared -> global).
-// A CTA walks a contiguous range of (stream group, block) items; every run inside a group starts with one priming
-// block (the 64 samples before it: the previous block, or the object's history for the first block of a call).
+// A CTA walks a contiguous range of (tile, block) items; every run inside a tile starts with kHB priming blocks (the
+// samples before it: earlier blocks, the tail of the previous segment, or the object's history at the start of a call).
 #include "common.cuh"
 #include "fused_common.cuh"
 
