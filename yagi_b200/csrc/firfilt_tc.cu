@@ -458,16 +458,10 @@ int32_t make_map(CUtensorMap* tm, const float2* base, long long n, long long pit
     return YG_OK;
 }
 
-// segment length: 8192 samples (64 KB) for long streams, an eighth of the stream for short ones
-long long segment_len(long long n)
-{
-    static const long long q_long = [] {            // YG_TC_SEG: segment length for long streams (tuning knob, default 8192)
-        const char* e = getenv("YG_TC_SEG");
-        const long long v = e ? atoll(e) : 0;
-        return (v >= 64 && v % 64 == 0) ? v : 8192LL;
-    }();
-    return n >= 8 * q_long ? q_long : n / kTileSegs;
-}
+// segment length: 8192 samples (64 KB) for long streams (1 K .. 128 K measured: no difference, profiles/r02_firfilt_tc_sweeps.log),
+// an eighth of the stream for short ones
+constexpr long long kLongSegment = 8192;
+long long segment_len(long long n) { return n >= kTileSegs * kLongSegment ? kLongSegment : n / kTileSegs; }
 
 float tf32_rna(float v)
 {
@@ -489,8 +483,7 @@ template <class C> constexpr long long min_segment() { return C::kBlk == 64 ? 64
 template <class C>
 long long prefix_t(long long n)
 {
-    const long long q_long = segment_len(1LL << 40);
-    const long long unit = (n >= kTileSegs * q_long) ? q_long : (long long)kTileSegs * min_segment<C>();
+    const long long unit = (n >= kTileSegs * kLongSegment) ? kLongSegment : (long long)kTileSegs * min_segment<C>();
     const long long n_main = n / unit * unit;
     return n_main >= kTileSegs * min_segment<C>() ? n_main : 0;
 }
