@@ -173,8 +173,8 @@ def reference_arm(args):
     if rank != 0:
         return 0
     threads = cpu_threads()
-    n_per_thread = 1 << 21
-    passes = 1
+    n_per_thread = 1 << 22                     # per step and thread: 3 passes over 2^22 samples (~0.4 s per step), long enough
+    passes = 3                                 # that thread start-up and stragglers do not set the number
     vals, times = [], []
     for _ in range(max(args.warmup, 1)):
         run_cpu_path(n_per_thread, passes, threads)
@@ -185,7 +185,7 @@ def reference_arm(args):
         if time.time() - t0 > 150:
             break
     value = statistics.median(vals)
-    sample = "%d threads x 2^21 samples of the M=256 m=7 workload per step (%d steps run)" % (threads, len(vals))
+    sample = "%d threads x %d passes x 2^22 samples of the M=256 m=7 workload per step (%d steps run)" % (threads, passes, len(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
         "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * statistics.median(times), "higher_is_better": True,
