@@ -418,6 +418,7 @@ def test_nccl_gather_of_time_shards_and_channel_major():
     (130, 1 << 14, 1, None, 2.0),                           # a single tap
     (512, 1 << 13, 65, [0, 4096, 8192], 1.0),               # the longest filter the K = 128 window holds
     (24, 3 << 16, 33, None, 1.0),                           # long streams: 8192-sample segments, 24 of them (3 segment groups)
+    (8, 11 * 8192, 63, None, 1.0),                          # 11 segments: the second segment group is ragged (3 of 8 rows used)
     (96, 5000, 63, None, 1.0),                              # ragged length: tensor cores on the first 4608 samples, FFMA2 on 392
     (20, 70002, 17, [0, 70002 - 4000, 70002], 0.25),        # long ragged stream: 8 segments + a 4466-sample tail, then a short call
     (1024, 1 << 12, 63, None, 1.0),                         # more (tile, block) items than CTAs: runs spanning tiles
