@@ -20,9 +20,18 @@ OK, EINTERNAL, ECONFIG, EVALUE, ERANGE, EMODE, ENOCONV = range(7)
 def build(force: bool = False) -> str:
     """Compile the C restatement with gcc (oracle/Makefile)."""
     srcs = [os.path.join(_HERE, f) for f in ("core.c", "filters.c", "channelizer.c", "cpu_bench.c", "yagi_oracle.h")]
-    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
-    if force or stale:
-        subprocess.check_call(["make", "-C", _HERE, "-B", "libyagi_oracle.so"], stdout=subprocess.DEVNULL)
+    def stale():
+        return (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if force or stale():
+        # several ranks of one job may get here at once: build under a lock, and re-check once it is held
+        import fcntl
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lk:
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            try:
+                if force or stale():
+                    subprocess.check_call(["make", "-C", _HERE, "-B", "libyagi_oracle.so"], stdout=subprocess.DEVNULL)
+            finally:
+                fcntl.flock(lk, fcntl.LOCK_UN)
     return _SO
 
 
