@@ -210,8 +210,9 @@ def workload_config(n_gpus: int, log2_samples: int, scaling: str):
         "M": M, "m": SEMI, "As": AS, "samples_per_gpu": (1 << log2_samples) if scaling == "weak" else (1 << log2_samples) // n_gpus,
         "n_gpus": n_gpus,
         "sharding": "time blocks, halo (4m-1)*M/2 = %d samples per boundary, no collective" % HALO,
-        "l2_policy": "inputs (2 GiB) and outputs (4 GiB) per step exceed the 126 MB L2; no flush needed"
-                     if scaling == "weak" or n_gpus <= 8 else "see strong.l2_policy",
+        "l2_policy": "per-GPU inputs (%d MiB) and outputs (%d MiB) per step exceed the 126 MB L2; no flush needed"
+                     % (((1 << log2_samples) // (1 if scaling == "weak" else n_gpus)) * 8 >> 20,
+                        ((1 << log2_samples) // (1 if scaling == "weak" else n_gpus)) * 16 >> 20),
     }
 
 

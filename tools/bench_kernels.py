@@ -70,12 +70,14 @@ def main():
         x = randc(N)
         Y = torch.empty(2 * N, dtype=torch.complex64, device="cuda")
         qa = yb.FirPfbCh2.new_kaiser(yb.ANALYZER, M, m, 60.0)
-        ms = timed(lambda: qa.execute_block(x, N // (M // 2), out=Y), steps=5)
-        report("firpfbch2 analysis M=1024 m=4 N=2^%d (path %d)" % (N.bit_length() - 1, qa.last_path()), ms, 24.0 * N, N, "samples_in")
+        ms = timed(lambda: qa.execute_block(x, N // (M // 2), out=Y), steps=20)
+        report("firpfbch2 analysis M=1024 m=4 N=2^%d (path %d)" % (N.bit_length() - 1, qa.last_path()), ms, 24.0 * N, N, "samples_in",
+               {"kernel_ms": round(float(np.mean(qa.kernel_times_ms(4))), 4)})
         y = torch.empty(N, dtype=torch.complex64, device="cuda")
         qs = yb.FirPfbCh2.new_kaiser(yb.SYNTHESIZER, M, m, 60.0)
-        ms = timed(lambda: qs.execute_block(Y, N // (M // 2), out=y), steps=5)
-        report("firpfbch2 synthesis M=1024 m=4 N=2^%d (path %d)" % (N.bit_length() - 1, qs.last_path()), ms, 24.0 * N, N, "samples_out")
+        ms = timed(lambda: qs.execute_block(Y, N // (M // 2), out=y), steps=20)
+        report("firpfbch2 synthesis M=1024 m=4 N=2^%d (path %d)" % (N.bit_length() - 1, qs.last_path()), ms, 24.0 * N, N, "samples_out",
+               {"kernel_ms": round(float(np.mean(qs.kernel_times_ms(4))), 4)})
         del x, Y, y, qa, qs
     if "small" in which:
         for M in (64, 128):
@@ -98,11 +100,11 @@ def main():
             x = randc(N)
             Y = torch.empty(2 * N, dtype=torch.complex64, device="cuda")
             qa = yb.FirPfbCh2.new_kaiser(yb.ANALYZER, M, m, 60.0)
-            ms = timed(lambda: qa.execute_block(x, N // (M // 2), out=Y), steps=5)
+            ms = timed(lambda: qa.execute_block(x, N // (M // 2), out=Y), steps=20)
             report("firpfbch2 analysis M=%d m=%d N=2^26 (path %d)" % (M, m, qa.last_path()), ms, 24.0 * N, N, "samples_in")
             y = torch.empty(N, dtype=torch.complex64, device="cuda")
             qs = yb.FirPfbCh2.new_kaiser(yb.SYNTHESIZER, M, m, 60.0)
-            ms = timed(lambda: qs.execute_block(Y, N // (M // 2), out=y), steps=5)
+            ms = timed(lambda: qs.execute_block(Y, N // (M // 2), out=y), steps=20)
             report("firpfbch2 synthesis M=%d m=%d N=2^26 (path %d)" % (M, m, qs.last_path()), ms, 24.0 * N, N, "samples_out")
             del x, Y, y, qa, qs
     if "pfbch" in which:

@@ -89,7 +89,7 @@ struct TcParams {
     int n_streams;
     float scale;
     const float* toep;        // [2][kToepBytes / 4]: hi table, lo table
-    long long n_blocks;       // blocks per segment: Q / 64
+    long long n_blocks;       // blocks per segment: Q / kBlk
     int n_groups;             // tiles: ceil(n_streams / 8) stream groups x seg_groups segment groups
     int seg_groups;           // ceil((n / Q) / 8)
     int q_floats;             // 2 Q: floats per segment
