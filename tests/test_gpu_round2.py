@@ -564,3 +564,40 @@ def test_firfilt_crcf_copy_autotest_on_cuda(monkeypatch):
         assert bool(torch.equal(torch.view_as_real(ya), torch.view_as_real(yb_)))
         ref = po.firfilt_crcf(yb.fir_design_kaiser(21, 0.345, 60.0, 0.0), np.concatenate([x1.view(S_, n)[0].cpu().numpy(), x2.view(S_, n)[0].cpu().numpy()]), scale=2.0)[n:]
         assert_parity(ya.view(S_, n)[0].cpu().numpy(), ref, "continuation after clone, %d streams" % S_)
+
+
+def test_back_to_back_calls_under_programmatic_dependent_launch():
+    """The fused M=256 kernel is launched with programmatic stream serialization: consecutive calls may overlap one
+    launch's prologue with the previous one's tail.  Nothing may be read or written early: (a) 40 unsynchronised calls of
+    random even sizes writing consecutive slices, (b) the same calls all writing the SAME buffer with a torch copy kernel
+    (reader of that buffer) between them -- both must reproduce the oracle."""
+    import torch
+    M, m = 256, 7
+    rng = np.random.default_rng(77)
+    sizes = [int(2 * rng.integers(32, 700)) for _ in range(40)]
+    K = sum(sizes)
+    x = stimulus.noise_plus_tones(0, K * M // 2, M)
+    ref = po.FirPfbCh2.new_kaiser(po.ANALYZER, M, m, 60.0).execute_block(x).reshape(K, M)
+    xd = torch.from_numpy(x).cuda()
+    # (a) consecutive slices
+    q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+    y = torch.empty(K * M, dtype=torch.complex64, device="cuda")
+    l0 = yb.launch_count()
+    f = 0
+    for n in sizes:
+        q.execute_block(xd[f * M // 2:(f + n) * M // 2], n, out=y[f * M:(f + n) * M])
+        f += n
+    torch.cuda.synchronize()
+    assert yb.launch_count() - l0 == len(sizes)                  # one launch per call
+    assert_parity(y.cpu().numpy().reshape(K, M), ref, "consecutive slices")
+    # (b) one output buffer, copied out by a torch kernel between the calls
+    q.reset()
+    buf = torch.empty(max(sizes) * M, dtype=torch.complex64, device="cuda")
+    keep = torch.empty(K * M, dtype=torch.complex64, device="cuda")
+    f = 0
+    for n in sizes:
+        q.execute_block(xd[f * M // 2:(f + n) * M // 2], n, out=buf[: n * M])
+        keep[f * M:(f + n) * M].copy_(buf[: n * M])
+        f += n
+    torch.cuda.synchronize()
+    assert_parity(keep.cpu().numpy().reshape(K, M), ref, "shared output buffer")
