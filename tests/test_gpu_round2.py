@@ -601,3 +601,42 @@ def test_back_to_back_calls_under_programmatic_dependent_launch():
         f += n
     torch.cuda.synchronize()
     assert_parity(keep.cpu().numpy().reshape(K, M), ref, "shared output buffer")
+
+
+# ------------------------------------------------------------------ reference golden vectors straight on the GPU (no oracle)
+def test_reference_dotprod_vectors_on_the_gpu(monkeypatch):
+    """dotprod_crcf rand01 / rand02 / rand01-reversed (src/dotprod/mod.rs:455-524, tol 1e-3) as one output of the GPU FIR:
+    with taps g = reverse(h), out[len-1] = sum_i h[i] x[i].  Once through the small-call kernels and once embedded in a
+    32-stream x 4096-sample call that the tensor-core kernel takes."""
+    import golden_vectors as gv
+    import torch
+    G = gv.load()
+    cases = [(G["DOTPROD_CRCF_RAND01_H"], G["DOTPROD_CRCF_RAND01_X"], G["DOTPROD_CRCF_RAND01_Y"][0]),
+             (G["DOTPROD_CRCF_RAND02_H"], G["DOTPROD_CRCF_RAND02_X"], G["DOTPROD_CRCF_RAND02_Y"][0]),
+             (G["DOTPROD_CRCF_RAND01_H"][::-1], G["DOTPROD_CRCF_RAND01_X"], G["DOTPROD_CRCF_RAND01_YREV"][0])]
+    monkeypatch.setenv("YG_FIRFILT_TC", "1")
+    for h, x, want in cases:
+        n = h.size
+        g = np.ascontiguousarray(h[::-1], dtype=np.float32)
+        y = yb.FirFilt.new(g).execute_block(x.astype(np.complex64))
+        assert abs(y[n - 1] - want) < 1e-3
+        S_, N = 32, 4096
+        X = np.zeros((S_, N), dtype=np.complex64)
+        for s in range(S_):
+            X[s, 100 * s + 5: 100 * s + 5 + n] = x
+        q = yb.FirFilt.new(g, n_streams=S_)
+        Y = q.execute_block(torch.from_numpy(X).cuda()).view(S_, N).cpu().numpy()
+        assert q.last_path() == 4
+        for s in range(S_):
+            assert abs(Y[s, 100 * s + 5 + n - 1] - want) < 1e-3, s
+
+
+def test_reference_firdecim_vectors_on_the_gpu():
+    """firdecim_crcf golden vectors (src/filter/fir/firdecim_test_data.rs, tol 1e-3): y[k] = (x * h)[k M], i.e. every M-th
+    output of the GPU FIR (the decimator keeps the output after the FIRST sample of each block, firdecim.rs:179-191)."""
+    import golden_vectors as gv
+    G = gv.load()
+    for M, case in gv.FIRDECIM_CASES:
+        h, x, yr = (G["FIRDECIM_CRCF_DATA_%s_%s" % (case, k)] for k in "HXY")
+        y = yb.FirFilt.new(h).execute_block(x.astype(np.complex64))
+        np.testing.assert_allclose(y[::M][: yr.size], yr, atol=1e-3, rtol=1e-3)
