@@ -424,9 +424,10 @@ def test_nccl_gather_of_time_shards_and_channel_major():
     (1024, 1 << 12, 63, None, 1.0),                         # more (tile, block) items than CTAs: runs spanning tiles
     (64, 4096, 66, None, 1.0),                              # 66 .. 97 taps: 32-sample blocks, 3 blocks of history
     (40, 6144 + 100, 97, [0, 2048, 6244], 0.5),             # ... with state across calls and a ragged tail
-    (64, 1 << 13, 127, None, 1.0),                          # 98 .. 161 taps: 32-sample blocks, 5 blocks of history
+    (64, 1 << 13, 127, None, 1.0),                          # 98 .. 129 taps: 32-sample blocks, 4 blocks of history (130 .. 161: 5)
     (16, 3 << 16, 161, [0, 1 << 16, 3 << 16], 1.0),         # the longest filter tensor memory has columns for, long streams
     (300, 2048, 129, None, 1.0),                            # ragged stream count, the shortest call the variant takes
+    (32, 4096, 130, None, 1.0),                             # first tap count of the deepest instance
 ])
 def test_firfilt_tensor_core_path(monkeypatch, S_, N, taps, cuts, scale):
     """The tcgen05 3xTF32 Toeplitz kernel (last_path 4) against an f64 convolution and against the oracle's f32

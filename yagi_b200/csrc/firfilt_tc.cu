@@ -57,7 +57,7 @@ constexpr int kThreads = 320;
 // Geometry of one instantiation: blocks of kBlk samples (= outputs per tile, N of the MMA) and kHB blocks of history, so the
 // K window is (kHB + 1) kBlk samples and filters of up to kHB kBlk + 1 taps fit.  TMEM holds kHB + 2 blocks of A (hi) + as
 // many (lo) + two accumulators: 2 (kHB + 2) kBlk + 2 kBlk <= 512 columns.
-//   <64, 1>: up to  65 taps, K = 128 (BASELINE config #2)        <32, 3>: up to 97 taps, K = 128        <32, 5>: up to 161 taps, K = 192
+//   <64, 1>: up to 65 taps, K = 128 (BASELINE config #2)     <32, 3> / <32, 4> / <32, 5>: up to 97 / 129 / 161 taps, K = 128 / 160 / 192
 template <int kBlk_, int kHB_>
 struct Cfg {
     static constexpr int kBlk = kBlk_, kHB = kHB_;
@@ -276,6 +276,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_firfilt_tc(const __grid_constan
                             tc_mma_ts(dd, tmem + C::kColHi + col, bh, id, 1u);
                         }
                     } else {
+                        // (a run-time skip of the K steps whose slice of the band is all zero for the actual tap count was tried:
+                        // the per-step branches push the operands out of the uniform datapath and the MMA warp, the pacemaker
+                        // of these instances, gets slower -- 4.52 vs 4.03 ms at 127 taps; hence one instance per history depth)
 #pragma unroll
                         for (int s = 0; s < C::kKSteps; s++) {
                             constexpr int kPerBlock = kBlk / 8;                                // K steps per block of A
@@ -475,6 +478,7 @@ float tf32_rna(float v)
 
 using Cfg65 = Cfg<64, 1>;       // up to 65 taps (BASELINE config #2)
 using Cfg97 = Cfg<32, 3>;       // up to 97 taps
+using Cfg129 = Cfg<32, 4>;      // up to 129 taps
 using Cfg161 = Cfg<32, 5>;      // up to 161 taps
 
 // shortest segment a variant accepts: whole blocks, and the kHB blocks of history must lie inside the previous segment
@@ -549,7 +553,7 @@ long long firfilt_tc_prefix(size_t h_len, long long n, long long n_streams, cons
     if (n & 1) return 0;                                                   // row pitch must be a multiple of 16 bytes
     if (n >= (1LL << 29) || n_streams > 0x7fffffffLL) return 0;            // int32 box coordinates
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return 0;
-    const long long n_main = h_len <= (size_t)Cfg65::kMaxTaps ? prefix_t<Cfg65>(n) : h_len <= (size_t)Cfg97::kMaxTaps ? prefix_t<Cfg97>(n) : prefix_t<Cfg161>(n);
+    const long long n_main = h_len <= (size_t)Cfg65::kMaxTaps ? prefix_t<Cfg65>(n) : prefix_t<Cfg161>(n);      // all 32-sample instances alike
     if (n_main * n_streams < (1LL << 16)) return 0;                        // tiny calls: not worth 148 persistent CTAs
     return encode_tiled() != nullptr ? n_main : 0;
 }
@@ -558,6 +562,7 @@ int32_t firfilt_tc_plan(const float* h, size_t h_len, float** d_toep)
 {
     if (h_len <= (size_t)Cfg65::kMaxTaps) return plan_t<Cfg65>(h, h_len, d_toep);
     if (h_len <= (size_t)Cfg97::kMaxTaps) return plan_t<Cfg97>(h, h_len, d_toep);
+    if (h_len <= (size_t)Cfg129::kMaxTaps) return plan_t<Cfg129>(h, h_len, d_toep);
     return plan_t<Cfg161>(h, h_len, d_toep);
 }
 
@@ -567,6 +572,7 @@ int32_t firfilt_tc_launch(const float* d_toep, size_t h_len, float scale, const 
 {
     if (h_len <= (size_t)Cfg65::kMaxTaps) return launch_t<Cfg65>(d_toep, scale, hist, Hlen, x, y, n, pitch, n_streams, n_sm, st);
     if (h_len <= (size_t)Cfg97::kMaxTaps) return launch_t<Cfg97>(d_toep, scale, hist, Hlen, x, y, n, pitch, n_streams, n_sm, st);
+    if (h_len <= (size_t)Cfg129::kMaxTaps) return launch_t<Cfg129>(d_toep, scale, hist, Hlen, x, y, n, pitch, n_streams, n_sm, st);
     return launch_t<Cfg161>(d_toep, scale, hist, Hlen, x, y, n, pitch, n_streams, n_sm, st);
 }
 
