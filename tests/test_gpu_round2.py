@@ -604,6 +604,80 @@ def test_back_to_back_calls_under_programmatic_dependent_launch():
     assert_parity(keep.cpu().numpy().reshape(K, M), ref, "shared output buffer")
 
 
+def test_calls_hopping_between_streams_keep_the_state_in_order():
+    """A handle's state lives on the device and is handed from call to call; the caller may issue consecutive calls on
+    different (non-blocking) streams, through host pointers, or touch the state (get_state / set_state / reset / clone)
+    in between without synchronising.  The library orders them (StreamOrder, common.cuh): the concatenated output must be
+    the oracle's single-run output for every kernel family."""
+    import torch
+    rng = np.random.default_rng(5)
+    for M, m, K in ((256, 7, 2048), (1024, 4, 1024), (32, 3, 1024), (96, 3, 512)):
+        x = stimulus.noise_plus_tones(M, K * M // 2, M)
+        ref = po.FirPfbCh2.new_kaiser(po.ANALYZER, M, m, 60.0).execute_block(x).reshape(K, M)
+        xd = torch.from_numpy(x).cuda()
+        y = torch.empty(K * M, dtype=torch.complex64, device="cuda")
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.default_stream()]
+        q = yb.FirPfbCh2.new_kaiser(A, M, m, 60.0)
+        cuts = sorted(set(int(c) for c in rng.integers(1, K, 11))) + [K]   # odd cuts too
+        f = 0
+        host_parts = {}
+        for i, e in enumerate(cuts):
+            n = e - f
+            kind = i % 4
+            if kind == 3:                                   # host-pointer call between device calls
+                host_parts[f] = q.execute_block(x[f * M // 2:e * M // 2], n)
+            else:
+                with torch.cuda.stream(streams[kind]):
+                    q.execute_block(xd[f * M // 2:e * M // 2], n, out=y[f * M:e * M])
+            if i == 4:                                      # state read + written back, then a clone takes over
+                st = q.get_state()
+                q.set_state(*st)
+                q = q.clone()
+            f = e
+        torch.cuda.synchronize()
+        out = y.cpu().numpy().reshape(K, M)
+        for f0, part in host_parts.items():
+            out[f0:f0 + part.size // M] = part.reshape(-1, M)
+        assert_parity(out, ref, "stream hopping M=%d" % M)
+        # reset between streams: second half restarts from zero state
+        q.reset()
+        with torch.cuda.stream(streams[0]):
+            q.execute_block(xd[: 64 * M // 2], 64, out=y[: 64 * M])
+        q.reset()
+        with torch.cuda.stream(streams[1]):
+            q.execute_block(xd[: K * M // 2], K, out=y)
+        torch.cuda.synchronize()
+        assert_parity(y.cpu().numpy().reshape(K, M), ref, "reset between streams M=%d" % M)
+
+
+def test_firfilt_calls_hopping_between_streams(monkeypatch):
+    import torch
+    S_, N, taps = 32, 1 << 14, 65
+    rng = np.random.default_rng(9)
+    h = rng.standard_normal(taps).astype(np.float32)
+    x = (rng.standard_normal((S_, N)) + 1j * rng.standard_normal((S_, N))).astype(np.complex64)
+    ref = np.stack([po.firfilt_crcf(h, x[s]) for s in range(S_)])
+    xd = torch.from_numpy(x).cuda()
+    y = torch.empty((S_, N), dtype=torch.complex64, device="cuda")
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.default_stream(), torch.cuda.Stream()]
+    q = yb.FirFilt.new(h, n_streams=S_)
+    cuts = [4096, 4096 + 2048, 4096 + 2048 + 66, 12288, N]
+    f = 0
+    paths = []
+    for i, e in enumerate(cuts):
+        with torch.cuda.stream(streams[i % 3]):
+            xs = xd[:, f:e].contiguous()
+            ys = q.execute_block(xs)
+            y[:, f:e] = ys.view(S_, e - f)
+        paths.append(q.last_path())
+        f = e
+    torch.cuda.synchronize()
+    assert 4 in paths                                        # the tensor-core kernel took the large slices
+    assert_parity(y.cpu().numpy(), ref, "firfilt stream hopping")
+
+
 # ------------------------------------------------------------------ reference golden vectors straight on the GPU (no oracle)
 def test_reference_dotprod_vectors_on_the_gpu(monkeypatch):
     """dotprod_crcf rand01 / rand02 / rand01-reversed (src/dotprod/mod.rs:455-524, tol 1e-3) as one output of the GPU FIR:
