@@ -9,4 +9,4 @@ if [ "$1" != "nokernels" ]; then
 timeout 900 python tools/bench_kernels.py synth small ana1024 largeM pfbch firfilt > gpurun_out/bench_kernels.log 2>&1; echo "rc=$?" >> gpurun_out/bench_kernels.log
 fi
 tail -n 16 gpurun_out/pytest_gpu.log; tail -n 3 gpurun_out/smoke.log; tail -c 600 gpurun_out/bench_ref.log
-tail -c 5000 gpurun_out/bench.log; [ "$1" != "nokernels" ] && cat gpurun_out/bench_kernels.log
+tail -c 5000 gpurun_out/bench.log; if [ "$1" != "nokernels" ]; then cat gpurun_out/bench_kernels.log; fi
