@@ -15,6 +15,7 @@ struct Firpfbch2FastPlan {
     void* d_scratch = nullptr;    // large-M fused analysis: per-group V ring (device)
     void* d_flags = nullptr;      //   and its counters
     int n_groups = 0;             //   0: fused large-M kernel not available
+    bool single_sm = false;       // M = 1024, m <= 4: the one-CTA-per-SM analysis kernel takes the call
 };
 
 // Decide whether (M, m) has a fused kernel and upload its tap / twiddle tables.

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <type_traits>
 #include <vector>
 
@@ -122,7 +123,8 @@ __device__ __forceinline__ float2 xaddj(float2 a, float2 b) { return make_float2
 __device__ __forceinline__ float2 xsubj(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }   // a - j b
 __device__ __forceinline__ float2 xmul(float2 a, float wr, float wi)
 {
-    return make_float2(fmaf(a.x, wr, -a.y * wi), fmaf(a.x, wi, a.y * wr));
+    const float2 t = __fmul2_rn(a, make_float2(wr, wr));                // one packed multiply + two FMAs (was 2 + 2)
+    return make_float2(fmaf(-a.y, wi, t.x), fmaf(a.x, wi, t.y));
 }
 __device__ __forceinline__ void xdft4(float2& a0, float2& a1, float2& a2, float2& a3)
 {
@@ -153,6 +155,29 @@ __device__ __forceinline__ void xdft32(float2 (&v)[32], const float2* w32 /* e^{
         if (b == 0) v[16] = d;
         else if (b == 8) v[24] = make_float2(-d.y, d.x);                // W32^8 = j
         else { const float2 w = w32[b]; v[16 + b] = xmul(d, w.x, w.y); }
+    }
+    xdft16<0>(v);
+    xdft16<16>(v);
+}
+
+// the same with e^{+j 2 pi b / 32} as immediates instead of 16 broadcast loads per transform
+__device__ __forceinline__ void xdft32c(float2 (&v)[32])
+{
+    constexpr float kC[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
+                              0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f, 0.f, -0.19509032201612825f,
+                              -0.38268343236508977f, -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f,
+                              -0.92387953251128674f, -0.98078528040323043f};
+    constexpr float kS[16] = {0.f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f, 0.70710678118654752f,
+                              0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f, 1.f, 0.98078528040323043f,
+                              0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f, 0.55557023301960218f,
+                              0.38268343236508977f, 0.19509032201612825f};
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+        const float2 s = xadd(v[b], v[16 + b]), d = xsub(v[b], v[16 + b]);
+        v[b] = s;
+        if (b == 0) v[16] = d;
+        else if (b == 8) v[24] = make_float2(-d.y, d.x);                // W32^8 = j
+        else v[16 + b] = xmul(d, kC[b], kS[b]);
     }
     xdft16<0>(v);
     xdft16<16>(v);
@@ -629,6 +654,217 @@ int32_t launch_fused(const FusedParams& fp, cudaStream_t st)
     return YG_OK;
 }
 
+// ------------------------------------------------------------------ single-SM fused analysis kernel: M = 1024, m <= 4
+// The kernels above split a frame over G CTAs because M register-resident branch windows do not fit one SM, and pay for
+// it with the V exchange through L2.  For M = 1024 with at most 9 taps per branch the frame fits one SM after all if the
+// WINDOWS stay in shared memory and only the TAPS are register-resident:
+//   * input ring: 16 frame pairs (128 KB, eight 16 KB TMA bulk copies of two pairs each); a pair stays in the ring until
+//     the windows of eight later pairs have read it, so the ring IS the window storage;
+//   * FIR role (warps 0-7): thread t owns the taps of branches t, t + 256, t + 512, t + 768 (72 registers); per batch of
+//     two pairs and per branch it reads a transient 10-sample window from the ring (conflict-free LDS.64, 20 B per
+//     output sample), runs the packed even/odd-frame FFMA2 dot products of K1 and stores the four frames' V values
+//     UNPACKED (one 8 KB region per frame, double-buffered: 64 KB);
+//   * DFT role (warps 8-15): one warp per frame, the 32 x 32 warp transform of the two-stage path (radix 32 in
+//     registers, ONE XOR-swizzled exchange, done in place in the frame's V region), 256-byte coalesced stores.
+// HBM and L2 see the algorithmic 24 B per sample; shared memory moves ~56 B per output sample (K1: 40).
+namespace s1k {
+constexpr int kM = 1024, kM2 = 512;
+constexpr int kBP = 2;                                   // frame pairs per batch
+constexpr int kStages = 8;                               // ring of 8 batches = 16 pairs
+constexpr int kStageBytes = kBP * kM * 8;                // 16 KB
+constexpr int kRowBytes = kM * 8;                        // one pair of input = one frame of V = 8 KB
+constexpr int kVBufBytes = 2 * kBP * kRowBytes;          // 4 frames
+constexpr int kOffV = kStages * kStageBytes;             // 131072
+constexpr int kOffTw = kOffV + 2 * kVBufBytes;           // W1024^{lane k1} as [k1 / 2][lane] float4 (k1 even, k1 odd): 8 KB
+constexpr int kOffBar = kOffTw + 8192;
+constexpr int kBarInFull = 0;                            // [8] TMA transaction barriers
+constexpr int kBarInFree = 8;                            // [8] the 8 FIR warps no longer need the stage
+constexpr int kBarVFull = 16;                            // [2] the 8 FIR warps have written the buffer
+constexpr int kBarVFree = 18;                            // [2] its 4 DFT warps have read it
+constexpr int kSmem = kOffBar + 20 * 8;
+constexpr int kThreads = 512;
+constexpr int kMaxTaps = 9;
+// column of branch t + 256 k inside a pair of input, plus t: pos(j) = (511 - j) mod 1024
+__host__ __device__ constexpr int pos_k(int k) { return k == 0 ? 511 : k == 1 ? 255 : k == 2 ? 1023 : 767; }
+
+template <int kTaps>
+__device__ __forceinline__ void fir_role(const LargeParams& p, uint32_t smem, long long b0, long long b1)
+{
+    constexpr int kHist = kTaps - 1;                     // pairs of history a window reaches back
+    const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
+    const uint32_t bar = smem + kOffBar;
+
+    float2 T[4][kTaps];                                  // taps of branches t + 256 k
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int i = 0; i < kTaps; i++) T[k][i] = __ldg(&p.taps[(t + 256 * k) * kTaps + i]);
+    pdl_wait();                                          // x and the history may come from the previous kernel
+
+    const long long call_off = p.f0 * kM2;
+    const long long q_first = p.pair_begin + b0 * kBP;   // first pair of the slab, relative to f0
+    const float2* xb = p.x + call_off + q_first * kM;    // its first sample
+    const long long nb = b1 - b0;
+
+    auto issue_load = [&](long long lb) {                // local batch lb -> stage (lb + 4) mod 8
+        const int st = (int)((lb + 4) & 7);
+        mbar_expect_tx(bar + 8 * (kBarInFull + st), kStageBytes);
+        tma_load_1d(smem + st * kStageBytes, xb + lb * (long long)(kBP * kM), kStageBytes, bar + 8 * (kBarInFull + st));
+    };
+    if (t == 0)
+        for (long long lb = 0; lb < 4 && lb < nb; lb++) issue_load(lb);
+
+    // the eight pairs before the slab (ring rows 0-7) come from x, the history buffer or zeros
+    for (int idx = t; idx < 8 * kM; idx += 256) {
+        const long long ta = (q_first - 8) * kM + idx + call_off;
+        float2 v = make_float2(0.f, 0.f);
+        if (ta >= 0) v = __ldg(&p.x[ta]);
+        else if (p.Hlen + ta >= 0) v = __ldg(&p.hist[p.Hlen + ta]);
+        sts64(smem + idx * 8, v);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // these rows are overwritten by bulk copies later
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+
+    const uint32_t ring_t = smem - t * 8;
+    const uint32_t v_t = smem + kOffV + t * 8;
+
+    auto do_batch = [&](auto ph_tag, long long lb) {
+        constexpr int PH = decltype(ph_tag)::value;      // lb mod 8: every ring row below is a compile-time constant
+        constexpr int ST = (PH + 4) & 7;
+        constexpr int BUF = PH & 1;
+        mbar_wait(bar + 8 * (kBarInFull + ST), (uint32_t)((lb >> 3) & 1));       // the batch's own two pairs have landed
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float2 w[kTaps + 1];                         // u[q0 - kHist .. q0 + 1]
+#pragma unroll
+            for (int i = 0; i <= kTaps; i++) w[i] = lds64(ring_t + ((2 * PH + 8 - kHist + i) & 15) * kRowBytes + pos_k(k) * 8);
+            // accumulators are (re, im) of one frame: complex sample x broadcast real tap, so that a frame's value is
+            // one aligned register pair for the 8-byte store (K1 packs (even, odd) instead and stores both frames at once)
+            float2 e0 = make_float2(0.f, 0.f), o0 = e0, e1 = e0, o1 = e0;
+#pragma unroll
+            for (int i = kTaps - 1; i >= 0; i--) {       // oldest sample first, as K1
+                e0 = fma2(w[kHist - i], f2(T[k][i].x), e0);
+                o0 = fma2(w[kHist - i], f2(T[k][i].y), o0);
+                e1 = fma2(w[kHist + 1 - i], f2(T[k][i].x), e1);
+                o1 = fma2(w[kHist + 1 - i], f2(T[k][i].y), o1);
+            }
+            if (k == 0 && lb >= 2) mbar_wait(bar + 8 * (kBarVFree + BUF), (uint32_t)(((lb >> 1) - 1) & 1));
+            const uint32_t vo = v_t + BUF * kVBufBytes + k * (256 * 8);
+            sts64(vo + 0 * kRowBytes, e0);                               // pair 0, even frame
+            sts64(vo + 1 * kRowBytes, o0);                               //         odd frame
+            sts64(vo + 2 * kRowBytes, e1);                               // pair 1
+            sts64(vo + 3 * kRowBytes, o1);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(bar + 8 * (kBarVFull + BUF));
+            mbar_arrive(bar + 8 * (kBarInFree + PH));    // rows 2 lb, 2 lb + 1 (stage lb mod 8) are out of every later window
+            if (wrp == PH && lb + 4 < nb) {              // the FIR warps take turns refilling that stage with batch lb + 4
+                mbar_wait(bar + 8 * (kBarInFree + PH), (uint32_t)((lb >> 3) & 1));
+                issue_load(lb + 4);
+            }
+        }
+    };
+    for (long long lb = 0; lb < nb; lb += 8) {
+        do_batch(std::integral_constant<int, 0>{}, lb);
+        if (lb + 1 < nb) do_batch(std::integral_constant<int, 1>{}, lb + 1);
+        if (lb + 2 < nb) do_batch(std::integral_constant<int, 2>{}, lb + 2);
+        if (lb + 3 < nb) do_batch(std::integral_constant<int, 3>{}, lb + 3);
+        if (lb + 4 < nb) do_batch(std::integral_constant<int, 4>{}, lb + 4);
+        if (lb + 5 < nb) do_batch(std::integral_constant<int, 5>{}, lb + 5);
+        if (lb + 6 < nb) do_batch(std::integral_constant<int, 6>{}, lb + 6);
+        if (lb + 7 < nb) do_batch(std::integral_constant<int, 7>{}, lb + 7);
+    }
+}
+
+__device__ __forceinline__ void dft_role(const LargeParams& p, const unsigned char* smem_raw, uint32_t smem, long long b0, long long b1)
+{
+    const int dt = threadIdx.x - 256, lane = dt & 31, dw = dt >> 5;
+    const int buf = dw >> 2, fi = dw & 3;                // this warp's V buffer and frame (pair 0 even, odd, pair 1 even, odd)
+    const uint32_t bar = smem + kOffBar;
+    const uint32_t frame = smem + kOffV + buf * kVBufBytes + fi * kRowBytes;
+    const uint32_t twt = smem + kOffTw + lane * 16;
+    const long long nb = b1 - b0;
+    pdl_wait();                                          // nothing is written before the previous kernel has completed
+    for (long long lb = buf; lb < nb; lb += 2) {
+        mbar_wait(bar + 8 * (kBarVFull + buf), (uint32_t)((lb >> 1) & 1));
+        float2 v[32];
+#pragma unroll
+        for (int n1 = 0; n1 < 32; n1++) v[n1] = lds64(frame + (32 * n1 + lane) * 8);
+        xdft32c(v);
+        __syncwarp();                                    // every lane has read the frame: exchange in place
+        // inter-pass twiddles from the transposed shared table: a gather twid[lane * k1] from global costs one L1 tag
+        // lookup per distinct line, ~700 LSU cycles per frame, which made this role the bottleneck (0.56 -> see DESIGN)
+#pragma unroll
+        for (int a = 0; a < 16; a++) {
+            const float4 w = lds128(twt + a * 512);
+            float2 z0 = v[dr32(2 * a)], z1 = v[dr32(2 * a + 1)];
+            if (a > 0) z0 = xmul(z0, w.x, w.y);
+            z1 = xmul(z1, w.z, w.w);
+            sts64(frame + (((lane << 5) | ((2 * a) ^ lane)) << 3), z0);
+            sts64(frame + (((lane << 5) | ((2 * a + 1) ^ lane)) << 3), z1);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) v[n2] = lds64(frame + (((n2 << 5) | (lane ^ n2)) << 3));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + 8 * (kBarVFree + buf));
+        xdft32c(v);
+        const long long q = p.pair_begin + (b0 + lb) * kBP + (fi >> 1);
+        float2* fr = p.y + (p.f0 + 2 * q + (fi & 1)) * (long long)kM + lane;
+#pragma unroll
+        for (int k2 = 0; k2 < 32; k2++) __stcs(fr + 32 * k2, v[dr32(k2)]);
+    }
+}
+
+template <int kTaps>
+__global__ void __launch_bounds__(kThreads, 1) k_m1024_fused(const LargeParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t smem = smem_u32(smem_raw);
+    const long long n_batches = (p.pair_end - p.pair_begin) / kBP;
+    const long long b0 = (n_batches * blockIdx.x) / gridDim.x, b1 = (n_batches * (blockIdx.x + 1)) / gridDim.x;
+    if (threadIdx.x == 0) {
+        const uint32_t bar = smem + kOffBar;
+        for (int i = 0; i < 8; i++) mbar_init(bar + 8 * (kBarInFull + i), 1);
+        for (int i = 0; i < 8; i++) mbar_init(bar + 8 * (kBarInFree + i), 8);
+        for (int i = 0; i < 2; i++) mbar_init(bar + 8 * (kBarVFull + i), 8);
+        for (int i = 0; i < 2; i++) mbar_init(bar + 8 * (kBarVFree + i), 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 1024; i += kThreads) {              // entry i: k1 = 2 (i >> 6) + (i & 1), lane = (i >> 1) & 31
+        const int k1 = 2 * (i >> 6) + (i & 1), ln = (i >> 1) & 31;
+        reinterpret_cast<float2*>(smem_raw + kOffTw)[i] = __ldg(&p.twid[ln * k1]);
+    }
+    __syncthreads();
+    pdl_launch_dependents();
+    if (b0 >= b1) return;                                // never taken: the grid has at most one CTA per batch
+    if (threadIdx.x < 256) fir_role<kTaps>(p, smem, b0, b1);
+    else dft_role(p, smem_raw, smem, b0, b1);
+}
+
+template <int kTaps>
+int32_t launch(const Firpfbch2FastPlan& plan, const LargeParams& p, cudaStream_t st)
+{
+    YG_CUDA(cudaFuncSetAttribute(k_m1024_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    const long long n_batches = (p.pair_end - p.pair_begin) / kBP;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min<long long>(plan.n_sm, n_batches));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = plan.pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    YG_CUDA(cudaLaunchKernelEx(&cfg, k_m1024_fused<kTaps>, p));
+    count_launch();
+    return YG_OK;
+}
+}  // namespace s1k
+
 int32_t launch_fft(const Firpfbch2FastPlan& plan, const float2* prefix, const float2* x, long long v0, float2* dst,
                    long long n_frames, int streaming, cudaStream_t st)
 {
@@ -1074,6 +1310,12 @@ int32_t firpfbch2_large_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
     YG_CUDA(yg::memcpy_sync(plan.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
     YG_TRY(plan_common(plan, M));
     if (plan.supported) YG_TRY(plan_fused(plan, false));
+    if (plan.supported && M == 1024 && 2 * m + 1 <= (uint32_t)s1k::kMaxTaps) {
+        const char* e = getenv("YG_LARGE_SINGLE_SM");     // debugging knob: 0 keeps the group kernel
+        plan.single_sm = !(e && e[0] == '0');
+        const char* d = getenv("YG_PDL");
+        plan.pdl = !(d && d[0] == '0');
+    }
     return YG_OK;
 }
 
@@ -1086,7 +1328,27 @@ int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist
     const int M = (int)plan.M;
     const long long n_pairs = (long long)(n_frames / 2);
     long long fused_pairs = 0;
-    if (plan.n_groups > 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {      // the fused kernel stages 16-byte chunks
+    if (plan.single_sm && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {         // M = 1024, m <= 4: one CTA per SM, no exchange
+        fused_pairs = (n_pairs / s1k::kBP) * s1k::kBP;
+        if (fused_pairs > 0) {
+            LargeParams p;
+            p.hist = hist; p.Hlen = Hlen; p.x = x; p.y = y;
+            p.f0 = (long long)f0;
+            p.pair_begin = 0;
+            p.pair_end = fused_pairs;
+            p.slabs = 0;
+            p.M = M;
+            p.taps = reinterpret_cast<const float2*>(plan.d_taps);
+            p.twid = reinterpret_cast<const float2*>(plan.d_twid);
+            switch (plan.m) {
+                case 1: YG_TRY(s1k::launch<3>(plan, p, st)); break;
+                case 2: YG_TRY(s1k::launch<5>(plan, p, st)); break;
+                case 3: YG_TRY(s1k::launch<7>(plan, p, st)); break;
+                case 4: YG_TRY(s1k::launch<9>(plan, p, st)); break;
+                default: return fail(YG_EINTERNAL, "single-SM large-M kernel not instantiated for m = %u", plan.m);
+            }
+        }
+    } else if (plan.n_groups > 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {      // the fused kernel stages 16-byte chunks
         // whole 16-pair batches go through the fused kernel; what is left (< 32 frames) takes the two-stage path below
         const long long n_batches = n_pairs / kPairsPerBatch;
         fused_pairs = n_batches * kPairsPerBatch;
