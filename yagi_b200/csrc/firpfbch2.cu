@@ -326,7 +326,8 @@ int32_t launch_analysis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames
         }
         else if (use_small) YG_TRY(firpfbch2_small_launch(q->small, hist, (long long)q->hist_len, x, y, lead, body, st));
         else if (use_tiny) YG_TRY(firpfbch2_tiny_launch(q->tiny, hist, (long long)q->hist_len, x, y, lead, body, st));
-        else YG_TRY(firpfbch2_large_launch(q->large, hist, (long long)q->hist_len, x, y, lead, body, st));
+        else YG_TRY(firpfbch2_large_launch(q->large, hist, (long long)q->hist_len, x, y, lead, body, st,
+                                           reinterpret_cast<float2*>(q->d_hist[q->cur ^ 1].p), (long long)n_frames * q->M2, hist_done));
         if (q->timing_on) YG_CUDA(cudaEventRecord(q->ev1, st));
         q->timed = q->timing_on;
         q->last_path = (use_fused || use_small || use_tiny) ? 2 : 3;

@@ -15,7 +15,7 @@ struct Firpfbch2FastPlan {
     void* d_scratch = nullptr;    // large-M fused analysis: per-group V ring (device)
     void* d_flags = nullptr;      //   and its counters
     int n_groups = 0;             //   0: fused large-M kernel not available
-    bool single_sm = false;       // M = 1024, m <= 4: the one-CTA-per-SM analysis kernel takes the call
+    bool single_sm = false;       // M = 1024, m <= 4: the one-CTA-per-SM analysis / synthesis kernel takes the call
 };
 
 // Decide whether (M, m) has a fused kernel and upload its tap / twiddle tables.
@@ -61,8 +61,11 @@ int32_t firpfbch2_tiny_synth_launch(const Firpfbch2FastPlan& p, const float2* pr
 // Large-M analysis (firpfbch2_large.cu, M = 512 / 1024 / 2048 / 4096): one fused cooperative kernel (FIR role -> L2 ring
 // -> DFT teams) for whole 32-frame batches; FIR stage + in-place FFT stage per L2-sized chunk for the rest.
 int32_t firpfbch2_large_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m, const float* h);
+// With `hist_new` and `hist_done` non-null the kernel that takes the call may also write the object's next state (see
+// firpfbch2_fast_launch); *hist_done tells whether it did.
 int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& p, const float2* hist, long long Hlen, const float2* x, float2* y,
-                               size_t f0, size_t n_frames, cudaStream_t st);
+                               size_t f0, size_t n_frames, cudaStream_t st, float2* hist_new = nullptr, long long n_new = 0,
+                               bool* hist_done = nullptr);
 
 // Large-M synthesis (same sizes): one fused cooperative kernel (DFT teams -> L2 ring -> overlap-add role), or, when
 // that cannot launch, IFFT stage into an L2-resident scratch + overlap-add stage per chunk.

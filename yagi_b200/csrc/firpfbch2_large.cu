@@ -43,6 +43,8 @@ struct LargeParams {
     int M;                    // channels (power of two, multiple of 256)
     const float2* taps;       // [M][2m+1] (even, odd) tap pairs, 1/M folded in
     const float2* twid;       // [M] e^{+j 2 pi k / M}
+    float2* hist_new = nullptr;          // single-SM kernel only: if non-null it also writes the object's next state, the
+    long long n_new = 0;                 //   last Hlen samples of (hist ++ x[0 .. n_new)), like the M = 256 kernel
 };
 
 // ------------------------------------------------------------------ stage A: branch FIRs
@@ -786,6 +788,14 @@ __device__ __forceinline__ void dft_role(const LargeParams& p, const unsigned ch
     const uint32_t twt = smem + kOffTw + lane * 16;
     const long long nb = b1 - b0;
     pdl_wait();                                          // nothing is written before the previous kernel has completed
+    // state hand-off folded into this launch (as in the M = 256 kernel): the DFT warps of the last CTA are idle until the
+    // first V buffer is full
+    if (p.hist_new != nullptr && blockIdx.x == gridDim.x - 1) {
+        for (long long i = dt; i < p.Hlen; i += 256) {
+            const long long ts = p.n_new - p.Hlen + i;
+            p.hist_new[i] = (ts >= 0) ? __ldg(&p.x[ts]) : __ldg(&p.hist[p.Hlen + ts]);
+        }
+    }
     for (long long lb = buf; lb < nb; lb += 2) {
         mbar_wait(bar + 8 * (kBarVFull + buf), (uint32_t)((lb >> 1) & 1));
         float2 v[32];
@@ -1180,6 +1190,223 @@ int32_t launch_synth_fused(const SynthFusedParams& p, cudaStream_t st)
     return YG_OK;
 }
 
+// ------------------------------------------------------------------ single-SM fused synthesis kernel: M = 1024, m <= 4
+// The mirror image of s1k.  Holding the overlap-add WINDOWS of 1024 columns on one SM would take 4m frames of U (128 KB
+// at m = 4) on top of the frames in flight; holding the partial OUTPUT sums instead takes half of that and fits the
+// register file.  With g_i[l] = h[i + l M/2] / 2 and c = i + (f odd ? M/2 : 0)
+//       y_f[i] = sum_{l < 4m} g_i[l] u_{f-l}[c],
+// so a value u_g[c] is read ONCE, when frame g arrives, and added into the 2m outputs of its column's parity that it
+// reaches (taps of even lag from a frame of that parity, taps of odd lag from a frame of the other parity):
+//   * frame ring: 6 stages of 4 input frames (192 KB); a stage is filled by TMA bulk copies, transformed IN PLACE by four
+//     DFT warps (the 32 x 32 warp transform of s1k, one frame per warp) and then read once by the overlap-add role;
+//   * overlap-add role (warps 0-7): thread t owns output samples i = t and t + 256: per i 2m running sums for the even
+//     frames, 2m for the odd frames (64 registers at m = 4) and the 4m taps (32 registers); per pair of frames and i it
+//     reads four values (conflict-free LDS.64, 16 B per output sample), issues 8m packed FFMA2 and emits two outputs.
+//     The sums rotate through their registers by unrolling one period of 2m pairs; a slab starts one period early on
+//     zeroed sums and drops that period's outputs (the warm-up frames come from the call or from the kept prefix).
+// The order of the additions differs from the two-bank form of the other synthesis kernels (old to new across both
+// banks instead of bank by bank), within the same f32 rounding bound.
+namespace s1ks {
+constexpr int kM = 1024, kM2 = 512;
+constexpr int kFB = 4;                                   // frames per batch
+constexpr int kFrameBytes = kM * 8;
+constexpr int kStageBytes = kFB * kFrameBytes;           // 32 KB
+constexpr int kStages = 6;
+constexpr int kOffTw = kStages * kStageBytes;            // W1024^{lane k1}, the s1k table: 8 KB
+constexpr int kOffBar = kOffTw + 8192;
+constexpr int kBarInFull = 0;                            // [6] TMA transaction barriers
+constexpr int kBarUFull = 6;                             // [6] the stage's four DFT warps have transformed it
+constexpr int kBarFree = 12;                             // [6] the eight overlap-add warps have read it
+constexpr int kSmem = kOffBar + 18 * 8;
+constexpr int kThreads = 512;
+constexpr int kMaxM = 4;
+
+struct Params {
+    const float2* prefix;     // the 32 input frames preceding x[0]
+    const float2* x;          // input frames of the call, [frame][1024]
+    float2* y;                // output sample 0 of the call
+    long long f0;             // first frame handled (even global parity)
+    long long n_batches;      // batches of 4 frames
+    const float* taps;        // [1024][4m]  h[(j & 511) + l * 512] / 2
+    const float2* twid;       // [1024] e^{+j 2 pi k / 1024}
+};
+
+template <int kL>                                        // kL = 2m: pairs of frames a sum collects
+__device__ __forceinline__ void ola_role(const Params& p, uint32_t smem, long long b0, long long b1)
+{
+    constexpr int kWarm = kL / 2;                        // batches per period of kL pairs = warm-up batches
+    const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
+    const uint32_t bar = smem + kOffBar;
+
+    float A[2][kL], B[2][kL];                            // taps of even / odd lag of outputs t and t + 256
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int j = 0; j < kL; j++) {
+            A[s][j] = __ldg(&p.taps[(t + 256 * s) * (2 * kL) + 2 * j]);
+            B[s][j] = __ldg(&p.taps[(t + 256 * s) * (2 * kL) + 2 * j + 1]);
+        }
+    float2 E[2][kL], O[2][kL];                           // running sums of the even- and odd-frame outputs
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int j = 0; j < kL; j++) E[s][j] = O[s][j] = make_float2(0.f, 0.f);
+    pdl_wait();                                          // x and the prefix may come from the previous kernel
+
+    const int nb = (int)(b1 - b0) + kWarm;               // local batches, warm-up period first
+    const long long fr_base = p.f0 + (b0 - kWarm) * kFB; // call-relative frame of local batch 0 (>= -16)
+    auto issue_load = [&](int lb, int stg) {
+        const uint32_t fb = bar + 8 * (kBarInFull + stg);
+        const uint32_t dst = smem + stg * kStageBytes;
+        const long long fr = fr_base + (long long)lb * kFB;
+        mbar_expect_tx(fb, kStageBytes);
+        if (fr >= 0) tma_load_1d(dst, p.x + fr * kM, kStageBytes, fb);
+        else if (fr + kFB <= 0) tma_load_1d(dst, p.prefix + (32 + fr) * kM, kStageBytes, fb);
+        else
+            for (int k = 0; k < kFB; k++)
+                tma_load_1d(dst + k * kFrameBytes, fr + k >= 0 ? p.x + (fr + k) * kM : p.prefix + (32 + fr + k) * kM, kFrameBytes, fb);
+    };
+    if (t == 0)
+        for (int lb = 0; lb < kStages && lb < nb; lb++) issue_load(lb, lb);
+
+    float2* yo = p.y + fr_base * kM2 + t;                // output of the current batch's first frame
+    int st = 0;
+    uint32_t ph = 0;
+    for (int lb0 = 0; lb0 < nb; lb0 += kWarm) {
+        const bool emit = lb0 > 0;                       // the first period only warms the sums up
+#pragma unroll
+        for (int bb = 0; bb < kWarm; bb++) {
+            const int lb = lb0 + bb;
+            if (lb >= nb) break;
+            mbar_wait(bar + 8 * (kBarUFull + st), ph);
+            const uint32_t fr = smem + st * kStageBytes + t * 8;
+#pragma unroll
+            for (int pq = 0; pq < 2; pq++) {
+                const int pp = 2 * bb + pq;              // pair within the period: every register index below is a constant
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    const uint32_t a = fr + 2 * pq * kFrameBytes + s * 2048;
+                    // outputs of the even frames g, g + 2, ...: lag 2j from u_g, lag 2j + 1 from u_{g+1} (to g + 2 + 2j)
+                    const float2 ue = lds64(a);                                  // column i of the even frame
+#pragma unroll
+                    for (int j = 0; j < kL; j++) E[s][(pp + j) % kL] = fma2(ue, f2(A[s][j]), E[s][(pp + j) % kL]);
+                    if (emit) __stcs(yo + 2 * pq * kM2 + 256 * s, E[s][pp % kL]);
+                    const float2 uo = lds64(a + kFrameBytes);                    //            of the odd frame
+#pragma unroll
+                    for (int j = 0; j < kL - 1; j++) E[s][(pp + 1 + j) % kL] = fma2(uo, f2(B[s][j]), E[s][(pp + 1 + j) % kL]);
+                    E[s][pp % kL] = mul2(uo, f2(B[s][kL - 1]));
+                    // outputs of the odd frames g + 1, g + 3, ...: lag 2j + 1 from u_g, lag 2j from u_{g+1}
+                    const float2 ve = lds64(a + 4096);                           // column i + 512 of the even frame
+                    O[s][(pp + kL - 1) % kL] = mul2(ve, f2(B[s][kL - 1]));
+#pragma unroll
+                    for (int j = 0; j < kL - 1; j++) O[s][(pp + j) % kL] = fma2(ve, f2(B[s][j]), O[s][(pp + j) % kL]);
+                    const float2 vo = lds64(a + kFrameBytes + 4096);             //                 of the odd frame
+#pragma unroll
+                    for (int j = 0; j < kL; j++) O[s][(pp + j) % kL] = fma2(vo, f2(A[s][j]), O[s][(pp + j) % kL]);
+                    if (emit) __stcs(yo + (2 * pq + 1) * kM2 + 256 * s, O[s][pp % kL]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar + 8 * (kBarFree + st));
+                if (wrp == (lb & 7) && lb + kStages < nb) {          // the overlap-add warps take turns refilling the stage
+                    mbar_wait(bar + 8 * (kBarFree + st), ph);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the DFT warps wrote it with plain stores
+                    issue_load(lb + kStages, st);
+                }
+            }
+            yo += kFB * kM2;
+            if (++st == kStages) { st = 0; ph ^= 1; }
+        }
+    }
+}
+
+__device__ __forceinline__ void dft_role(uint32_t smem, int nb)
+{
+    const int dt = threadIdx.x - 256, lane = dt & 31, dw = dt >> 5;
+    const int grp = dw >> 2, fi = dw & 3;                // batches of this warp's parity, frame fi of each
+    const uint32_t bar = smem + kOffBar;
+    const uint32_t twt = smem + kOffTw + lane * 16;
+    int st = grp;
+    uint32_t ph = 0;
+    for (int lb = grp; lb < nb; lb += 2) {
+        mbar_wait(bar + 8 * (kBarInFull + st), ph);
+        const uint32_t frame = smem + st * kStageBytes + fi * kFrameBytes;
+        float2 v[32];
+#pragma unroll
+        for (int n1 = 0; n1 < 32; n1++) v[n1] = lds64(frame + (32 * n1 + lane) * 8);
+        xdft32c(v);
+        __syncwarp();                                    // every lane has read the frame: exchange in place
+#pragma unroll
+        for (int a = 0; a < 16; a++) {
+            const float4 w = lds128(twt + a * 512);
+            float2 z0 = v[dr32(2 * a)], z1 = v[dr32(2 * a + 1)];
+            if (a > 0) z0 = xmul(z0, w.x, w.y);
+            z1 = xmul(z1, w.z, w.w);
+            sts64(frame + (((lane << 5) | ((2 * a) ^ lane)) << 3), z0);
+            sts64(frame + (((lane << 5) | ((2 * a + 1) ^ lane)) << 3), z1);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) v[n2] = lds64(frame + (((n2 << 5) | (lane ^ n2)) << 3));
+        __syncwarp();
+        xdft32c(v);
+#pragma unroll
+        for (int k2 = 0; k2 < 32; k2++) sts64(frame + (32 * k2 + lane) * 8, v[dr32(k2)]);      // U in natural order
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + 8 * (kBarUFull + st));
+        st += 2;
+        if (st >= kStages) { st -= kStages; ph ^= 1; }
+    }
+}
+
+template <int kL>
+__global__ void __launch_bounds__(kThreads, 1) k_m1024_synth_fused(const Params p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t smem = smem_u32(smem_raw);
+    const long long b0 = (p.n_batches * blockIdx.x) / gridDim.x, b1 = (p.n_batches * (blockIdx.x + 1)) / gridDim.x;
+    if (threadIdx.x == 0) {
+        const uint32_t bar = smem + kOffBar;
+        for (int i = 0; i < kStages; i++) {
+            mbar_init(bar + 8 * (kBarInFull + i), 1);
+            mbar_init(bar + 8 * (kBarUFull + i), 4);
+            mbar_init(bar + 8 * (kBarFree + i), 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 1024; i += kThreads) {              // entry i: k1 = 2 (i >> 6) + (i & 1), lane = (i >> 1) & 31
+        const int k1 = 2 * (i >> 6) + (i & 1), ln = (i >> 1) & 31;
+        reinterpret_cast<float2*>(smem_raw + kOffTw)[i] = __ldg(&p.twid[ln * k1]);
+    }
+    __syncthreads();
+    pdl_launch_dependents();
+    if (b0 >= b1) return;                                // never taken: the grid has at most one CTA per batch
+    if (threadIdx.x < 256) ola_role<kL>(p, smem, b0, b1);
+    else dft_role(smem, (int)(b1 - b0) + kL / 2);
+}
+
+template <int kL>
+int32_t launch(const Firpfbch2FastPlan& plan, const Params& p, cudaStream_t st)
+{
+    YG_CUDA(cudaFuncSetAttribute(k_m1024_synth_fused<kL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min<long long>(plan.n_sm, p.n_batches));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = plan.pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    YG_CUDA(cudaLaunchKernelEx(&cfg, k_m1024_synth_fused<kL>, p));
+    count_launch();
+    return YG_OK;
+}
+}  // namespace s1ks
+
 template <int kTaps>
 int32_t launch_wola(const WolaParams& p, cudaStream_t st)
 {
@@ -1320,8 +1547,9 @@ int32_t firpfbch2_large_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
 }
 
 int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist, long long Hlen, const float2* x, float2* y,
-                               size_t f0, size_t n_frames, cudaStream_t st)
+                               size_t f0, size_t n_frames, cudaStream_t st, float2* hist_new, long long n_new, bool* hist_done)
 {
+    if (hist_done) *hist_done = false;
     if (!plan.supported) return fail(YG_EINTERNAL, "large-M path not available for this geometry");
     if (n_frames == 0) return YG_OK;
     if (n_frames & 1) return fail(YG_EINTERNAL, "large-M path needs an even number of frames");
@@ -1340,6 +1568,7 @@ int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist
             p.M = M;
             p.taps = reinterpret_cast<const float2*>(plan.d_taps);
             p.twid = reinterpret_cast<const float2*>(plan.d_twid);
+            if (hist_done && hist_new) { p.hist_new = hist_new; p.n_new = n_new; *hist_done = true; }
             switch (plan.m) {
                 case 1: YG_TRY(s1k::launch<3>(plan, p, st)); break;
                 case 2: YG_TRY(s1k::launch<5>(plan, p, st)); break;
@@ -1426,6 +1655,12 @@ int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t
     YG_CUDA(yg::memcpy_sync(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
     YG_TRY(plan_common(plan, M));
     if (plan.supported) YG_TRY(plan_fused(plan, true));
+    if (plan.supported && M == 1024 && m <= (uint32_t)s1ks::kMaxM) {
+        const char* e = getenv("YG_LARGE_SINGLE_SM");     // debugging knob: 0 keeps the group kernel
+        plan.single_sm = !(e && e[0] == '0');
+        const char* d = getenv("YG_PDL");
+        plan.pdl = !(d && d[0] == '0');
+    }
     return YG_OK;
 }
 
@@ -1436,7 +1671,7 @@ long long firpfbch2_large_synth_scratch_frames(uint32_t M) { return chunk_frames
 namespace {
 bool synth_fused_ok(const Firpfbch2FastPlan& plan, const float2* prefix, const float2* x)
 {
-    return plan.n_groups > 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(prefix)) & 15) == 0;
+    return (plan.n_groups > 0 || plan.single_sm) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(prefix)) & 15) == 0;
 }
 }  // namespace
 
@@ -1452,6 +1687,21 @@ int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& plan, const float2
     if (n_frames == 0) return YG_OK;
     if (n_frames % 32) return fail(YG_EINTERNAL, "large-M synthesis path needs a multiple of 32 frames");
     const int M = (int)plan.M;
+    if (plan.single_sm && synth_fused_ok(plan, prefix, x)) {       // M = 1024, m <= 4: one CTA per SM, no exchange
+        s1ks::Params p;
+        p.prefix = prefix; p.x = x; p.y = y;
+        p.f0 = (long long)f0;
+        p.n_batches = (long long)(n_frames / s1ks::kFB);
+        p.taps = reinterpret_cast<const float*>(plan.d_taps);
+        p.twid = reinterpret_cast<const float2*>(plan.d_twid);
+        switch (plan.m) {
+            case 1: return s1ks::launch<2>(plan, p, st);
+            case 2: return s1ks::launch<4>(plan, p, st);
+            case 3: return s1ks::launch<6>(plan, p, st);
+            case 4: return s1ks::launch<8>(plan, p, st);
+            default: return fail(YG_EINTERNAL, "single-SM large-M synthesis kernel not instantiated for m = %u", plan.m);
+        }
+    }
     if (synth_fused_ok(plan, prefix, x)) {                 // the fused kernel stages 16-byte chunks
         SynthFusedParams p;
         p.prefix = prefix; p.x = x; p.y = y;
