@@ -741,6 +741,16 @@ def test_single_sm_M1024_synthesis(m):
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
     assert_parity(y / scale, ref / scale, "single-SM synthesis M=1024 m=%d" % m)
+    # whole batches only: ONE launch per call, the kernel writes the next state (the last 32 input frames) itself
+    q2 = yb.FirPfbCh2.new(S, M, m, h)
+    outs = []
+    for a, b in ((0, 640), (640, 704), (704, 1344)):
+        n0 = yb.launch_count()
+        outs.append(q2.execute_block(X[a * M: b * M]))
+        assert q2.last_path() == 3 and yb.launch_count() - n0 == 1, (a, b, yb.launch_count() - n0)
+    y2 = np.concatenate(outs).reshape(1344, M // 2)
+    per_frame = np.abs(y2 - ref[:1344]).max(axis=1) / scale
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())
 
 
 @pytest.mark.parametrize("m", [1, 3])

@@ -376,7 +376,7 @@ int32_t launch_generic_synthesis(yg_firpfbch2_crcf q, const float2* hist, const 
     return YG_OK;
 }
 
-int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st)
+int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frames, yg_cf32* d_y, cudaStream_t st, bool* hist_done)
 {
     const float2* hist = reinterpret_cast<const float2*>(q->d_hist[q->cur].p);
     const float2* x = reinterpret_cast<const float2*>(d_x);
@@ -397,7 +397,8 @@ int32_t launch_synthesis(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frame
         if (use_fused && q->M == 256) YG_TRY(firpfbch2_synth_fast_launch(q->sfast, hist, x, y, lead, body, st));
         else if (use_fused && q->M >= 64) YG_TRY(firpfbch2_small_synth_launch(q->sfast, hist, x, y, lead, body, st));
         else if (use_fused) YG_TRY(firpfbch2_tiny_synth_launch(q->sfast, hist, x, y, lead, body, st));
-        else YG_TRY(firpfbch2_large_synth_launch(q->slarge, hist, x, y, reinterpret_cast<float2*>(q->d_Uc.p), lead, body, st));
+        else YG_TRY(firpfbch2_large_synth_launch(q->slarge, hist, x, y, reinterpret_cast<float2*>(q->d_Uc.p), lead, body, st,
+                                                 reinterpret_cast<float2*>(q->d_hist[q->cur ^ 1].p), (long long)n_frames * q->M, hist_done));
         if (q->timing_on) YG_CUDA(cudaEventRecord(q->ev1, st));
         q->timed = q->timing_on;
         q->last_path = use_fused ? 2 : 3;
@@ -427,7 +428,7 @@ int32_t execute_dev_impl(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frame
     if (n_frames == 0) return YG_OK;
     bool hist_done = false;
     if (q->type == YG_ANALYZER) YG_TRY(launch_analysis(q, d_x, n_frames, d_y, st, &hist_done));
-    else YG_TRY(launch_synthesis(q, d_x, n_frames, d_y, st));
+    else YG_TRY(launch_synthesis(q, d_x, n_frames, d_y, st, &hist_done));
     // both types keep the tail of their INPUT stream as state
     const long long n_new = (long long)n_frames * (q->type == YG_ANALYZER ? q->M2 : q->M);
     const long long Hlen = (long long)q->hist_len;

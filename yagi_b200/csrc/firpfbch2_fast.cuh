@@ -73,7 +73,9 @@ int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& p, uint32_t M, uint32_t m,
 long long firpfbch2_large_synth_scratch_frames(uint32_t M);
 // false when the fused kernel will take the call (its ring lives in the plan) and `scratch` may be null
 bool firpfbch2_large_synth_needs_scratch(const Firpfbch2FastPlan& p, const float2* prefix, const float2* x);
+// `hist_new` / `hist_done` as in firpfbch2_large_launch (n_new counts input samples, M per frame).
 int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& p, const float2* prefix, const float2* x, float2* y,
-                                     float2* scratch, size_t f0, size_t n_frames, cudaStream_t st);
+                                     float2* scratch, size_t f0, size_t n_frames, cudaStream_t st, float2* hist_new = nullptr,
+                                     long long n_new = 0, bool* hist_done = nullptr);
 
 }  // namespace yg

@@ -683,7 +683,8 @@ constexpr int kBarInFull = 0;                            // [8] TMA transaction 
 constexpr int kBarInFree = 8;                            // [8] the 8 FIR warps no longer need the stage
 constexpr int kBarVFull = 16;                            // [2] the 8 FIR warps have written the buffer
 constexpr int kBarVFree = 18;                            // [2] its 4 DFT warps have read it
-constexpr int kSmem = kOffBar + 20 * 8;
+constexpr int kBarHist = 20;                             // the part of the slab's eight history pairs that is copied from x
+constexpr int kSmem = kOffBar + 21 * 8;
 constexpr int kThreads = 512;
 constexpr int kMaxTaps = 9;
 // column of branch t + 256 k inside a pair of input, plus t: pos(j) = (511 - j) mod 1024
@@ -696,13 +697,6 @@ __device__ __forceinline__ void fir_role(const LargeParams& p, uint32_t smem, lo
     const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
     const uint32_t bar = smem + kOffBar;
 
-    float2 T[4][kTaps];                                  // taps of branches t + 256 k
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-#pragma unroll
-        for (int i = 0; i < kTaps; i++) T[k][i] = __ldg(&p.taps[(t + 256 * k) * kTaps + i]);
-    pdl_wait();                                          // x and the history may come from the previous kernel
-
     const long long call_off = p.f0 * kM2;
     const long long q_first = p.pair_begin + b0 * kBP;   // first pair of the slab, relative to f0
     const float2* xb = p.x + call_off + q_first * kM;    // its first sample
@@ -713,19 +707,46 @@ __device__ __forceinline__ void fir_role(const LargeParams& p, uint32_t smem, lo
         mbar_expect_tx(bar + 8 * (kBarInFull + st), kStageBytes);
         tma_load_1d(smem + st * kStageBytes, xb + lb * (long long)(kBP * kM), kStageBytes, bar + 8 * (kBarInFull + st));
     };
-    if (t == 0)
+    // The eight pairs before the slab (ring rows 0-7): whatever of them lies inside x (all of it for every slab but the
+    // call's first) comes in with bulk copies as well, the rest -- history buffer or zeros -- with plain loads.
+    const long long ta0 = (q_first - 8) * kM + call_off; // call-relative sample index of ring row 0 (a multiple of 512)
+    const int n_head = ta0 >= 0 ? 0 : (int)min(-ta0, (long long)(8 * kM));
+    if (t == 0) {                                        // first of all: get the copies going
+        pdl_wait();                                      // x and the history may come from the previous kernel
+        if (n_head < 8 * kM) {
+            const uint32_t bytes = (uint32_t)(8 * kM - n_head) * 8;
+            mbar_expect_tx(bar + 8 * kBarHist, bytes);
+            for (uint32_t off = 0; off < bytes; off += 16384)
+                tma_load_1d(smem + n_head * 8 + off, p.x + (ta0 + n_head) + off / 8, min(16384u, bytes - off), bar + 8 * kBarHist);
+        }
         for (long long lb = 0; lb < 4 && lb < nb; lb++) issue_load(lb);
+    }
 
-    // the eight pairs before the slab (ring rows 0-7) come from x, the history buffer or zeros
-    for (int idx = t; idx < 8 * kM; idx += 256) {
-        const long long ta = (q_first - 8) * kM + idx + call_off;
-        float2 v = make_float2(0.f, 0.f);
-        if (ta >= 0) v = __ldg(&p.x[ta]);
-        else if (p.Hlen + ta >= 0) v = __ldg(&p.hist[p.Hlen + ta]);
-        sts64(smem + idx * 8, v);
+    float2 T[4][kTaps];                                  // taps of branches t + 256 k
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int i = 0; i < kTaps; i++) T[k][i] = __ldg(&p.taps[(t + 256 * k) * kTaps + i]);
+    pdl_wait();
+
+    for (int i0 = 0; i0 < n_head; i0 += 8 * 256) {       // eight loads in flight per thread
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int idx = i0 + u * 256 + t;
+            const long long ta = ta0 + idx;
+            v[u] = make_float2(0.f, 0.f);
+            if (idx < n_head && p.Hlen + ta >= 0) v[u] = __ldg(&p.hist[p.Hlen + ta]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int idx = i0 + u * 256 + t;
+            if (idx < n_head) sts64(smem + idx * 8, v[u]);
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // these rows are overwritten by bulk copies later
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (n_head < 8 * kM) mbar_wait(bar + 8 * kBarHist, 0);
 
     const uint32_t ring_t = smem - t * 8;
     const uint32_t v_t = smem + kOffV + t * 8;
@@ -788,10 +809,12 @@ __device__ __forceinline__ void dft_role(const LargeParams& p, const unsigned ch
     const uint32_t twt = smem + kOffTw + lane * 16;
     const long long nb = b1 - b0;
     pdl_wait();                                          // nothing is written before the previous kernel has completed
-    // state hand-off folded into this launch (as in the M = 256 kernel): the DFT warps of the last CTA are idle until the
-    // first V buffer is full
-    if (p.hist_new != nullptr && blockIdx.x == gridDim.x - 1) {
-        for (long long i = dt; i < p.Hlen; i += 256) {
+    // state hand-off folded into this launch (as in the M = 256 kernel): every CTA copies a slice of the next state
+    // while its DFT warps wait for the first V buffer
+    if (p.hist_new != nullptr) {
+        const long long per = (p.Hlen + gridDim.x - 1) / gridDim.x;
+        const long long i1 = min(p.Hlen, per * (long long)(blockIdx.x + 1));
+        for (long long i = per * blockIdx.x + dt; i < i1; i += 256) {
             const long long ts = p.n_new - p.Hlen + i;
             p.hist_new[i] = (ts >= 0) ? __ldg(&p.x[ts]) : __ldg(&p.hist[p.Hlen + ts]);
         }
@@ -840,6 +863,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_m1024_fused(const LargeParams p
         for (int i = 0; i < 8; i++) mbar_init(bar + 8 * (kBarInFree + i), 8);
         for (int i = 0; i < 2; i++) mbar_init(bar + 8 * (kBarVFull + i), 8);
         for (int i = 0; i < 2; i++) mbar_init(bar + 8 * (kBarVFree + i), 4);
+        mbar_init(bar + 8 * kBarHist, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -1229,6 +1253,8 @@ struct Params {
     long long n_batches;      // batches of 4 frames
     const float* taps;        // [1024][4m]  h[(j & 511) + l * 512] / 2
     const float2* twid;       // [1024] e^{+j 2 pi k / 1024}
+    float2* hist_new;         // if non-null the kernel also writes the object's next state there: the last 32 frames of
+    long long n_new;          //   (prefix ++ x[0 .. n_new))
 };
 
 template <int kL>                                        // kL = 2m: pairs of frames a sum collects
@@ -1237,21 +1263,6 @@ __device__ __forceinline__ void ola_role(const Params& p, uint32_t smem, long lo
     constexpr int kWarm = kL / 2;                        // batches per period of kL pairs = warm-up batches
     const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
     const uint32_t bar = smem + kOffBar;
-
-    float A[2][kL], B[2][kL];                            // taps of even / odd lag of outputs t and t + 256
-#pragma unroll
-    for (int s = 0; s < 2; s++)
-#pragma unroll
-        for (int j = 0; j < kL; j++) {
-            A[s][j] = __ldg(&p.taps[(t + 256 * s) * (2 * kL) + 2 * j]);
-            B[s][j] = __ldg(&p.taps[(t + 256 * s) * (2 * kL) + 2 * j + 1]);
-        }
-    float2 E[2][kL], O[2][kL];                           // running sums of the even- and odd-frame outputs
-#pragma unroll
-    for (int s = 0; s < 2; s++)
-#pragma unroll
-        for (int j = 0; j < kL; j++) E[s][j] = O[s][j] = make_float2(0.f, 0.f);
-    pdl_wait();                                          // x and the prefix may come from the previous kernel
 
     const int nb = (int)(b1 - b0) + kWarm;               // local batches, warm-up period first
     const long long fr_base = p.f0 + (b0 - kWarm) * kFB; // call-relative frame of local batch 0 (>= -16)
@@ -1266,8 +1277,25 @@ __device__ __forceinline__ void ola_role(const Params& p, uint32_t smem, long lo
             for (int k = 0; k < kFB; k++)
                 tma_load_1d(dst + k * kFrameBytes, fr + k >= 0 ? p.x + (fr + k) * kM : p.prefix + (32 + fr + k) * kM, kFrameBytes, fb);
     };
-    if (t == 0)
+    if (t == 0) {                                        // first of all: get the copies going
+        pdl_wait();                                      // x and the prefix may come from the previous kernel
         for (int lb = 0; lb < kStages && lb < nb; lb++) issue_load(lb, lb);
+    }
+
+    float A[2][kL], B[2][kL];                            // taps of even / odd lag of outputs t and t + 256
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int j = 0; j < kL; j++) {
+            A[s][j] = __ldg(&p.taps[(t + 256 * s) * (2 * kL) + 2 * j]);
+            B[s][j] = __ldg(&p.taps[(t + 256 * s) * (2 * kL) + 2 * j + 1]);
+        }
+    float2 E[2][kL], O[2][kL];                           // running sums of the even- and odd-frame outputs
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int j = 0; j < kL; j++) E[s][j] = O[s][j] = make_float2(0.f, 0.f);
+    pdl_wait();                                          // nothing is written before the previous kernel has completed
 
     float2* yo = p.y + fr_base * kM2 + t;                // output of the current batch's first frame
     int st = 0;
@@ -1321,12 +1349,23 @@ __device__ __forceinline__ void ola_role(const Params& p, uint32_t smem, long lo
     }
 }
 
-__device__ __forceinline__ void dft_role(uint32_t smem, int nb)
+__device__ __forceinline__ void dft_role(const Params& p, uint32_t smem, int nb)
 {
     const int dt = threadIdx.x - 256, lane = dt & 31, dw = dt >> 5;
     const int grp = dw >> 2, fi = dw & 3;                // batches of this warp's parity, frame fi of each
     const uint32_t bar = smem + kOffBar;
     const uint32_t twt = smem + kOffTw + lane * 16;
+    // state hand-off folded into this launch: every CTA copies a slice of the next state (the tail of the input stream)
+    if (p.hist_new != nullptr) {
+        constexpr long long kH = 32 * kM;
+        pdl_wait();                                      // nothing is written before the previous kernel has completed
+        const long long per = (kH / 2 + gridDim.x - 1) / gridDim.x;
+        const long long i1 = min(kH / 2, per * (long long)(blockIdx.x + 1));
+        for (long long i = per * blockIdx.x + dt; i < i1; i += 256) {            // 16 bytes per thread and turn
+            const long long ts = p.n_new - kH + 2 * i;
+            reinterpret_cast<float4*>(p.hist_new)[i] = __ldg(reinterpret_cast<const float4*>(ts >= 0 ? p.x + ts : p.prefix + (kH + ts)));
+        }
+    }
     int st = grp;
     uint32_t ph = 0;
     for (int lb = grp; lb < nb; lb += 2) {
@@ -1384,7 +1423,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_m1024_synth_fused(const Params 
     pdl_launch_dependents();
     if (b0 >= b1) return;                                // never taken: the grid has at most one CTA per batch
     if (threadIdx.x < 256) ola_role<kL>(p, smem, b0, b1);
-    else dft_role(smem, (int)(b1 - b0) + kL / 2);
+    else dft_role(p, smem, (int)(b1 - b0) + kL / 2);
 }
 
 template <int kL>
@@ -1681,8 +1720,10 @@ bool firpfbch2_large_synth_needs_scratch(const Firpfbch2FastPlan& plan, const fl
 }
 
 int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& plan, const float2* prefix, const float2* x, float2* y,
-                                     float2* scratch, size_t f0, size_t n_frames, cudaStream_t st)
+                                     float2* scratch, size_t f0, size_t n_frames, cudaStream_t st, float2* hist_new, long long n_new,
+                                     bool* hist_done)
 {
+    if (hist_done) *hist_done = false;
     if (!plan.supported) return fail(YG_EINTERNAL, "large-M synthesis path not available for this geometry");
     if (n_frames == 0) return YG_OK;
     if (n_frames % 32) return fail(YG_EINTERNAL, "large-M synthesis path needs a multiple of 32 frames");
@@ -1694,6 +1735,8 @@ int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& plan, const float2
         p.n_batches = (long long)(n_frames / s1ks::kFB);
         p.taps = reinterpret_cast<const float*>(plan.d_taps);
         p.twid = reinterpret_cast<const float2*>(plan.d_twid);
+        p.hist_new = nullptr; p.n_new = 0;
+        if (hist_done && hist_new) { p.hist_new = hist_new; p.n_new = n_new; *hist_done = true; }     // x and the prefix are 16-byte aligned here
         switch (plan.m) {
             case 1: return s1ks::launch<2>(plan, p, st);
             case 2: return s1ks::launch<4>(plan, p, st);
