@@ -12,6 +12,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libyagi_b200.so")
+# A/B builds (tools/build_variant.sh) live next to it; YG_LIB=<name> loads lib/libyagi_b200_<name>.so instead
+if os.environ.get("YG_LIB"):
+    SO = os.path.join(LIBDIR, "libyagi_b200_%s.so" % os.environ["YG_LIB"])
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

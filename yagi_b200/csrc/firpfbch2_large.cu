@@ -867,9 +867,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_m1024_fused(const LargeParams p
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    // (filling this table inside the DFT role, off the FIR role's start-up path, made the kernels 3-4 % slower: same-box A/B)
     for (int i = threadIdx.x; i < 1024; i += kThreads) {              // entry i: k1 = 2 (i >> 6) + (i & 1), lane = (i >> 1) & 31
         const int k1 = 2 * (i >> 6) + (i & 1), ln = (i >> 1) & 31;
-        reinterpret_cast<float2*>(smem_raw + kOffTw)[i] = __ldg(&p.twid[ln * k1]);
+        sts64(smem + kOffTw + i * 8, __ldg(&p.twid[ln * k1]));
     }
     __syncthreads();
     pdl_launch_dependents();
@@ -881,7 +882,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_m1024_fused(const LargeParams p
 template <int kTaps>
 int32_t launch(const Firpfbch2FastPlan& plan, const LargeParams& p, cudaStream_t st)
 {
-    YG_CUDA(cudaFuncSetAttribute(k_m1024_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     const long long n_batches = (p.pair_end - p.pair_begin) / kBP;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)std::min<long long>(plan.n_sm, n_batches));
@@ -895,6 +895,18 @@ int32_t launch(const Firpfbch2FastPlan& plan, const LargeParams& p, cudaStream_t
     cfg.numAttrs = 1;
     YG_CUDA(cudaLaunchKernelEx(&cfg, k_m1024_fused<kTaps>, p));
     count_launch();
+    return YG_OK;
+}
+
+// plan time, on the object's device: the kernel instance may use kSmem bytes of dynamic shared memory
+inline int32_t prepare(uint32_t m)
+{
+    switch (m) {
+        case 1: YG_CUDA(cudaFuncSetAttribute(k_m1024_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); break;
+        case 2: YG_CUDA(cudaFuncSetAttribute(k_m1024_fused<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); break;
+        case 3: YG_CUDA(cudaFuncSetAttribute(k_m1024_fused<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); break;
+        default: YG_CUDA(cudaFuncSetAttribute(k_m1024_fused<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); break;
+    }
     return YG_OK;
 }
 }  // namespace s1k
@@ -1241,7 +1253,8 @@ constexpr int kOffBar = kOffTw + 8192;
 constexpr int kBarInFull = 0;                            // [6] TMA transaction barriers
 constexpr int kBarUFull = 6;                             // [6] the stage's four DFT warps have transformed it
 constexpr int kBarFree = 12;                             // [6] the eight overlap-add warps have read it
-constexpr int kSmem = kOffBar + 18 * 8;
+constexpr int kOffSrc = kOffBar + 18 * 8;                // address of the slab's local frame 0 in x (refills never reach the prefix)
+constexpr int kSmem = kOffSrc + 8;
 constexpr int kThreads = 512;
 constexpr int kMaxM = 4;
 
@@ -1280,6 +1293,7 @@ __device__ __forceinline__ void ola_role(const Params& p, uint32_t smem, long lo
     if (t == 0) {                                        // first of all: get the copies going
         pdl_wait();                                      // x and the prefix may come from the previous kernel
         for (int lb = 0; lb < kStages && lb < nb; lb++) issue_load(lb, lb);
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(smem + kOffSrc), "l"(p.x + fr_base * kM) : "memory");
     }
 
     float A[2][kL], B[2][kL];                            // taps of even / odd lag of outputs t and t + 256
@@ -1340,7 +1354,13 @@ __device__ __forceinline__ void ola_role(const Params& p, uint32_t smem, long lo
                 if (wrp == (lb & 7) && lb + kStages < nb) {          // the overlap-add warps take turns refilling the stage
                     mbar_wait(bar + 8 * (kBarFree + st), ph);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the DFT warps wrote it with plain stores
-                    issue_load(lb + kStages, st);
+                    // batch lb + 6 lies inside x (kStages > kWarm); its address comes from shared memory, not from
+                    // registers every thread would have to keep alive across the loop
+                    unsigned long long src;
+                    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(src) : "r"(smem + kOffSrc) : "memory");
+                    mbar_expect_tx(bar + 8 * (kBarInFull + st), kStageBytes);
+                    tma_load_1d(smem + st * kStageBytes, reinterpret_cast<const char*>(src) + (long long)(lb + kStages) * kStageBytes,
+                                kStageBytes, bar + 8 * (kBarInFull + st));
                 }
             }
             yo += kFB * kM2;
@@ -1415,9 +1435,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_m1024_synth_fused(const Params 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    // (filling this table inside the DFT role, off the FIR role's start-up path, made the kernels 3-4 % slower: same-box A/B)
     for (int i = threadIdx.x; i < 1024; i += kThreads) {              // entry i: k1 = 2 (i >> 6) + (i & 1), lane = (i >> 1) & 31
         const int k1 = 2 * (i >> 6) + (i & 1), ln = (i >> 1) & 31;
-        reinterpret_cast<float2*>(smem_raw + kOffTw)[i] = __ldg(&p.twid[ln * k1]);
+        sts64(smem + kOffTw + i * 8, __ldg(&p.twid[ln * k1]));
     }
     __syncthreads();
     pdl_launch_dependents();
@@ -1429,7 +1450,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_m1024_synth_fused(const Params 
 template <int kL>
 int32_t launch(const Firpfbch2FastPlan& plan, const Params& p, cudaStream_t st)
 {
-    YG_CUDA(cudaFuncSetAttribute(k_m1024_synth_fused<kL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)std::min<long long>(plan.n_sm, p.n_batches));
     cfg.blockDim = dim3(kThreads);
@@ -1442,6 +1462,17 @@ int32_t launch(const Firpfbch2FastPlan& plan, const Params& p, cudaStream_t st)
     cfg.numAttrs = 1;
     YG_CUDA(cudaLaunchKernelEx(&cfg, k_m1024_synth_fused<kL>, p));
     count_launch();
+    return YG_OK;
+}
+
+inline int32_t prepare(uint32_t m)
+{
+    switch (m) {
+        case 1: YG_CUDA(cudaFuncSetAttribute(k_m1024_synth_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); break;
+        case 2: YG_CUDA(cudaFuncSetAttribute(k_m1024_synth_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); break;
+        case 3: YG_CUDA(cudaFuncSetAttribute(k_m1024_synth_fused<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); break;
+        default: YG_CUDA(cudaFuncSetAttribute(k_m1024_synth_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); break;
+    }
     return YG_OK;
 }
 }  // namespace s1ks
@@ -1579,6 +1610,7 @@ int32_t firpfbch2_large_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
     if (plan.supported && M == 1024 && 2 * m + 1 <= (uint32_t)s1k::kMaxTaps) {
         const char* e = getenv("YG_LARGE_SINGLE_SM");     // debugging knob: 0 keeps the group kernel
         plan.single_sm = !(e && e[0] == '0');
+        if (plan.single_sm) YG_TRY(s1k::prepare(m));
         const char* d = getenv("YG_PDL");
         plan.pdl = !(d && d[0] == '0');
     }
@@ -1697,6 +1729,7 @@ int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t
     if (plan.supported && M == 1024 && m <= (uint32_t)s1ks::kMaxM) {
         const char* e = getenv("YG_LARGE_SINGLE_SM");     // debugging knob: 0 keeps the group kernel
         plan.single_sm = !(e && e[0] == '0');
+        if (plan.single_sm) YG_TRY(s1ks::prepare(m));
         const char* d = getenv("YG_PDL");
         plan.pdl = !(d && d[0] == '0');
     }
