@@ -1,8 +1,12 @@
 // firpfbch2_large.cu -- firpfbch2 analysis and synthesis for large power-of-two M (512 .. 4096; M = 1024 is
 // BASELINE config #4), sm_100a.
 //
-// One SM cannot hold M >= 512 branch windows plus the transform.  Two implementations live here:
+// One SM cannot hold M >= 512 register-resident branch windows plus the transform.  Three implementations live here:
 //
+//  * SINGLE-SM (s1k::k_m1024_fused / s1ks::k_m1024_synth_fused, M = 1024 with m <= 4 = BASELINE config #4): one CTA per SM
+//    and no exchange at all -- taps in registers, windows in a shared-memory input ring (analysis) / running output sums in
+//    registers over a shared-memory frame ring transformed in place (synthesis).  Described where they are defined.
+
 //  * FUSED (k_large_fused / k_large_synth_fused, one cooperative launch per call): groups of G = M / 256
 //    persistent CTAs; in every CTA warps 0-7 own 256 polyphase branches (the register-window FIR / overlap-add
 //    arithmetic of the M = 256 kernels) and warps 8-15 transform frame pairs in packed (even, odd) form as teams
