@@ -463,7 +463,8 @@ def test_firfilt_tensor_core_path(monkeypatch, S_, N, taps, cuts, scale):
 def test_kernels_do_not_write_outside_their_output():
     """Out-of-bounds writes would land in the guard bands around `out`: the fused M=256 kernel (incl. its folded state
     hand-off), the tensor-core firfilt (TMA tensor stores, ragged stream count), the channel-major transpose and the
-    large-M cooperative kernel all leave a NaN-patterned band of 1 MiB on either side untouched."""
+    large-M kernels (single-SM and cooperative, both directions) all leave a NaN-patterned band of 1 MiB on either side
+    untouched."""
     import torch
     pad = 1 << 17
 
@@ -491,6 +492,21 @@ def test_kernels_do_not_write_outside_their_output():
     q.execute_block(x, K, out=out)
     torch.cuda.synchronize()
     assert q.last_path() == 3 and intact(buf, K * M) and bool(torch.isfinite(torch.view_as_real(out)).all())
+    # the same geometry the other way (single-SM synthesis kernel, state written by the kernel), then m = 6, which
+    # stays on the cooperative group kernels
+    K = 2048 + 64
+    X = torch.from_numpy(_rand_c(rng, K * M)).cuda()
+    buf, out = guarded(K * M // 2)
+    q = yb.FirPfbCh2.new_kaiser(S, M, m, 60.0)
+    q.execute_block(X, K, out=out)
+    torch.cuda.synchronize()
+    assert q.last_path() == 3 and intact(buf, K * M // 2) and bool(torch.isfinite(torch.view_as_real(out)).all())
+    for type_, n_in, n_out in ((A, K * M // 2, K * M), (S, K * M, K * M // 2)):
+        buf, out = guarded(n_out)
+        q = yb.FirPfbCh2.new_kaiser(type_, M, 6, 60.0)
+        q.execute_block(X[:n_in], K, out=out)
+        torch.cuda.synchronize()
+        assert q.last_path() == 3 and intact(buf, n_out) and bool(torch.isfinite(torch.view_as_real(out)).all())
     # tensor-core firfilt, 100 streams (12.5 tiles of 8) x 4096
     S_, N = 100, 4096
     x = torch.from_numpy(_rand_c(rng, S_ * N)).cuda()

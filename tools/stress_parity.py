@@ -99,13 +99,16 @@ def main():
     if len(sys.argv) > 3 and sys.argv[3] == "streams":
         return stream_objects(rng, budget)
     sizes = [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 6, 24, 48, 100]
+    if os.environ.get("YG_STRESS_SIZES"):                     # e.g. YG_STRESS_SIZES=1024 YG_STRESS_MMAX=4: the single-SM kernels only
+        sizes = [int(v) for v in os.environ["YG_STRESS_SIZES"].split(",")]
+    m_max = int(os.environ.get("YG_STRESS_MMAX", "8"))
     t0 = time.time()
     case = 0
     while time.time() - t0 < budget:
         case += 1
         M = int(rng.choice(sizes))
         synth = bool(rng.integers(0, 2))
-        m = int(rng.integers(1, 8 if synth else 9))
+        m = int(rng.integers(1, min(m_max, 7 if synth else 8) + 1))
         # total frames: enough for several batches per slab sometimes, small otherwise; bounded by oracle time
         total_samples = int(rng.choice([1 << 16, 1 << 18, 1 << 20, 3 << 20]))
         K = max(40, total_samples // (M // 2))
