@@ -734,20 +734,20 @@ def test_reference_firdecim_vectors_on_the_gpu():
 
 
 # ------------------------------------------------------------------ single-SM M = 1024 kernels (config #4)
-@pytest.mark.parametrize("m", [1, 2, 3, 4])
-def test_single_sm_M1024_synthesis(m):
-    """The one-CTA-per-SM synthesis kernel (M = 1024, m <= 4; running output sums in registers, frames transformed
-    in place in a 6-stage shared ring): random prototype, three calls -- a short one (one batch per CTA, warm-up out
-    of the zero prefix), a long one starting on an ODD frame (lead frame on the generic kernel, warm-up batches that
-    straddle prefix | x, every CTA wrapping its ring twice) and the rest -- against the CPU path, per frame."""
-    M = 1024
-    K = 8320 + 75
+@pytest.mark.parametrize("M,m", [(1024, 1), (1024, 2), (1024, 3), (1024, 4), (512, 1), (512, 2), (512, 3), (512, 4), (512, 5),
+                                 (512, 6), (512, 7)])
+def test_single_sm_synthesis(M, m):
+    """The one-CTA-per-SM synthesis kernels (M = 1024, m <= 4 and M = 512, m <= 7; running output sums in registers,
+    frames transformed in place in a 6-stage shared ring): random prototype, three calls -- a short one (one batch per
+    CTA, warm-up out of the zero prefix), a long one starting on an ODD frame (lead frame on the generic kernel, warm-up
+    batches that straddle prefix | x, every CTA wrapping its ring twice) and the rest -- against the CPU path, per frame."""
+    K = (8320 if M == 1024 else 16640) + 75
     rng = np.random.default_rng(5100 + m)
     h = rng.standard_normal(2 * M * m).astype(np.float32)
     X = _rand_c(rng, K * M)
     ref = po.FirPfbCh2.new(po.SYNTHESIZER, M, m, h).execute_block(X).reshape(K, M // 2)
     q = yb.FirPfbCh2.new(S, M, m, h)
-    cuts = [0, 97, 97 + 6400 + 1, K]
+    cuts = [0, 97, 97 + (6400 if M == 1024 else 12800) + 1, K]
     outs = []
     for a, b in zip(cuts, cuts[1:]):
         outs.append(q.execute_block(X[a * M: b * M]))
@@ -756,7 +756,7 @@ def test_single_sm_M1024_synthesis(m):
     scale = max(1.0, np.abs(ref).max())
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
-    assert_parity(y / scale, ref / scale, "single-SM synthesis M=1024 m=%d" % m)
+    assert_parity(y / scale, ref / scale, "single-SM synthesis M=%d m=%d" % (M, m))
     # whole batches only: ONE launch per call, the kernel writes the next state (the last 32 input frames) itself
     q2 = yb.FirPfbCh2.new(S, M, m, h)
     outs = []
@@ -769,12 +769,11 @@ def test_single_sm_M1024_synthesis(m):
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
 
 
-@pytest.mark.parametrize("m", [1, 3])
-def test_single_sm_M1024_analysis_state_in_kernel(m):
-    """The one-CTA-per-SM analysis kernel also writes the object's next state (one launch per call): uneven calls,
-    odd-parity starts and a call shorter than the history, against the CPU path."""
-    M = 1024
-    K = 2600
+@pytest.mark.parametrize("M,m", [(1024, 1), (1024, 3), (512, 1), (512, 2), (512, 3), (512, 4), (512, 5), (512, 6), (512, 7)])
+def test_single_sm_analysis_state_in_kernel(M, m):
+    """The one-CTA-per-SM analysis kernels (M = 1024, m <= 4; M = 512, m <= 7) also write the object's next state (one
+    launch per call): uneven calls, odd-parity starts and a call shorter than the history, against the CPU path."""
+    K = 2600 if M == 1024 else 5200
     rng = np.random.default_rng(5200 + m)
     h = rng.standard_normal(2 * M * m).astype(np.float32)
     x = _rand_c(rng, K * M // 2)
@@ -785,10 +784,10 @@ def test_single_sm_M1024_analysis_state_in_kernel(m):
     for a, b in zip(cuts, cuts[1:]):
         n0 = yb.launch_count()
         outs.append(q.execute_block(x[a * M // 2: b * M // 2]))
-        if b - a >= 64 and (b - a) % 4 == 0 and a % 2 == 0:
+        if b - a >= 64 and (b - a) % (4 if M == 1024 else 8) == 0 and a % 2 == 0:
             assert q.last_path() == 3 and yb.launch_count() - n0 == 1, (a, b, yb.launch_count() - n0)
     y = np.concatenate(outs).reshape(K, M)
     scale = max(1.0, np.abs(ref).max())
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
-    assert_parity(y / scale, ref / scale, "single-SM analysis M=1024 m=%d" % m)
+    assert_parity(y / scale, ref / scale, "single-SM analysis M=%d m=%d" % (M, m))

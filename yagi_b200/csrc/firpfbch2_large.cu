@@ -915,6 +915,280 @@ inline int32_t prepare(uint32_t m)
 }
 }  // namespace s1k
 
+// ------------------------------------------------------------------ single-SM fused analysis kernel: M = 512, m <= 7
+// s1k re-cut for half the frame length: a pair of input is 4 KB, so the same 128 KB ring holds 32 pairs (16 of history,
+// enough for 15 taps per branch), a batch is FOUR pairs (still one 16 KB bulk copy, still 32 KB of V), a FIR thread owns
+// the taps of TWO branches (t, t + 256; 60 registers at m = 7) and walks the batch as two half-batches of two pairs, and a
+// DFT warp takes a PAIR of frames: 16 x 32 -- lane n2 runs the 16-point transforms over n1 of both frames, one
+// XOR-swizzled exchange in place in the pair's 8 KB of V, lane (frame, k1) runs one 32-point transform over n2.
+namespace s5k {
+constexpr int kM = 512, kM2 = 256;
+constexpr int kBP = 4;                                   // frame pairs per batch
+constexpr int kStages = 8;                               // ring of 8 batches = 32 pairs
+constexpr int kStageBytes = kBP * kM * 8;                // 16 KB
+constexpr int kRowBytes = kM * 8;                        // one pair of input = one frame of V = 4 KB
+constexpr int kHistPairs = 16;                           // ring rows 0-15 hold the pairs before the slab
+constexpr int kVBufBytes = 2 * kBP * kRowBytes;          // 8 frames
+constexpr int kOffV = kStages * kStageBytes;             // 131072
+constexpr int kOffTw = kOffV + 2 * kVBufBytes;           // W512^{lane k1} as [k1 / 2][lane] float4 (k1 even, k1 odd): 4 KB
+constexpr int kOffBar = kOffTw + 4096;
+constexpr int kBarInFull = 0;                            // [8] TMA transaction barriers
+constexpr int kBarInFree = 8;                            // [8] the 8 FIR warps no longer need the stage
+constexpr int kBarVFull = 16;                            // [2] the 8 FIR warps have written the buffer
+constexpr int kBarVFree = 18;                            // [2] its 4 DFT warps have read it
+constexpr int kBarHist = 20;                             // the part of the slab's history pairs that is copied from x
+constexpr int kSmem = kOffBar + 21 * 8;
+constexpr int kThreads = 512;
+constexpr int kMaxM = 7;
+// column of branch t + 256 k inside a pair of input, plus t: pos(j) = (255 - j) mod 512
+__host__ __device__ constexpr int pos_k(int k) { return k == 0 ? 255 : 511; }
+
+template <int kTaps>
+__device__ __forceinline__ void fir_role(const LargeParams& p, uint32_t smem, long long b0, long long b1)
+{
+    constexpr int kHist = kTaps - 1;                     // pairs of history a window reaches back (<= 14)
+    const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
+    const uint32_t bar = smem + kOffBar;
+
+    const long long call_off = p.f0 * kM2;
+    const long long q_first = p.pair_begin + b0 * kBP;   // first pair of the slab, relative to f0
+    const float2* xb = p.x + call_off + q_first * kM;    // its first sample
+    const long long nb = b1 - b0;
+
+    auto issue_load = [&](long long lb) {                // local batch lb -> stage (lb + 4) mod 8
+        const int st = (int)((lb + 4) & 7);
+        mbar_expect_tx(bar + 8 * (kBarInFull + st), kStageBytes);
+        tma_load_1d(smem + st * kStageBytes, xb + lb * (long long)(kBP * kM), kStageBytes, bar + 8 * (kBarInFull + st));
+    };
+    // the sixteen pairs before the slab (ring rows 0-15): bulk copies for what lies inside x, plain loads for the rest
+    constexpr int kHead = kHistPairs * kM;               // 8192 samples
+    const long long ta0 = (q_first - kHistPairs) * kM + call_off;
+    const int n_head = ta0 >= 0 ? 0 : (int)min(-ta0, (long long)kHead);
+    if (t == 0) {
+        pdl_wait();                                      // x and the history may come from the previous kernel
+        if (n_head < kHead) {
+            const uint32_t bytes = (uint32_t)(kHead - n_head) * 8;
+            mbar_expect_tx(bar + 8 * kBarHist, bytes);
+            for (uint32_t off = 0; off < bytes; off += 16384)
+                tma_load_1d(smem + n_head * 8 + off, p.x + (ta0 + n_head) + off / 8, min(16384u, bytes - off), bar + 8 * kBarHist);
+        }
+        for (long long lb = 0; lb < 4 && lb < nb; lb++) issue_load(lb);
+    }
+
+    float2 T[2][kTaps];                                  // taps of branches t, t + 256
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int i = 0; i < kTaps; i++) T[k][i] = __ldg(&p.taps[(t + 256 * k) * kTaps + i]);
+    pdl_wait();
+
+    for (int i0 = 0; i0 < n_head; i0 += 8 * 256) {       // eight loads in flight per thread
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int idx = i0 + u * 256 + t;
+            const long long ta = ta0 + idx;
+            v[u] = make_float2(0.f, 0.f);
+            if (idx < n_head && p.Hlen + ta >= 0) v[u] = __ldg(&p.hist[p.Hlen + ta]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int idx = i0 + u * 256 + t;
+            if (idx < n_head) sts64(smem + idx * 8, v[u]);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // these rows are overwritten by bulk copies later
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (n_head < kHead) mbar_wait(bar + 8 * kBarHist, 0);
+
+    const uint32_t ring_t = smem - t * 8;
+    const uint32_t v_t = smem + kOffV + t * 8;
+
+    auto do_batch = [&](auto ph_tag, long long lb) {
+        constexpr int PH = decltype(ph_tag)::value;      // lb mod 8: every ring row below is a compile-time constant
+        constexpr int ST = (PH + 4) & 7;
+        constexpr int BUF = PH & 1;
+        mbar_wait(bar + 8 * (kBarInFull + ST), (uint32_t)((lb >> 3) & 1));       // the batch's own four pairs have landed
+#pragma unroll
+        for (int half = 0; half < 2; half++)
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                float2 w[kTaps + 1];                     // u[q0 - kHist .. q0 + 1], q0 = 4 lb + 2 half
+#pragma unroll
+                for (int i = 0; i <= kTaps; i++)
+                    w[i] = lds64(ring_t + ((4 * PH + 2 * half + kHistPairs - kHist + i) & 31) * kRowBytes + pos_k(k) * 8);
+                float2 e0 = make_float2(0.f, 0.f), o0 = e0, e1 = e0, o1 = e0;
+#pragma unroll
+                for (int i = kTaps - 1; i >= 0; i--) {   // oldest sample first, as K1
+                    e0 = fma2(w[kHist - i], f2(T[k][i].x), e0);
+                    o0 = fma2(w[kHist - i], f2(T[k][i].y), o0);
+                    e1 = fma2(w[kHist + 1 - i], f2(T[k][i].x), e1);
+                    o1 = fma2(w[kHist + 1 - i], f2(T[k][i].y), o1);
+                }
+                if (half == 0 && k == 0 && lb >= 2) mbar_wait(bar + 8 * (kBarVFree + BUF), (uint32_t)(((lb >> 1) - 1) & 1));
+                const uint32_t vo = v_t + BUF * kVBufBytes + (4 * half) * kRowBytes + k * (256 * 8);
+                sts64(vo + 0 * kRowBytes, e0);                           // pair 2 half: even frame
+                sts64(vo + 1 * kRowBytes, o0);                           //              odd frame
+                sts64(vo + 2 * kRowBytes, e1);                           // pair 2 half + 1
+                sts64(vo + 3 * kRowBytes, o1);
+            }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(bar + 8 * (kBarVFull + BUF));
+            mbar_arrive(bar + 8 * (kBarInFree + PH));    // the pairs of batch lb - 4 (stage lb mod 8) are out of every later window
+            if (wrp == PH && lb + 4 < nb) {              // the FIR warps take turns refilling that stage with batch lb + 4
+                mbar_wait(bar + 8 * (kBarInFree + PH), (uint32_t)((lb >> 3) & 1));
+                issue_load(lb + 4);
+            }
+        }
+    };
+    for (long long lb = 0; lb < nb; lb += 8) {
+        do_batch(std::integral_constant<int, 0>{}, lb);
+        if (lb + 1 < nb) do_batch(std::integral_constant<int, 1>{}, lb + 1);
+        if (lb + 2 < nb) do_batch(std::integral_constant<int, 2>{}, lb + 2);
+        if (lb + 3 < nb) do_batch(std::integral_constant<int, 3>{}, lb + 3);
+        if (lb + 4 < nb) do_batch(std::integral_constant<int, 4>{}, lb + 4);
+        if (lb + 5 < nb) do_batch(std::integral_constant<int, 5>{}, lb + 5);
+        if (lb + 6 < nb) do_batch(std::integral_constant<int, 6>{}, lb + 6);
+        if (lb + 7 < nb) do_batch(std::integral_constant<int, 7>{}, lb + 7);
+    }
+}
+
+// 512-point backward DFTs of the two frames in `tile` (frame h at tile + 4096 h, natural order), in place as far as the
+// exchange goes; on return lane (h, k1) = (lane >> 4, lane & 15) holds X_h[k1 + 16 k2] in v[dr32(k2)].  `twt` = this
+// lane's column of the shared twiddle table; `on_read` runs when the tile has been read for the last time.
+template <typename F>
+__device__ __forceinline__ void pair_dft512(float2 (&v)[32], uint32_t tile, uint32_t twt, int lane, F on_read)
+{
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) v[16 * h + n1] = lds64(tile + h * 4096 + (32 * n1 + lane) * 8);
+    xdft16<0>(v);
+    xdft16<16>(v);
+    __syncwarp();                                        // every lane has read both frames: exchange in place
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        const float4 w = lds128(twt + a * 512);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            float2 z0 = v[16 * h + dr4(2 * a)], z1 = v[16 * h + dr4(2 * a + 1)];
+            if (a > 0) z0 = xmul(z0, w.x, w.y);
+            z1 = xmul(z1, w.z, w.w);
+            sts64(tile + (((h << 9) | (lane << 4) | ((2 * a) ^ (lane & 15))) << 3), z0);
+            sts64(tile + (((h << 9) | (lane << 4) | ((2 * a + 1) ^ (lane & 15))) << 3), z1);
+        }
+    }
+    __syncwarp();
+    const int h = lane >> 4, k1 = lane & 15;
+#pragma unroll
+    for (int n2 = 0; n2 < 32; n2++) v[n2] = lds64(tile + (((h << 9) | (n2 << 4) | (k1 ^ (n2 & 15))) << 3));
+    __syncwarp();
+    on_read();
+    xdft32c(v);
+}
+
+__device__ __forceinline__ void dft_role(const LargeParams& p, uint32_t smem, long long b0, long long b1)
+{
+    const int dt = threadIdx.x - 256, lane = dt & 31, dw = dt >> 5;
+    const int buf = dw >> 2, fi = dw & 3;                // this warp's V buffer and frame pair of the batch
+    const uint32_t bar = smem + kOffBar;
+    const uint32_t tile = smem + kOffV + buf * kVBufBytes + fi * (2 * kRowBytes);
+    const uint32_t twt = smem + kOffTw + lane * 16;
+    const long long nb = b1 - b0;
+    pdl_wait();                                          // nothing is written before the previous kernel has completed
+    if (p.hist_new != nullptr) {                         // every CTA copies a slice of the object's next state
+        const long long per = (p.Hlen + gridDim.x - 1) / gridDim.x;
+        const long long i1 = min(p.Hlen, per * (long long)(blockIdx.x + 1));
+        for (long long i = per * blockIdx.x + dt; i < i1; i += 256) {
+            const long long ts = p.n_new - p.Hlen + i;
+            p.hist_new[i] = (ts >= 0) ? __ldg(&p.x[ts]) : __ldg(&p.hist[p.Hlen + ts]);
+        }
+    }
+    for (long long lb = buf; lb < nb; lb += 2) {
+        mbar_wait(bar + 8 * (kBarVFull + buf), (uint32_t)((lb >> 1) & 1));
+        float2 v[32];
+        pair_dft512(v, tile, twt, lane, [&] { if (lane == 0) mbar_arrive(bar + 8 * (kBarVFree + buf)); });
+        const long long q = p.pair_begin + (b0 + lb) * kBP + fi;
+        float2* fr = p.y + (p.f0 + 2 * q + (lane >> 4)) * (long long)kM + (lane & 15);
+#pragma unroll
+        for (int k2 = 0; k2 < 32; k2++) __stcs(fr + 16 * k2, v[dr32(k2)]);
+    }
+}
+
+__device__ __forceinline__ void fill_twiddles(uint32_t smem_tw, const float2* __restrict__ twid)
+{
+    for (int i = threadIdx.x; i < 512; i += kThreads) {               // entry i: k1 = 2 (i >> 6) + (i & 1), lane = (i >> 1) & 31
+        const int k1 = 2 * (i >> 6) + (i & 1), ln = (i >> 1) & 31;
+        sts64(smem_tw + i * 8, __ldg(&twid[ln * k1]));
+    }
+}
+
+template <int kTaps>
+__global__ void __launch_bounds__(kThreads, 1) k_m512_fused(const LargeParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t smem = smem_u32(smem_raw);
+    const long long n_batches = (p.pair_end - p.pair_begin) / kBP;
+    const long long b0 = (n_batches * blockIdx.x) / gridDim.x, b1 = (n_batches * (blockIdx.x + 1)) / gridDim.x;
+    if (threadIdx.x == 0) {
+        const uint32_t bar = smem + kOffBar;
+        for (int i = 0; i < 8; i++) mbar_init(bar + 8 * (kBarInFull + i), 1);
+        for (int i = 0; i < 8; i++) mbar_init(bar + 8 * (kBarInFree + i), 8);
+        for (int i = 0; i < 2; i++) mbar_init(bar + 8 * (kBarVFull + i), 8);
+        for (int i = 0; i < 2; i++) mbar_init(bar + 8 * (kBarVFree + i), 4);
+        mbar_init(bar + 8 * kBarHist, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    fill_twiddles(smem + kOffTw, p.twid);
+    __syncthreads();
+    pdl_launch_dependents();
+    if (b0 >= b1) return;                                // never taken: the grid has at most one CTA per batch
+    if (threadIdx.x < 256) fir_role<kTaps>(p, smem, b0, b1);
+    else dft_role(p, smem, b0, b1);
+}
+
+template <int kTaps>
+int32_t launch(const Firpfbch2FastPlan& plan, const LargeParams& p, cudaStream_t st)
+{
+    const long long n_batches = (p.pair_end - p.pair_begin) / kBP;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min<long long>(plan.n_sm, n_batches));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = plan.pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    YG_CUDA(cudaLaunchKernelEx(&cfg, k_m512_fused<kTaps>, p));
+    count_launch();
+    return YG_OK;
+}
+
+template <int kTaps>
+int32_t prepare_one() { YG_CUDA(cudaFuncSetAttribute(k_m512_fused<kTaps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); return YG_OK; }
+
+// per tap count: f(std::integral_constant<int, 2 m + 1>) for m = 1 .. 7
+template <typename F>
+int32_t for_m(uint32_t m, F f)
+{
+    switch (m) {
+        case 1: return f(std::integral_constant<int, 3>{});
+        case 2: return f(std::integral_constant<int, 5>{});
+        case 3: return f(std::integral_constant<int, 7>{});
+        case 4: return f(std::integral_constant<int, 9>{});
+        case 5: return f(std::integral_constant<int, 11>{});
+        case 6: return f(std::integral_constant<int, 13>{});
+        case 7: return f(std::integral_constant<int, 15>{});
+        default: return fail(YG_EINTERNAL, "single-SM M = 512 kernel not instantiated for m = %u", m);
+    }
+}
+inline int32_t prepare(uint32_t m) { return for_m(m, [](auto tag) { return prepare_one<decltype(tag)::value>(); }); }
+}  // namespace s5k
+
 int32_t launch_fft(const Firpfbch2FastPlan& plan, const float2* prefix, const float2* x, long long v0, float2* dst,
                    long long n_frames, int streaming, cudaStream_t st)
 {
@@ -1481,6 +1755,217 @@ inline int32_t prepare(uint32_t m)
 }
 }  // namespace s1ks
 
+// ------------------------------------------------------------------ single-SM fused synthesis kernel: M = 512, m <= 7
+// s1ks re-cut for half the frame length: a stage of the frame ring holds EIGHT input frames (still 32 KB), each of its four
+// DFT warps transforms a PAIR of frames in place (s5k::pair_dft512), and an overlap-add thread owns ONE output sample
+// i = t with its 2m + 2m running sums (56 registers at m = 7) and 4m taps.  The sums rotate with a period of 2m pairs
+// while a batch is four pairs, so one period of lcm(2m, 4) pairs is unrolled; the warm-up (ceil(2m / 4) batches before
+// the slab, at most the 32 frames of kept prefix) is a run-time flag per batch.
+namespace s5ks {
+constexpr int kM = 512, kM2 = 256;
+constexpr int kFB = 8;                                   // frames per batch
+constexpr int kFrameBytes = kM * 8;
+constexpr int kStageBytes = kFB * kFrameBytes;           // 32 KB
+constexpr int kStages = 6;
+constexpr int kOffTw = kStages * kStageBytes;            // the s5k twiddle table: 4 KB
+constexpr int kOffBar = kOffTw + 4096;
+constexpr int kBarInFull = 0;                            // [6] TMA transaction barriers
+constexpr int kBarUFull = 6;                             // [6] the stage's four DFT warps have transformed it
+constexpr int kBarFree = 12;                             // [6] the eight overlap-add warps have read it
+constexpr int kOffSrc = kOffBar + 18 * 8;                // address of the slab's local frame 0 in x (refills never reach the prefix)
+constexpr int kSmem = kOffSrc + 8;
+constexpr int kThreads = 512;
+constexpr int kMaxM = 7;
+using Params = s1ks::Params;                             // taps: [512][4m]  h[(j & 255) + l * 256] / 2
+
+template <int kL>                                        // kL = 2m: pairs of frames a sum collects
+__device__ __forceinline__ void ola_role(const Params& p, uint32_t smem, long long b0, long long b1)
+{
+    constexpr int kWarm = (kL + 3) / 4;                  // warm-up batches (>= kL pairs)
+    constexpr int kPer = (kL % 4 == 0 ? kL : kL % 4 == 2 ? 2 * kL : 4 * kL) / 4;      // batches per rotation period
+    static_assert(kStages > kWarm, "refills must lie inside x");
+    const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
+    const uint32_t bar = smem + kOffBar;
+
+    const int nb = (int)(b1 - b0) + kWarm;               // local batches, warm-up first
+    const long long fr_base = p.f0 + (b0 - kWarm) * kFB; // call-relative frame of local batch 0 (>= -32)
+    auto issue_load = [&](int lb, int stg) {
+        const uint32_t fb = bar + 8 * (kBarInFull + stg);
+        const uint32_t dst = smem + stg * kStageBytes;
+        const long long fr = fr_base + (long long)lb * kFB;
+        mbar_expect_tx(fb, kStageBytes);
+        if (fr >= 0) tma_load_1d(dst, p.x + fr * kM, kStageBytes, fb);
+        else if (fr + kFB <= 0) tma_load_1d(dst, p.prefix + (32 + fr) * kM, kStageBytes, fb);
+        else
+            for (int k = 0; k < kFB; k++)
+                tma_load_1d(dst + k * kFrameBytes, fr + k >= 0 ? p.x + (fr + k) * kM : p.prefix + (32 + fr + k) * kM, kFrameBytes, fb);
+    };
+    if (t == 0) {                                        // first of all: get the copies going
+        pdl_wait();                                      // x and the prefix may come from the previous kernel
+        for (int lb = 0; lb < kStages && lb < nb; lb++) issue_load(lb, lb);
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(smem + kOffSrc), "l"(p.x + fr_base * kM) : "memory");
+    }
+
+    float A[kL], B[kL];                                  // taps of even / odd lag of output t
+#pragma unroll
+    for (int j = 0; j < kL; j++) {
+        A[j] = __ldg(&p.taps[t * (2 * kL) + 2 * j]);
+        B[j] = __ldg(&p.taps[t * (2 * kL) + 2 * j + 1]);
+    }
+    float2 E[kL], O[kL];                                 // running sums of the even- and odd-frame outputs
+#pragma unroll
+    for (int j = 0; j < kL; j++) E[j] = O[j] = make_float2(0.f, 0.f);
+    pdl_wait();                                          // nothing is written before the previous kernel has completed
+
+    float2* yo = p.y + fr_base * kM2 + t;                // output of the current batch's first frame
+    int st = 0;
+    uint32_t ph = 0;
+    for (int lb0 = 0; lb0 < nb; lb0 += kPer) {
+#pragma unroll
+        for (int bb = 0; bb < kPer; bb++) {
+            const int lb = lb0 + bb;
+            if (lb >= nb) break;
+            const bool emit = lb >= kWarm;               // the first batches only warm the sums up
+            mbar_wait(bar + 8 * (kBarUFull + st), ph);
+            const uint32_t fr = smem + st * kStageBytes + t * 8;
+#pragma unroll
+            for (int pq = 0; pq < 4; pq++) {
+                const int pp = (4 * bb + pq) % kL;       // pair within the rotation: every register index below is a constant
+                const uint32_t a = fr + 2 * pq * kFrameBytes;
+                // outputs of the even frames g, g + 2, ...: lag 2j from u_g, lag 2j + 1 from u_{g+1} (to g + 2 + 2j)
+                const float2 ue = lds64(a);                                      // column i of the even frame
+#pragma unroll
+                for (int j = 0; j < kL; j++) E[(pp + j) % kL] = fma2(ue, f2(A[j]), E[(pp + j) % kL]);
+                if (emit) __stcs(yo + 2 * pq * kM2, E[pp % kL]);
+                const float2 uo = lds64(a + kFrameBytes);                        //            of the odd frame
+#pragma unroll
+                for (int j = 0; j < kL - 1; j++) E[(pp + 1 + j) % kL] = fma2(uo, f2(B[j]), E[(pp + 1 + j) % kL]);
+                E[pp % kL] = mul2(uo, f2(B[kL - 1]));
+                // outputs of the odd frames g + 1, g + 3, ...: lag 2j + 1 from u_g, lag 2j from u_{g+1}
+                const float2 ve = lds64(a + kM2 * 8);                            // column i + 256 of the even frame
+                O[(pp + kL - 1) % kL] = mul2(ve, f2(B[kL - 1]));
+#pragma unroll
+                for (int j = 0; j < kL - 1; j++) O[(pp + j) % kL] = fma2(ve, f2(B[j]), O[(pp + j) % kL]);
+                const float2 vo = lds64(a + kFrameBytes + kM2 * 8);              //                 of the odd frame
+#pragma unroll
+                for (int j = 0; j < kL; j++) O[(pp + j) % kL] = fma2(vo, f2(A[j]), O[(pp + j) % kL]);
+                if (emit) __stcs(yo + (2 * pq + 1) * kM2, O[pp % kL]);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar + 8 * (kBarFree + st));
+                if (wrp == (lb & 7) && lb + kStages < nb) {          // the overlap-add warps take turns refilling the stage
+                    mbar_wait(bar + 8 * (kBarFree + st), ph);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the DFT warps wrote it with plain stores
+                    unsigned long long src;
+                    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(src) : "r"(smem + kOffSrc) : "memory");
+                    mbar_expect_tx(bar + 8 * (kBarInFull + st), kStageBytes);
+                    tma_load_1d(smem + st * kStageBytes, reinterpret_cast<const char*>(src) + (long long)(lb + kStages) * kStageBytes,
+                                kStageBytes, bar + 8 * (kBarInFull + st));
+                }
+            }
+            yo += kFB * kM2;
+            if (++st == kStages) { st = 0; ph ^= 1; }
+        }
+    }
+}
+
+__device__ __forceinline__ void dft_role(const Params& p, uint32_t smem, int nb)
+{
+    const int dt = threadIdx.x - 256, lane = dt & 31, dw = dt >> 5;
+    const int grp = dw >> 2, fi = dw & 3;                // batches of this warp's parity, frame pair fi of each
+    const uint32_t bar = smem + kOffBar;
+    const uint32_t twt = smem + kOffTw + lane * 16;
+    if (p.hist_new != nullptr) {                         // every CTA copies a slice of the next state (the tail of the input stream)
+        constexpr long long kH = 32 * kM;
+        pdl_wait();                                      // nothing is written before the previous kernel has completed
+        const long long per = (kH / 2 + gridDim.x - 1) / gridDim.x;
+        const long long i1 = min(kH / 2, per * (long long)(blockIdx.x + 1));
+        for (long long i = per * blockIdx.x + dt; i < i1; i += 256) {            // 16 bytes per thread and turn
+            const long long ts = p.n_new - kH + 2 * i;
+            reinterpret_cast<float4*>(p.hist_new)[i] = __ldg(reinterpret_cast<const float4*>(ts >= 0 ? p.x + ts : p.prefix + (kH + ts)));
+        }
+    }
+    int st = grp;
+    uint32_t ph = 0;
+    for (int lb = grp; lb < nb; lb += 2) {
+        mbar_wait(bar + 8 * (kBarInFull + st), ph);
+        const uint32_t tile = smem + st * kStageBytes + fi * (2 * kFrameBytes);
+        float2 v[32];
+        s5k::pair_dft512(v, tile, twt, lane, [] {});
+        const uint32_t uo = tile + (lane >> 4) * kFrameBytes + (lane & 15) * 8;
+#pragma unroll
+        for (int k2 = 0; k2 < 32; k2++) sts64(uo + 16 * k2 * 8, v[dr32(k2)]);    // U in natural order
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + 8 * (kBarUFull + st));
+        st += 2;
+        if (st >= kStages) { st -= kStages; ph ^= 1; }
+    }
+}
+
+template <int kL>
+__global__ void __launch_bounds__(kThreads, 1) k_m512_synth_fused(const Params p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t smem = smem_u32(smem_raw);
+    const long long b0 = (p.n_batches * blockIdx.x) / gridDim.x, b1 = (p.n_batches * (blockIdx.x + 1)) / gridDim.x;
+    if (threadIdx.x == 0) {
+        const uint32_t bar = smem + kOffBar;
+        for (int i = 0; i < kStages; i++) {
+            mbar_init(bar + 8 * (kBarInFull + i), 1);
+            mbar_init(bar + 8 * (kBarUFull + i), 4);
+            mbar_init(bar + 8 * (kBarFree + i), 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    s5k::fill_twiddles(smem + kOffTw, p.twid);
+    __syncthreads();
+    pdl_launch_dependents();
+    if (b0 >= b1) return;                                // never taken: the grid has at most one CTA per batch
+    if (threadIdx.x < 256) s5ks::ola_role<kL>(p, smem, b0, b1);           // (qualified: Params is s1ks's, so ADL would find both)
+    else s5ks::dft_role(p, smem, (int)(b1 - b0) + (kL + 3) / 4);
+}
+
+template <int kL>
+int32_t launch(const Firpfbch2FastPlan& plan, const Params& p, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min<long long>(plan.n_sm, p.n_batches));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = plan.pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    YG_CUDA(cudaLaunchKernelEx(&cfg, k_m512_synth_fused<kL>, p));
+    count_launch();
+    return YG_OK;
+}
+
+template <int kL>
+int32_t prepare_one() { YG_CUDA(cudaFuncSetAttribute(k_m512_synth_fused<kL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); return YG_OK; }
+
+// per filter length: f(std::integral_constant<int, 2 m>) for m = 1 .. 7
+template <typename F>
+int32_t for_m(uint32_t m, F f)
+{
+    switch (m) {
+        case 1: return f(std::integral_constant<int, 2>{});
+        case 2: return f(std::integral_constant<int, 4>{});
+        case 3: return f(std::integral_constant<int, 6>{});
+        case 4: return f(std::integral_constant<int, 8>{});
+        case 5: return f(std::integral_constant<int, 10>{});
+        case 6: return f(std::integral_constant<int, 12>{});
+        case 7: return f(std::integral_constant<int, 14>{});
+        default: return fail(YG_EINTERNAL, "single-SM M = 512 synthesis kernel not instantiated for m = %u", m);
+    }
+}
+inline int32_t prepare(uint32_t m) { return for_m(m, [](auto tag) { return prepare_one<decltype(tag)::value>(); }); }
+}  // namespace s5ks
+
 template <int kTaps>
 int32_t launch_wola(const WolaParams& p, cudaStream_t st)
 {
@@ -1611,10 +2096,10 @@ int32_t firpfbch2_large_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
     YG_CUDA(yg::memcpy_sync(plan.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
     YG_TRY(plan_common(plan, M));
     if (plan.supported) YG_TRY(plan_fused(plan, false));
-    if (plan.supported && M == 1024 && 2 * m + 1 <= (uint32_t)s1k::kMaxTaps) {
+    if (plan.supported && ((M == 1024 && 2 * m + 1 <= (uint32_t)s1k::kMaxTaps) || (M == 512 && m <= (uint32_t)s5k::kMaxM))) {
         const char* e = getenv("YG_LARGE_SINGLE_SM");     // debugging knob: 0 keeps the group kernel
         plan.single_sm = !(e && e[0] == '0');
-        if (plan.single_sm) YG_TRY(s1k::prepare(m));
+        if (plan.single_sm) YG_TRY(M == 1024 ? s1k::prepare(m) : s5k::prepare(m));
         const char* d = getenv("YG_PDL");
         plan.pdl = !(d && d[0] == '0');
     }
@@ -1632,7 +2117,8 @@ int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist
     const long long n_pairs = (long long)(n_frames / 2);
     long long fused_pairs = 0;
     if (plan.single_sm && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {         // M = 1024, m <= 4: one CTA per SM, no exchange
-        fused_pairs = (n_pairs / s1k::kBP) * s1k::kBP;
+        const int bp = M == 1024 ? s1k::kBP : s5k::kBP;
+        fused_pairs = (n_pairs / bp) * bp;
         if (fused_pairs > 0) {
             LargeParams p;
             p.hist = hist; p.Hlen = Hlen; p.x = x; p.y = y;
@@ -1644,7 +2130,8 @@ int32_t firpfbch2_large_launch(const Firpfbch2FastPlan& plan, const float2* hist
             p.taps = reinterpret_cast<const float2*>(plan.d_taps);
             p.twid = reinterpret_cast<const float2*>(plan.d_twid);
             if (hist_done && hist_new) { p.hist_new = hist_new; p.n_new = n_new; *hist_done = true; }
-            switch (plan.m) {
+            if (M == 512) YG_TRY(s5k::for_m(plan.m, [&](auto tag) { return s5k::launch<decltype(tag)::value>(plan, p, st); }));
+            else switch (plan.m) {
                 case 1: YG_TRY(s1k::launch<3>(plan, p, st)); break;
                 case 2: YG_TRY(s1k::launch<5>(plan, p, st)); break;
                 case 3: YG_TRY(s1k::launch<7>(plan, p, st)); break;
@@ -1730,10 +2217,10 @@ int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t
     YG_CUDA(yg::memcpy_sync(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
     YG_TRY(plan_common(plan, M));
     if (plan.supported) YG_TRY(plan_fused(plan, true));
-    if (plan.supported && M == 1024 && m <= (uint32_t)s1ks::kMaxM) {
+    if (plan.supported && ((M == 1024 && m <= (uint32_t)s1ks::kMaxM) || (M == 512 && m <= (uint32_t)s5ks::kMaxM))) {
         const char* e = getenv("YG_LARGE_SINGLE_SM");     // debugging knob: 0 keeps the group kernel
         plan.single_sm = !(e && e[0] == '0');
-        if (plan.single_sm) YG_TRY(s1ks::prepare(m));
+        if (plan.single_sm) YG_TRY(M == 1024 ? s1ks::prepare(m) : s5ks::prepare(m));
         const char* d = getenv("YG_PDL");
         plan.pdl = !(d && d[0] == '0');
     }
@@ -1769,11 +2256,12 @@ int32_t firpfbch2_large_synth_launch(const Firpfbch2FastPlan& plan, const float2
         s1ks::Params p;
         p.prefix = prefix; p.x = x; p.y = y;
         p.f0 = (long long)f0;
-        p.n_batches = (long long)(n_frames / s1ks::kFB);
+        p.n_batches = (long long)(n_frames / (M == 1024 ? s1ks::kFB : s5ks::kFB));
         p.taps = reinterpret_cast<const float*>(plan.d_taps);
         p.twid = reinterpret_cast<const float2*>(plan.d_twid);
         p.hist_new = nullptr; p.n_new = 0;
         if (hist_done && hist_new) { p.hist_new = hist_new; p.n_new = n_new; *hist_done = true; }     // x and the prefix are 16-byte aligned here
+        if (M == 512) return s5ks::for_m(plan.m, [&](auto tag) { return s5ks::launch<decltype(tag)::value>(plan, p, st); });
         switch (plan.m) {
             case 1: return s1ks::launch<2>(plan, p, st);
             case 2: return s1ks::launch<4>(plan, p, st);
