@@ -101,7 +101,10 @@ def main():
             report("firpfbch2 synthesis M=%d m=7 N=2^27 out (path %d)" % (M, qs.last_path()), ms, 24.0 * No, No, "samples_out")
             del Y, y, qs
     if "largeM" in which:
-        for M, m in ((512, 7), (2048, 4), (4096, 4)):
+        geoms = ((512, 7), (2048, 4), (4096, 4))
+        if os.environ.get("YG_LARGE_GEOM"):                     # e.g. YG_LARGE_GEOM=512:4,512:7
+            geoms = tuple(tuple(int(v) for v in g.split(":")) for g in os.environ["YG_LARGE_GEOM"].split(","))
+        for M, m in geoms:
             N = 1 << 26
             x = randc(N)
             Y = torch.empty(2 * N, dtype=torch.complex64, device="cuda")
