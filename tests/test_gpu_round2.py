@@ -791,3 +791,51 @@ def test_single_sm_analysis_state_in_kernel(M, m):
     per_frame = np.abs(y - ref).max(axis=1) / scale
     assert per_frame.max() <= 1e-4, int(per_frame.argmax())
     assert_parity(y / scale, ref / scale, "single-SM analysis M=%d m=%d" % (M, m))
+
+
+# ------------------------------------------------------------------ generic kernels: mixed-radix transform for any even M
+@pytest.mark.parametrize("M,m", [(10, 3), (18, 2), (24, 4), (48, 5), (50, 2), (60, 3), (66, 2), (74, 1), (96, 4), (100, 5),
+                                 (120, 3), (126, 2), (202, 2), (240, 4), (250, 3), (384, 9), (768, 2), (1000, 4),
+                                 (1536, 3), (3000, 1), (256, 10), (64, 12)])
+def test_generic_kernels_any_even_M(M, m):
+    """Geometries without a fused kernel (M not a power of two, or m beyond the fused range) run on the generic
+    kernels, whose transform is a mixed-radix Stockham (one pass per prime factor, 4 before 2; a prime factor p costs
+    p MACs per bin -- M = 202 = 2 x 101 exercises a large one): analysis, then synthesis of the channel frames, against
+    the CPU path over several uneven calls, and the transform alone (delta prototype) against numpy's f64 FFT."""
+    rng = np.random.default_rng(6000 + M + m)
+    K = max(24, min(600, (1 << 17) // M))
+    h = rng.standard_normal(2 * M * m).astype(np.float32)
+    x = _rand_c(rng, K * M // 2)
+    ref = po.FirPfbCh2.new(po.ANALYZER, M, m, h).execute_block(x).reshape(K, M)
+    q = yb.FirPfbCh2.new(A, M, m, h)
+    cuts = [0, 1, 8, K // 2 + 1, K]
+    y = np.concatenate([q.execute_block(x[a * M // 2: b * M // 2]) for a, b in zip(cuts, cuts[1:])]).reshape(K, M)
+    assert q.last_path() == 1
+    scale = max(1.0, np.abs(ref).max())
+    per_frame = np.abs(y - ref).max(axis=1) / scale
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+    assert_parity(y / scale, ref / scale, "generic analysis M=%d m=%d" % (M, m))
+    refs = po.FirPfbCh2.new(po.SYNTHESIZER, M, m, h).execute_block(ref.reshape(-1)).reshape(K, M // 2)
+    qs = yb.FirPfbCh2.new(S, M, m, h)
+    ys = np.concatenate([qs.execute_block(ref.reshape(-1)[a * M: b * M]) for a, b in zip(cuts, cuts[1:])]).reshape(K, M // 2)
+    assert qs.last_path() == 1
+    sc = max(1.0, np.abs(refs).max())
+    per_frame = np.abs(ys - refs).max(axis=1) / sc
+    assert per_frame.max() <= 1e-4, int(per_frame.argmax())
+    assert_parity(ys / sc, refs / sc, "generic synthesis M=%d m=%d" % (M, m))
+    # oracle-free: delta prototype h[n] = [n < M] makes frame k of the analyser M^-1 * IDFT_unnorm of the (rotated) last M
+    # input samples, i.e. numpy.fft.ifft of them
+    hd = np.zeros(2 * M * m, dtype=np.float32)
+    hd[:M] = 1.0
+    qd = yb.FirPfbCh2.new(A, M, m, hd)
+    Kd = 16
+    xd = _rand_c(rng, Kd * M // 2)
+    yd = qd.execute_block(xd).reshape(Kd, M)
+    xs = np.concatenate([np.zeros(M, dtype=np.complex128), xd.astype(np.complex128)])
+    for k in range(2, Kd):
+        tk = (k + 1) * (M // 2) - 1 + M                    # index of the newest sample in xs
+        w = xs[tk - M + 1: tk + 1][::-1]                   # w[b] = x[tk - b]
+        X = np.roll(w, (M // 2) if (k & 1) else 0)         # branch b lands at (b + parity * M/2) mod M
+        expect = np.fft.ifft(X)
+        err = np.abs(yd[k] - expect).max() / max(1e-30, np.abs(expect).max())
+        assert err <= 2e-6 * max(2.0, np.log2(M)), (k, err)

@@ -92,8 +92,8 @@ __global__ void k_analysis_generic(const float* __restrict__ h, const float2* __
 
 // Small M (M <= 64, any even M): one frame per block would leave most of a warp idle, so a 256-thread block takes
 // F = 256 / M consecutive frames per pass, thread = (frame slot, branch) for the dot products and (frame slot, bin)
-// for a direct M-point DFT out of shared memory (M complex MACs per bin: cheaper than the passes of a transform
-// at these sizes, and valid for every M).  Shared: F*M samples + M twiddles.
+// for the mixed-radix passes of slot_dft out of shared memory (valid for every M; M = 48: 11 complex MACs per bin
+// where the direct DFT this kernel used first needs 48).  Shared: 2*F*M samples + M twiddles.
 __global__ void __launch_bounds__(256) k_analysis_generic_small(const float* __restrict__ h, const float2* __restrict__ tw,
                                                                 const float2* __restrict__ hist, long long Hlen,
                                                                 const float2* __restrict__ x, float2* __restrict__ y,
@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(256) k_analysis_generic_small(const float* __r
     extern __shared__ float2 sm[];
     const uint32_t F = 256 / M, M2 = M >> 1;
     float2* X = sm;
-    float2* T = sm + F * M;
+    float2* Y = sm + F * M;
+    float2* T = sm + 2 * F * M;
     const uint32_t fs = threadIdx.x / M, b = threadIdx.x - fs * M;
     for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) T[i] = __ldg(&tw[i]);
     const long long n_groups = (f_end - f_begin + F - 1) / F;
@@ -128,15 +129,9 @@ __global__ void __launch_bounds__(256) k_analysis_generic_small(const float* __r
             X[fs * M + dst] = acc;
         }
         __syncthreads();
+        const float2* r = slot_dft(X + (fs < F ? fs : 0) * M, Y + (fs < F ? fs : 0) * M, M, T, b, valid);
         if (valid) {
-            const float2* Xf = X + fs * M;
-            float2 acc = make_float2(0.f, 0.f);
-            uint32_t idx = 0;                                // (n * b) mod M, exactly
-            for (uint32_t n = 0; n < M; n++) {
-                acc = cadd(acc, cmul(Xf[n], T[idx]));
-                idx += b;
-                if (idx >= M) idx -= M;
-            }
+            const float2 acc = r[b];
             y[f * (long long)M + b] = make_float2(acc.x / Mf, acc.y / Mf);
         }
     }
@@ -150,7 +145,8 @@ __global__ void __launch_bounds__(256) k_synth_ifft_small(const float2* __restri
     extern __shared__ float2 sm[];
     const uint32_t F = 256 / M;
     float2* X = sm;
-    float2* T = sm + F * M;
+    float2* Y = sm + F * M;
+    float2* T = sm + 2 * F * M;
     const uint32_t fs = threadIdx.x / M, c = threadIdx.x - fs * M;
     for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) T[i] = __ldg(&tw[i]);
     const long long n_groups = (v_end - v_begin + F - 1) / F;
@@ -165,15 +161,9 @@ __global__ void __launch_bounds__(256) k_synth_ifft_small(const float2* __restri
             X[fs * M + c] = __ldg(&src[c]);
         }
         __syncthreads();
+        const float2* r = slot_dft(X + (fs < F ? fs : 0) * M, Y + (fs < F ? fs : 0) * M, M, T, c, valid);
         if (valid) {
-            const float2* Xf = X + fs * M;
-            float2 acc = make_float2(0.f, 0.f);
-            uint32_t idx = 0;
-            for (uint32_t n = 0; n < M; n++) {
-                acc = cadd(acc, cmul(Xf[n], T[idx]));
-                idx += c;
-                if (idx >= M) idx -= M;
-            }
+            float2 acc = r[c];
             acc.x *= s0; acc.y *= s0;                        // two f32 multiplies, as upstream
             acc.x *= s1; acc.y *= s1;
             U[(v - v_begin) * (long long)M + c] = acc;
@@ -280,7 +270,7 @@ int32_t launch_generic_analysis(yg_firpfbch2_crcf q, const float2* hist, const f
     if (f_end <= f_begin) return YG_OK;
     if (q->M <= 64) {                        // several frames per block
         const uint32_t F = 256 / q->M;
-        const size_t smem_s = ((size_t)F * q->M + q->M) * sizeof(float2);
+        const size_t smem_s = (2 * (size_t)F * q->M + q->M) * sizeof(float2);
         const long long groups = ((long long)(f_end - f_begin) + F - 1) / F;
         const int grid_s = (int)std::min<long long>(groups, q->n_sm * 8);
         k_analysis_generic_small<<<grid_s, 256, smem_s, st>>>(q->d_h.p, q->d_tw.p, hist, (long long)q->hist_len, x, y, q->M,
@@ -360,7 +350,7 @@ int32_t launch_generic_synthesis(yg_firpfbch2_crcf q, const float2* hist, const 
         const long long nf = std::min<long long>(chunk, (long long)f_end - f0);
         if (M <= 64) {                   // several frames per block
             const uint32_t F = 256 / M;
-            const size_t smem_s = ((size_t)F * M + M) * sizeof(float2);
+            const size_t smem_s = (2 * (size_t)F * M + M) * sizeof(float2);
             const int grid_s = (int)std::min<long long>((nh + nf + F - 1) / F, q->n_sm * 8);
             k_synth_ifft_small<<<grid_s, 256, smem_s, st>>>(q->d_tw.p, hist, (long long)(q->hist_len / M), x, U, M, f0 - nh, f0 + nf);
         } else {

@@ -3,7 +3,7 @@
 //
 // One SM cannot hold M >= 512 register-resident branch windows plus the transform.  Three implementations live here:
 //
-//  * SINGLE-SM (s1k::k_m1024_fused / s1ks::k_m1024_synth_fused, M = 1024 with m <= 4 = BASELINE config #4): one CTA per SM
+//  * SINGLE-SM (s1k / s1ks: M = 1024 with m <= 4 = BASELINE config #4; s5k / s5ks: M = 512 with m <= 7): one CTA per SM
 //    and no exchange at all -- taps in registers, windows in a shared-memory input ring (analysis) / running output sums in
 //    registers over a shared-memory frame ring transformed in place (synthesis).  Described where they are defined.
 
@@ -2095,7 +2095,6 @@ int32_t firpfbch2_large_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float2)));
     YG_CUDA(yg::memcpy_sync(plan.d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
     YG_TRY(plan_common(plan, M));
-    if (plan.supported) YG_TRY(plan_fused(plan, false));
     if (plan.supported && ((M == 1024 && 2 * m + 1 <= (uint32_t)s1k::kMaxTaps) || (M == 512 && m <= (uint32_t)s5k::kMaxM))) {
         const char* e = getenv("YG_LARGE_SINGLE_SM");     // debugging knob: 0 keeps the group kernel
         plan.single_sm = !(e && e[0] == '0');
@@ -2103,6 +2102,7 @@ int32_t firpfbch2_large_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t m, co
         const char* d = getenv("YG_PDL");
         plan.pdl = !(d && d[0] == '0');
     }
+    if (plan.supported && !plan.single_sm) YG_TRY(plan_fused(plan, false));      // the group kernel's L2 ring: only where it runs
     return YG_OK;
 }
 
@@ -2216,7 +2216,6 @@ int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t
     YG_CUDA(cudaMalloc(&plan.d_taps, taps.size() * sizeof(float)));
     YG_CUDA(yg::memcpy_sync(plan.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
     YG_TRY(plan_common(plan, M));
-    if (plan.supported) YG_TRY(plan_fused(plan, true));
     if (plan.supported && ((M == 1024 && m <= (uint32_t)s1ks::kMaxM) || (M == 512 && m <= (uint32_t)s5ks::kMaxM))) {
         const char* e = getenv("YG_LARGE_SINGLE_SM");     // debugging knob: 0 keeps the group kernel
         plan.single_sm = !(e && e[0] == '0');
@@ -2224,6 +2223,7 @@ int32_t firpfbch2_large_synth_plan(Firpfbch2FastPlan& plan, uint32_t M, uint32_t
         const char* d = getenv("YG_PDL");
         plan.pdl = !(d && d[0] == '0');
     }
+    if (plan.supported && !plan.single_sm) YG_TRY(plan_fused(plan, true));
     return YG_OK;
 }
 
