@@ -301,8 +301,8 @@ __device__ inline float2* block_dft(float2* X, float2* Y, uint32_t M, const floa
 // frame pass valid = false); returns the row that holds the result.  M = 48: 11 complex MACs per bin instead of 48.
 __device__ inline float2* slot_dft(float2* x, float2* y, uint32_t M, const float2* T, uint32_t o, bool valid)
 {
-    // a pass costs its radix in MACs plus ~8 MACs' worth of index arithmetic and a barrier: below that the direct DFT
-    // (= one pass of radix M) is cheaper (measured: M = 10 22 vs 18 Gsps, M = 24 17 vs 15, M = 48 12 vs 14.5)
+    // a pass costs its radix in MACs plus ~4 MACs' worth of index arithmetic and a barrier: below that (M <= 12 or so)
+    // the direct DFT (= one pass of radix M) is cheaper
     uint32_t cost = 0;
     for (uint32_t rem = M; rem > 1;) {
         uint32_t r = rem;
@@ -311,7 +311,7 @@ __device__ inline float2* slot_dft(float2* x, float2* y, uint32_t M, const float
         else
             for (uint32_t p = 3; p * p <= rem; p += 2)
                 if (rem % p == 0) { r = p; break; }
-        cost += r + 8;
+        cost += r + 4;
         rem /= r;
     }
     const bool direct = M <= cost;
