@@ -47,6 +47,19 @@ struct yg_firpfbch2_crcf_s {
     Firpfbch2FastPlan tiny;       // fused tiny-M analysis kernel (M = 8, 16, 32)
     Firpfbch2FastPlan slarge;     // two-stage large-M synthesis path (M = 1024)
     DevBuf<yg_cf32> d_Uc;         // its L2-sized U scratch
+    // tiled generic kernels (any even M whose tile fits shared memory): F frames per CTA pass, mixed-radix passes
+    struct Tiled {
+        bool supported = false;
+        int F = 0;                 // frames per tile
+        int n_pass = 0;
+        unsigned char radix[24] = {};
+        size_t smem = 0;
+        int ctas_per_sm = 1;
+        int threads = 256;         // 2048 threads per SM whatever the tile's footprint allows resident
+        int wF = 0;                // synthesiser stage 2 (overlap-add): frames per tile, 0 = one thread per output from global
+        size_t wsmem = 0;
+        int wctas = 1, wthreads = 256;
+    } tiled;
 };
 
 namespace {
@@ -238,6 +251,246 @@ __global__ void k_synth_wola(const float* __restrict__ h, const float2* __restri
     }
 }
 
+// ------------------------------------------------------------------ tiled generic kernels (G2)
+// The kernels above spend ~500 instructions per output bin on run-time index arithmetic.  For every even M whose tile
+// fits shared memory the same work is done by a CTA on F consecutive frames at once: the tile's input span, the taps
+// ([tap][branch], the prototype's own order) and the twiddles are staged in shared memory, the dot products read
+// only shared memory, and the transform runs as mixed-radix Stockham passes over all F frames with the radix-2/3/4/5
+// butterflies in registers (other prime factors: one output per thread, r MACs each).  A pass of radix r maps
+// butterfly j = jh Ns + k of frame fl from in[fl M + j + i M/r] (times W_M^{i k M / (Ns r)}, no reduction needed:
+// i k M / (Ns r) < M) to out[fl M + (jh r + q) Ns + k].
+struct TiledPass { unsigned char radix[24]; int n_pass; };
+
+__device__ __forceinline__ float2 cmulj(float2 a) { return make_float2(-a.y, a.x); }        // j a
+
+template <int R>
+__device__ __forceinline__ void dft_small(float2 (&v)[R])                                     // backward, in place
+{
+    if (R == 2) {
+        const float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b); v[1] = csub(a, b);
+    } else if (R == 3) {
+        constexpr float s3 = 0.86602540378443865f;
+        const float2 t1 = cadd(v[1], v[2]);
+        const float2 t2 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+        const float2 d = csub(v[1], v[2]);
+        const float2 t3 = make_float2(-s3 * d.y, s3 * d.x);                                   // j s3 (v1 - v2)
+        v[0] = cadd(v[0], t1); v[1] = cadd(t2, t3); v[2] = csub(t2, t3);
+    } else if (R == 4) {
+        const float2 apc = cadd(v[0], v[2]), amc = csub(v[0], v[2]);
+        const float2 bpd = cadd(v[1], v[3]), jbmd = cmulj(csub(v[1], v[3]));
+        v[0] = cadd(apc, bpd); v[1] = cadd(amc, jbmd); v[2] = csub(apc, bpd); v[3] = csub(amc, jbmd);
+    } else if (R == 5) {
+        constexpr float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
+        constexpr float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+        const float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]), t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+        const float2 a1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
+        const float2 a2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
+        const float2 b1 = cmulj(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
+        const float2 b2 = cmulj(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+        v[0] = cadd(v[0], cadd(t1, t2));
+        v[1] = cadd(a1, b1); v[4] = csub(a1, b1); v[2] = cadd(a2, b2); v[3] = csub(a2, b2);
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void tiled_pass(const float2* in, float2* out, const float2* T, uint32_t M, uint32_t Ns, uint32_t nf)
+{
+    const uint32_t L = M / R, step = M / (Ns * R);
+    const uint32_t items = nf * L;
+    for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
+        const uint32_t fl = it / L, j = it - fl * L;
+        const uint32_t jh = j / Ns, k = j - jh * Ns;
+        const float2* xi = in + fl * M + j;
+        float2 v[R];
+        v[0] = xi[0];
+#pragma unroll
+        for (int i = 1; i < R; i++) v[i] = cmul(xi[i * L], T[i * k * step]);
+        dft_small<R>(v);
+        float2* yo = out + fl * M + jh * R * Ns + k;
+#pragma unroll
+        for (int q = 0; q < R; q++) yo[q * Ns] = v[q];
+    }
+}
+
+// any other (prime) radix: one output per thread, r MACs each (block_dft's form)
+__device__ __forceinline__ void tiled_pass_any(const float2* in, float2* out, const float2* T, uint32_t M, uint32_t Ns, uint32_t r,
+                                               uint32_t nf)
+{
+    const uint32_t L = M / r, step = M / (Ns * r);
+    const uint32_t items = nf * M;
+    for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
+        const uint32_t fl = it / M, o = it - fl * M;
+        const uint32_t t = o / Ns, k = o - t * Ns, jh = t / r, q = t - jh * r;
+        const float2* xi = in + fl * M + jh * Ns + k;
+        const uint32_t e = (k + q * Ns) * step;
+        float2 acc = xi[0];
+        uint32_t idx = 0;
+        for (uint32_t i = 1; i < r; i++) {
+            idx += e;
+            if (idx >= M) idx -= M;
+            acc = cadd(acc, cmul(xi[i * L], T[idx]));
+        }
+        out[it] = acc;
+    }
+}
+
+// all passes over nf frames held in A (result: returned pointer, A or B); barriers inside, every thread must call it
+__device__ __forceinline__ float2* tiled_dft(float2* A, float2* B, const float2* T, uint32_t M, const TiledPass& tp, uint32_t nf)
+{
+    uint32_t Ns = 1;
+    for (int p = 0; p < tp.n_pass; p++) {
+        const uint32_t r = tp.radix[p];
+        switch (r) {
+            case 2: tiled_pass<2>(A, B, T, M, Ns, nf); break;
+            case 3: tiled_pass<3>(A, B, T, M, Ns, nf); break;
+            case 4: tiled_pass<4>(A, B, T, M, Ns, nf); break;
+            case 5: tiled_pass<5>(A, B, T, M, Ns, nf); break;
+            default: tiled_pass_any(A, B, T, M, Ns, r, nf); break;
+        }
+        __syncthreads();
+        float2* t = A; A = B; B = t;
+        Ns *= r;
+    }
+    return A;
+}
+
+// Shared: T[M] | taps[P M] floats | Xin[(F-1) M/2 + P M] | A[F M] | B[F M]
+__global__ void __launch_bounds__(1024) k_analysis_tiled(const float* __restrict__ h, const float2* __restrict__ tw,
+                                                        const float2* __restrict__ hist, long long Hlen,
+                                                        const float2* __restrict__ x, float2* __restrict__ y,
+                                                        uint32_t M, uint32_t P /*2m*/, long long f_begin, long long f_end, int flag0,
+                                                        uint32_t F, TiledPass tp)
+{
+    extern __shared__ float2 sm[];
+    const uint32_t M2 = M >> 1;
+    float2* T = sm;
+    float* taps = reinterpret_cast<float*>(sm + M);
+    float2* Xin = sm + M + (P * M + 1) / 2;
+    const uint32_t span = (F - 1) * M2 + P * M;
+    float2* A = Xin + span;
+    float2* B = A + F * M;
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) T[i] = __ldg(&tw[i]);
+    for (uint32_t i = threadIdx.x; i < P * M; i += blockDim.x) taps[i] = __ldg(&h[i]);
+    const long long n_tiles = (f_end - f_begin + F - 1) / F;
+    const float Mf = (float)M;
+    for (long long g = blockIdx.x; g < n_tiles; g += gridDim.x) {
+        const long long f0 = f_begin + g * F;
+        const uint32_t nf = (uint32_t)min((long long)F, f_end - f0);
+        // 1. the tile's input span: samples t_start .. t_start + (nf - 1) M/2 + P M - 1 of the stream (history ++ x)
+        const long long t_start = (f0 + 1) * (long long)M2 - (long long)P * M;
+        const uint32_t n_in = (nf - 1) * M2 + P * M;
+        __syncthreads();                                     // the previous tile has been stored (and T, taps are loaded)
+        for (uint32_t i = threadIdx.x; i < n_in; i += blockDim.x) {
+            const long long t = t_start + i;
+            float2 v = make_float2(0.f, 0.f);
+            if (t >= 0) v = __ldg(&x[t]);
+            else if (Hlen + t >= 0) v = __ldg(&hist[Hlen + t]);
+            Xin[i] = v;
+        }
+        __syncthreads();
+        // 2. branch dot products, oldest sample first (src/dotprod/mod.rs:36-39); sample t_k - b - n M sits at
+        //    Xin[fl M/2 + P M - 1 - b - n M]
+        for (uint32_t it = threadIdx.x; it < nf * M; it += blockDim.x) {
+            const uint32_t fl = it / M, b = it - fl * M;
+            const float2* xs = Xin + fl * M2 + P * M - 1 - b;
+            const float* hs = taps + b;
+            float2 acc = make_float2(0.f, 0.f);
+            for (int n = (int)P - 1; n >= 0; n--) {
+                const float c = hs[n * M];
+                const float2 v = xs[-(int)(n * M)];
+                acc.x = fmaf(c, v.x, acc.x);
+                acc.y = fmaf(c, v.y, acc.y);
+            }
+            const int par = (flag0 + (int)((f0 + fl) & 1)) & 1;
+            uint32_t dst = b + (par ? M2 : 0);
+            if (dst >= M) dst -= M;
+            A[fl * M + dst] = acc;
+        }
+        __syncthreads();
+        // 3. transform, 4. store
+        const float2* r = tiled_dft(A, B, T, M, tp, nf);
+        float2* yo = y + f0 * (long long)M;
+        for (uint32_t it = threadIdx.x; it < nf * M; it += blockDim.x) {
+            const float2 v = r[it];
+            yo[it] = make_float2(v.x / Mf, v.y / Mf);
+        }
+    }
+}
+
+// The synthesiser's stage 1 in the same shape.  Shared: T[M] | A[F M] | B[F M]
+__global__ void __launch_bounds__(1024) k_synth_ifft_tiled(const float2* __restrict__ tw, const float2* __restrict__ hist,
+                                                          long long hist_frames, const float2* __restrict__ x,
+                                                          float2* __restrict__ U, uint32_t M, long long v_begin, long long v_end,
+                                                          uint32_t F, TiledPass tp)
+{
+    extern __shared__ float2 sm[];
+    float2* T = sm;
+    float2* A = sm + M;
+    float2* B = A + F * M;
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) T[i] = __ldg(&tw[i]);
+    const long long n_tiles = (v_end - v_begin + F - 1) / F;
+    const float s0 = 1.0f / (float)M;
+    const float s1 = (float)(M >> 1);
+    for (long long g = blockIdx.x; g < n_tiles; g += gridDim.x) {
+        const long long v0 = v_begin + g * F;
+        const uint32_t nf = (uint32_t)min((long long)F, v_end - v0);
+        __syncthreads();
+        for (uint32_t it = threadIdx.x; it < nf * M; it += blockDim.x) {
+            const uint32_t fl = it / M, c = it - fl * M;
+            const long long v = v0 + fl;
+            const float2* src = (v >= 0) ? x + v * (long long)M : hist + (hist_frames + v) * (long long)M;
+            A[it] = __ldg(&src[c]);
+        }
+        __syncthreads();
+        const float2* r = tiled_dft(A, B, T, M, tp, nf);
+        float2* uo = U + (v0 - v_begin) * (long long)M;
+        for (uint32_t it = threadIdx.x; it < nf * M; it += blockDim.x) {
+            float2 vv = r[it];
+            vv.x *= s0; vv.y *= s0;                          // two f32 multiplies, as upstream
+            vv.x *= s1; vv.y *= s1;
+            uo[it] = vv;
+        }
+    }
+}
+
+// The synthesiser's stage 2 in the same shape: a CTA stages the F + 4m - 1 frames of U its F output frames reach and the
+// taps in shared memory.  Shared: taps[4m M/2] floats | Us[(F + 4m - 1) M]
+__global__ void __launch_bounds__(1024) k_synth_wola_tiled(const float* __restrict__ h, const float2* __restrict__ U,
+                                                           float2* __restrict__ y, uint32_t M, uint32_t m, long long n_frames,
+                                                           int par0, uint32_t F)
+{
+    extern __shared__ float2 sm[];
+    const uint32_t M2 = M >> 1, nh = 4 * m - 1, L = 4 * m * M2;
+    float* taps = reinterpret_cast<float*>(sm);
+    float2* Us = sm + (L + 1) / 2;
+    for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) taps[i] = __ldg(&h[i]);
+    const long long n_tiles = (n_frames + F - 1) / F;
+    for (long long g = blockIdx.x; g < n_tiles; g += gridDim.x) {
+        const long long f0 = g * F;
+        const uint32_t nf = (uint32_t)min((long long)F, n_frames - f0);
+        __syncthreads();                                     // the previous tile has been read (and the taps are loaded)
+        const float2* src = U + (f0 - (long long)nh) * (long long)M;             // the launch's U has its 4m-1 predecessors in front
+        for (uint32_t i = threadIdx.x; i < (nf + nh) * M; i += blockDim.x) Us[i] = __ldg(&src[i]);
+        __syncthreads();
+        for (uint32_t it = threadIdx.x; it < nf * M2; it += blockDim.x) {
+            const uint32_t fl = it / M2, i = it - fl * M2;
+            const int par = (par0 + (int)((f0 + fl) & 1)) & 1;
+            const float2* us = Us + (fl + nh) * M + i + (par ? M2 : 0);          // frame f of column col
+            const float* hs = taps + i;
+            // two banks (even / odd lag), each summed oldest first, then added (upstream y0 + y1)
+            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+            for (int n = (int)(2 * m) - 1; n >= 0; n--) {
+                const float c0 = hs[(2 * n) * M2], c1 = hs[(2 * n + 1) * M2];
+                const float2 u0 = us[-(int)((2 * n) * M)], u1 = us[-(int)((2 * n + 1) * M)];
+                a0.x = fmaf(c0, u0.x, a0.x); a0.y = fmaf(c0, u0.y, a0.y);
+                a1.x = fmaf(c1, u1.x, a1.x); a1.y = fmaf(c1, u1.y, a1.y);
+            }
+            y[f0 * (long long)M2 + it] = make_float2(a0.x + a1.x, a0.y + a1.y);
+        }
+    }
+}
+
 int32_t check(yg_firpfbch2_crcf q)
 {
     if (!q) return fail(YG_EVALUE, "null firpfbch2 handle");
@@ -268,6 +521,17 @@ int32_t launch_generic_analysis(yg_firpfbch2_crcf q, const float2* hist, const f
                                 size_t f_begin, size_t f_end, cudaStream_t st)
 {
     if (f_end <= f_begin) return YG_OK;
+    if (q->tiled.supported) {                // F frames per CTA pass out of shared memory
+        TiledPass tp;
+        memcpy(tp.radix, q->tiled.radix, sizeof(tp.radix));
+        tp.n_pass = q->tiled.n_pass;
+        const long long tiles = ((long long)(f_end - f_begin) + q->tiled.F - 1) / q->tiled.F;
+        const int grid_t = (int)std::min<long long>(tiles, (long long)q->n_sm * q->tiled.ctas_per_sm);
+        k_analysis_tiled<<<grid_t, q->tiled.threads, q->tiled.smem, st>>>(q->d_h.p, q->d_tw.p, hist, (long long)q->hist_len, x, y, q->M, 2 * q->m,
+                                                             (long long)f_begin, (long long)f_end, q->flag, (uint32_t)q->tiled.F, tp);
+        YG_LAUNCH_CHECK();
+        return YG_OK;
+    }
     if (q->M <= 64) {                        // several frames per block
         const uint32_t F = 256 / q->M;
         const size_t smem_s = (2 * (size_t)F * q->M + q->M) * sizeof(float2);
@@ -348,7 +612,15 @@ int32_t launch_generic_synthesis(yg_firpfbch2_crcf q, const float2* hist, const 
     const int block = (int)std::min<uint32_t>(256, (M + 31) / 32 * 32);
     for (long long f0 = (long long)f_begin; f0 < (long long)f_end; f0 += chunk) {
         const long long nf = std::min<long long>(chunk, (long long)f_end - f0);
-        if (M <= 64) {                   // several frames per block
+        if (q->tiled.supported) {
+            TiledPass tp;
+            memcpy(tp.radix, q->tiled.radix, sizeof(tp.radix));
+            tp.n_pass = q->tiled.n_pass;
+            const long long tiles = (nh + nf + q->tiled.F - 1) / q->tiled.F;
+            const int grid_t = (int)std::min<long long>(tiles, (long long)q->n_sm * q->tiled.ctas_per_sm);
+            k_synth_ifft_tiled<<<grid_t, q->tiled.threads, q->tiled.smem, st>>>(q->d_tw.p, hist, (long long)(q->hist_len / M), x, U, M, f0 - nh, f0 + nf,
+                                                                   (uint32_t)q->tiled.F, tp);
+        } else if (M <= 64) {            // several frames per block
             const uint32_t F = 256 / M;
             const size_t smem_s = (2 * (size_t)F * M + M) * sizeof(float2);
             const int grid_s = (int)std::min<long long>((nh + nf + F - 1) / F, q->n_sm * 8);
@@ -360,6 +632,12 @@ int32_t launch_generic_synthesis(yg_firpfbch2_crcf q, const float2* hist, const 
         YG_LAUNCH_CHECK();
         const long long total = nf * q->M2;
         const int grid2 = (int)std::min<long long>((total + 255) / 256, q->n_sm * 32);
+        if (q->tiled.wF > 0) {
+            const long long tiles = (nf + q->tiled.wF - 1) / q->tiled.wF;
+            const int grid_w = (int)std::min<long long>(tiles, (long long)q->n_sm * q->tiled.wctas);
+            k_synth_wola_tiled<<<grid_w, q->tiled.wthreads, q->tiled.wsmem, st>>>(q->d_h.p, U + nh * M, y + f0 * q->M2, M, q->m, nf,
+                                                                                  (q->flag + (int)(f0 & 1)) & 1, (uint32_t)q->tiled.wF);
+        } else
         k_synth_wola<<<grid2, 256, 0, st>>>(q->d_h.p, U + nh * M, y + f0 * q->M2, M, q->m, nf, (q->flag + (int)(f0 & 1)) & 1);
         YG_LAUNCH_CHECK();
     }
@@ -435,6 +713,65 @@ int32_t execute_dev_impl(yg_firpfbch2_crcf q, const yg_cf32* d_x, size_t n_frame
     return YG_OK;
 }
 
+// Tile geometry of the tiled generic kernels for this object (on its device): the prime factors of M (4 before 2, then
+// odd primes ascending), the largest tile of F frames that fits ~190 KB of shared memory (F M <= 8192, F <= 64).
+int32_t plan_tiled(yg_firpfbch2_crcf q)
+{
+    auto& t = q->tiled;
+    t.supported = false;
+    const char* e = getenv("YG_GENERIC_TILED");           // debugging knob: 0 keeps the one-frame-per-block kernels
+    if (e && e[0] == '0') return YG_OK;
+    const size_t M = q->M, P = 2 * (size_t)q->m;
+    // stage 2 of the synthesiser: F + 4m - 1 frames of U and the taps in shared memory -- pays up to M ~ 100 (M = 24:
+    // 27.5 -> 31.5 Gsps); beyond that the tile holds few frames and the one-thread-per-output kernel is as good or better
+    if (q->type == YG_SYNTHESIZER && M <= 128) {
+        const size_t nh = 2 * P - 1;
+        auto wbytes = [&](size_t F) { return 8 * ((P * M + 1) / 2 + (F + nh) * M); };
+        size_t F = std::min<size_t>(64, std::max<size_t>(2, 16384 / M));
+        while (F > 1 && wbytes(F) > 190 * 1024) F--;
+        if (wbytes(F) <= 190 * 1024 && F >= 2) {
+            t.wF = (int)F;
+            t.wsmem = wbytes(F);
+            YG_CUDA(cudaFuncSetAttribute(k_synth_wola_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+            t.wctas = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (t.wsmem + 1024)));
+            t.wthreads = std::min(1024, (2048 / t.wctas) & ~31);
+        }
+    }
+    uint32_t rem = q->M;
+    t.n_pass = 0;
+    while (rem > 1) {
+        uint32_t r = rem;
+        if ((rem & 3) == 0) r = 4;
+        else if ((rem & 1) == 0) r = 2;
+        else
+            for (uint32_t p = 3; p * p <= rem; p += 2)
+                if (rem % p == 0) { r = p; break; }
+        if (r > 255 || t.n_pass >= 24) return YG_OK;      // a large prime factor: the one-frame-per-block kernel takes it
+        t.radix[t.n_pass++] = (unsigned char)r;
+        rem /= r;
+    }
+    auto bytes = [&](size_t F) {
+        return q->type == YG_ANALYZER ? 8 * (M + (P * M + 1) / 2 + (F - 1) * (M / 2) + P * M + 2 * F * M) : 8 * (M + 2 * F * M);
+    };
+    // (smaller tiles for more resident CTAs were measured: the analyser loses -- every tile reloads P M samples of
+    // history and the taps -- and the synthesiser does not gain)
+    const size_t budget = 190 * 1024;
+    size_t F = std::min<size_t>(64, std::max<size_t>(1, 8192 / M));
+    while (F > 1 && bytes(F) > budget) F--;
+    if (bytes(F) > budget) return YG_OK;
+    // the synthesiser's stage 1 at a large power-of-two M is served better by the one-frame-per-block radix-4 kernel
+    // (16 independent blocks per SM; measured M = 256: 19.4 vs 16.8 Gsps, M = 1024: 23.6 vs 16.4)
+    if (q->type == YG_SYNTHESIZER && M >= 128 && (M & (M - 1)) == 0) return YG_OK;
+    t.F = (int)F;
+    t.smem = bytes(F);
+    if (q->type == YG_ANALYZER) YG_CUDA(cudaFuncSetAttribute(k_analysis_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    else YG_CUDA(cudaFuncSetAttribute(k_synth_ifft_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    t.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (t.smem + 1024)));
+    t.threads = std::min(1024, (2048 / t.ctas_per_sm) & ~31);
+    t.supported = true;
+    return YG_OK;
+}
+
 int32_t build(int32_t type, uint32_t M, uint32_t m, const float* h, size_t h_len, yg_firpfbch2_crcf* out)
 {
     if (!out) return fail(YG_EVALUE, "null output pointer");
@@ -473,6 +810,7 @@ int32_t build(int32_t type, uint32_t M, uint32_t m, const float* h, size_t h_len
         TRYQ(q->d_hist[b].reserve(q->hist_len));
         CUDAQ(yg::memset_sync(q->d_hist[b].p, 0, q->hist_len * sizeof(yg_cf32)));
     }
+    TRYQ(plan_tiled(q));
     if (type == YG_ANALYZER) TRYQ(firpfbch2_fast_plan(q->fast, M, m, q->h.data()));
     if (type == YG_ANALYZER) TRYQ(firpfbch2_large_plan(q->large, M, m, q->h.data()));
     if (type == YG_ANALYZER) TRYQ(firpfbch2_small_plan(q->small, M, m, q->h.data()));
