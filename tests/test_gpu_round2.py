@@ -839,3 +839,36 @@ def test_generic_kernels_any_even_M(M, m):
         expect = np.fft.ifft(X)
         err = np.abs(yd[k] - expect).max() / max(1e-30, np.abs(expect).max())
         assert err <= 2e-6 * max(2.0, np.log2(M)), (k, err)
+
+
+@pytest.mark.parametrize("M,p,S_", [(1, 3, 2), (2, 4, 3), (6, 5, 2), (10, 14, 3), (12, 3, 1), (48, 8, 3), (100, 6, 2), (128, 14, 3),
+                                    (202, 4, 1), (240, 10, 2), (256, 14, 2), (1000, 8, 1), (1024, 6, 2), (64, 20, 5)])
+def test_firpfbch_generic_kernels_any_M(M, p, S_):
+    """firpfbch geometries without a fused kernel (M other than 8 / 16 / 32 / 64, or p > 16): analysis and synthesis on the
+    tiled generic kernels against the CPU path, several streams, three uneven calls; then the analyser's transform alone
+    (prototype = one tap per branch) against numpy's f64 FFT."""
+    rng = np.random.default_rng(7000 + M + p)
+    h = rng.standard_normal(M * p).astype(np.float32)
+    Q = max(3 * p + 5, min(400, (1 << 15) // M))
+    x = _rand_c(rng, S_ * Q * M).reshape(S_, Q * M)
+    cuts = [0, 1, Q // 2, Q]
+    for type_, otype in ((A, po.ANALYZER), (S, po.SYNTHESIZER)):
+        q = yb.FirPfbCh.new(type_, M, p, h, n_streams=S_)
+        y = np.concatenate([q.execute_block(np.ascontiguousarray(x[:, a * M: b * M])).reshape(S_, -1) for a, b in zip(cuts, cuts[1:])],
+                           axis=1)
+        assert q.last_path() == 1
+        ref = np.stack([po.FirPfbCh.new(otype, M, p, h).execute_block(x[s]) for s in range(S_)])
+        scale = max(1.0, np.abs(ref).max())
+        assert_parity(y / scale, ref / scale, "generic firpfbch type=%d M=%d p=%d" % (int(type_), M, p))
+        per_frame = np.abs(y - ref).reshape(S_, Q, M).max(axis=2) / scale
+        assert per_frame.max() <= 1e-4, np.unravel_index(per_frame.argmax(), per_frame.shape)
+    # oracle-free: h[b + n M] = [n == 0] makes frame q the forward DFT of X[M-1-b] = x[q M + M-1 - b], i.e. of the frame
+    # itself (X[c] = x[q M + c])
+    hd = np.zeros(M * p, dtype=np.float32)
+    hd[:M] = 1.0
+    qd = yb.FirPfbCh.new(A, M, p, hd, n_streams=1)
+    xd = _rand_c(rng, 8 * M)
+    yd = qd.execute_block(xd).reshape(8, M)
+    expect = np.fft.fft(xd.astype(np.complex128).reshape(8, M), axis=1)
+    err = np.abs(yd - expect).max() / max(1e-30, np.abs(expect).max())
+    assert err <= 2e-6 * max(2.0, np.log2(M)), err

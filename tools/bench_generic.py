@@ -28,3 +28,17 @@ for M, m in GEOMS:
     ms = timed(lambda: qs.execute_block(Y, K, out=y), steps=5, warmup=2)
     print("synthesis M=%4d m=%2d path %d: %8.3f ms  %6.1f Gsps  %.3f of measured HBM peak" % (M, m, qs.last_path(), ms, N / ms / 1e6, 24.0 * N / ms / 1e6 / PEAK), flush=True)
     del x, Y, y, qa, qs
+
+# firpfbch (critically sampled) at sizes without a fused kernel: 64 streams
+for M, m in ((48, 5), (100, 5), (128, 7), (256, 7), (1000, 4), (1024, 4)):
+    if os.environ.get("YG_GEN_GEOM"):
+        break
+    S, n = 64, (1 << LOG2N) // 64 // M * M
+    x = randc(S * n)
+    y = torch.empty(S * n, dtype=torch.complex64, device="cuda")
+    for name, t in (("analysis ", yb.ANALYZER), ("synthesis", yb.SYNTHESIZER)):
+        q = yb.FirPfbCh.new_kaiser(t, M, m, 60.0, n_streams=S)
+        ms = timed(lambda: q.execute_block(x, n // M, out=y), steps=5, warmup=2)
+        print("firpfbch %s M=%4d m=%2d path %d: %8.3f ms  %6.1f Gsps  %.3f of measured HBM peak" % (name, M, m, q.last_path(), ms, S * n / ms / 1e6, 16.0 * S * n / ms / 1e6 / PEAK), flush=True)
+        del q
+    del x, y

@@ -2,7 +2,7 @@
 # tools/gpu_generic.sh -- parity of the generic kernels at any even M, then their throughput (new library, and the one
 # before the mixed-radix transform on the geometries where a direct DFT finishes in reasonable time)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "generic or any_even or geometry or autotest or random_prototype or roundtrip" > gpurun_out/gen_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/gen_pytest.log
+timeout 900 python -m pytest tests -m gpu -x -q -k "generic or any_even or any_M or geometry or autotest or random_prototype or roundtrip or firpfbch" > gpurun_out/gen_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/gen_pytest.log
 tail -n 6 gpurun_out/gen_pytest.log
 ( echo "== tiled generic kernels"; timeout 600 python tools/bench_generic.py 2>&1 | grep path
   echo "== one-frame-per-block kernels (YG_GENERIC_TILED=0)"; YG_GENERIC_TILED=0 timeout 600 python tools/bench_generic.py 2>&1 | grep path

@@ -7,6 +7,7 @@
 #include "firpfbch_fast.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 using namespace yg;
 
@@ -29,6 +30,13 @@ struct yg_firpfbch_crcf_s {
     FirpfbchFastPlan fast;         // fused kernels (M = 64)
     FirpfbchFastPlan tiny;         // fused tiny-M kernels (M = 8, 16, 32)
     int32_t last_path = 0;
+    // tiled generic kernels (any M whose tile fits shared memory): F frames of one stream per CTA pass
+    struct Tiled {
+        bool supported = false;
+        int F = 0, threads = 256, ctas_per_sm = 1;
+        size_t smem = 0;
+        TiledPass tp = {};
+    } tiled;
 };
 
 namespace {
@@ -124,6 +132,100 @@ __global__ void k_pfbch_synth_fir(const float* __restrict__ h, const float2* __r
     }
 }
 
+// ------------------------------------------------------------------ tiled generic kernels
+// The firpfbch2 scheme (firpfbch2.cu, k_analysis_tiled): a CTA takes F consecutive frames of ONE stream, stages their
+// input span ((F + p - 1) M samples of history ++ x), the taps and the twiddles in shared memory, runs the branch dot
+// products out of shared memory and the mixed-radix passes over all F frames.  The analyser's FORWARD transform is the
+// backward one on conjugated data: DFT_f(x) = conj(DFT_b(conj(x))).
+// Shared: T[M] | taps[p M] floats | Xin[(F + p - 1) M] | A[F M] | B[F M]
+__global__ void __launch_bounds__(1024) k_pfbch_analysis_tiled(const float* __restrict__ h, const float2* __restrict__ tw,
+                                                               const float2* __restrict__ hist, long long Hlen,
+                                                               const float2* __restrict__ x, float2* __restrict__ y,
+                                                               uint32_t M, uint32_t p, long long n_frames, long long n_streams,
+                                                               uint32_t F, TiledPass tp)
+{
+    extern __shared__ float2 sm[];
+    float2* T = sm;
+    float* taps = reinterpret_cast<float*>(sm + M);
+    float2* Xin = sm + M + (p * M + 1) / 2;
+    float2* A = Xin + (F + p - 1) * M;
+    float2* B = A + F * M;
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) T[i] = __ldg(&tw[i]);
+    for (uint32_t i = threadIdx.x; i < p * M; i += blockDim.x) taps[i] = __ldg(&h[i]);
+    const long long tiles_per = (n_frames + F - 1) / F;
+    const long long n_tiles = tiles_per * n_streams;
+    for (long long g = blockIdx.x; g < n_tiles; g += gridDim.x) {
+        const long long s = g / tiles_per, q0 = (g - s * tiles_per) * F;
+        const uint32_t nf = (uint32_t)min((long long)F, n_frames - q0);
+        const float2* xs = x + s * n_frames * (long long)M;
+        const float2* hs = hist + s * Hlen;
+        const long long t_start = (q0 - (long long)p + 1) * (long long)M;
+        __syncthreads();                                     // the previous tile has been stored (and T, taps are loaded)
+        for (uint32_t i = threadIdx.x; i < (nf + p - 1) * M; i += blockDim.x) {
+            const long long t = t_start + i;
+            float2 v = make_float2(0.f, 0.f);
+            if (t >= 0) v = __ldg(&xs[t]);
+            else if (Hlen + t >= 0) v = __ldg(&hs[Hlen + t]);
+            Xin[i] = v;
+        }
+        __syncthreads();
+        // sample t_q - b - n M sits at Xin[(fl + p) M - 1 - b - n M]
+        for (uint32_t it = threadIdx.x; it < nf * M; it += blockDim.x) {
+            const uint32_t fl = it / M, b = it - fl * M;
+            const float2* xw = Xin + (fl + p) * M - 1 - b;
+            const float* hw = taps + b;
+            float2 acc = make_float2(0.f, 0.f);
+            for (int n = (int)p - 1; n >= 0; n--) {          // oldest sample first (src/dotprod/mod.rs:36-39)
+                const float c = hw[n * M];
+                const float2 v = xw[-(int)(n * M)];
+                acc.x = fmaf(c, v.x, acc.x);
+                acc.y = fmaf(c, v.y, acc.y);
+            }
+            A[fl * M + (M - 1 - b)] = make_float2(acc.x, -acc.y);
+        }
+        __syncthreads();
+        const float2* r = tiled_dft(A, B, T, M, tp, nf);
+        float2* ys = y + (s * n_frames + q0) * (long long)M;
+        for (uint32_t it = threadIdx.x; it < nf * M; it += blockDim.x) {
+            const float2 v = r[it];
+            ys[it] = make_float2(v.x, -v.y);
+        }
+    }
+}
+
+// The synthesiser's stage 1 in the same shape (U frame g of a stream = IDFT of virtual input frame g - (p - 1)).
+// Shared: T[M] | A[F M] | B[F M]
+__global__ void __launch_bounds__(1024) k_pfbch_synth_ifft_tiled(const float2* __restrict__ tw, const float2* __restrict__ hist,
+                                                                 long long hist_frames, const float2* __restrict__ x,
+                                                                 float2* __restrict__ U, uint32_t M, uint32_t p, long long n_frames,
+                                                                 long long n_streams, uint32_t F, TiledPass tp)
+{
+    extern __shared__ float2 sm[];
+    float2* T = sm;
+    float2* A = sm + M;
+    float2* B = A + F * M;
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) T[i] = __ldg(&tw[i]);
+    const long long per = n_frames + p - 1;
+    const long long tiles_per = (per + F - 1) / F;
+    const long long n_tiles = tiles_per * n_streams;
+    for (long long g = blockIdx.x; g < n_tiles; g += gridDim.x) {
+        const long long s = g / tiles_per, g0 = (g - s * tiles_per) * F;
+        const uint32_t nf = (uint32_t)min((long long)F, per - g0);
+        __syncthreads();
+        for (uint32_t it = threadIdx.x; it < nf * M; it += blockDim.x) {
+            const uint32_t fl = it / M, c = it - fl * M;
+            const long long v = g0 + fl - (long long)(p - 1);
+            const float2* src = (v >= 0) ? x + (s * n_frames + v) * (long long)M
+                                         : hist + (s * hist_frames + hist_frames + v) * (long long)M;
+            A[it] = __ldg(&src[c]);
+        }
+        __syncthreads();
+        const float2* r = tiled_dft(A, B, T, M, tp, nf);
+        float2* us = U + (s * per + g0) * (long long)M;
+        for (uint32_t it = threadIdx.x; it < nf * M; it += blockDim.x) us[it] = r[it];
+    }
+}
+
 int32_t check(yg_firpfbch_crcf q)
 {
     if (!q) return fail(YG_EVALUE, "null firpfbch handle");
@@ -189,10 +291,19 @@ int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames
         if (s_fast < S) {
             const long long rest = S - s_fast;
             const long long per = (long long)n_frames * M;
-            YG_TRY(set_smem((const void*)k_pfbch_analysis, smem));
-            const int g1 = (int)std::min<long long>((long long)n_frames * rest, q->n_sm * 16);
-            k_pfbch_analysis<<<g1, block, smem, st>>>(q->d_h.p, q->d_tw.p, hist + s_fast * Hlen, Hlen, x + s_fast * per,
-                                                      y + s_fast * per, M, p, (long long)n_frames, rest);
+            if (q->tiled.supported) {
+                const long long tiles = (((long long)n_frames + q->tiled.F - 1) / q->tiled.F) * rest;
+                const int gt = (int)std::min<long long>(tiles, (long long)q->n_sm * q->tiled.ctas_per_sm);
+                k_pfbch_analysis_tiled<<<gt, q->tiled.threads, q->tiled.smem, st>>>(q->d_h.p, q->d_tw.p, hist + s_fast * Hlen, Hlen,
+                                                                                    x + s_fast * per, y + s_fast * per, M, p,
+                                                                                    (long long)n_frames, rest, (uint32_t)q->tiled.F,
+                                                                                    q->tiled.tp);
+            } else {
+                YG_TRY(set_smem((const void*)k_pfbch_analysis, smem));
+                const int g1 = (int)std::min<long long>((long long)n_frames * rest, q->n_sm * 16);
+                k_pfbch_analysis<<<g1, block, smem, st>>>(q->d_h.p, q->d_tw.p, hist + s_fast * Hlen, Hlen, x + s_fast * per,
+                                                          y + s_fast * per, M, p, (long long)n_frames, rest);
+            }
             YG_LAUNCH_CHECK();
         }
     } else {
@@ -216,10 +327,18 @@ int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames
             const long long ftm = (long long)(n_frames + p - 1) * M;
             YG_TRY(q->d_U.reserve((size_t)ftm * rest));
             float2* U = reinterpret_cast<float2*>(q->d_U.p);
-            YG_TRY(set_smem((const void*)k_pfbch_synth_ifft, smem));
-            const int g1 = (int)std::min<long long>((long long)(n_frames + p - 1) * rest, q->n_sm * 16);
-            k_pfbch_synth_ifft<<<g1, block, smem, st>>>(q->d_tw.p, hist + s_fast * Hlen, hist_frames, x + s_fast * per, U, M, p,
-                                                        (long long)n_frames, rest);
+            if (q->tiled.supported) {
+                const long long tiles = (((long long)(n_frames + p - 1) + q->tiled.F - 1) / q->tiled.F) * rest;
+                const int gt = (int)std::min<long long>(tiles, (long long)q->n_sm * q->tiled.ctas_per_sm);
+                k_pfbch_synth_ifft_tiled<<<gt, q->tiled.threads, q->tiled.smem, st>>>(q->d_tw.p, hist + s_fast * Hlen, hist_frames,
+                                                                                      x + s_fast * per, U, M, p, (long long)n_frames,
+                                                                                      rest, (uint32_t)q->tiled.F, q->tiled.tp);
+            } else {
+                YG_TRY(set_smem((const void*)k_pfbch_synth_ifft, smem));
+                const int g1 = (int)std::min<long long>((long long)(n_frames + p - 1) * rest, q->n_sm * 16);
+                k_pfbch_synth_ifft<<<g1, block, smem, st>>>(q->d_tw.p, hist + s_fast * Hlen, hist_frames, x + s_fast * per, U, M, p,
+                                                            (long long)n_frames, rest);
+            }
             YG_LAUNCH_CHECK();
             const long long total = per * rest;
             const int g3 = (int)std::min<long long>((total + 255) / 256, q->n_sm * 32);
@@ -237,6 +356,50 @@ int32_t execute_dev_impl(yg_firpfbch_crcf q, const yg_cf32* d_x, size_t n_frames
         YG_LAUNCH_CHECK();
         q->cur = nxt;
     }
+    return YG_OK;
+}
+
+// Tile geometry of the tiled generic kernels (see plan_tiled in firpfbch2.cu)
+int32_t plan_tiled(yg_firpfbch_crcf q)
+{
+    auto& t = q->tiled;
+    t.supported = false;
+    const char* e = getenv("YG_GENERIC_TILED");           // debugging knob: 0 keeps the one-frame-per-block kernels
+    if (e && e[0] == '0') return YG_OK;
+    const size_t M = q->M, P = q->p;
+    if (M < 2) return YG_OK;
+    uint32_t rem = q->M;
+    t.tp.n_pass = 0;
+    while (rem > 1) {
+        uint32_t r = rem;
+        if ((rem & 3) == 0) r = 4;
+        else if ((rem & 1) == 0) r = 2;
+        else
+            for (uint32_t f = 3; f * f <= rem; f += 2)
+                if (rem % f == 0) { r = f; break; }
+        if (r > 255 || t.tp.n_pass >= 24) return YG_OK;
+        t.tp.radix[t.tp.n_pass++] = (unsigned char)r;
+        rem /= r;
+    }
+    auto bytes = [&](size_t F) {
+        return q->type == YG_ANALYZER ? 8 * (M + (P * M + 1) / 2 + (F + P - 1) * M + 2 * F * M) : 8 * (M + 2 * F * M);
+    };
+    const size_t budget = 190 * 1024;
+    size_t F = std::min<size_t>(64, std::max<size_t>(1, 8192 / M));
+    while (F > 1 && bytes(F) > budget) F--;
+    if (bytes(F) > budget) return YG_OK;
+    // (as for firpfbch2: the synthesiser's stage 1 at a large power-of-two M stays on the radix-4 one-frame-per-block kernel)
+    if (q->type == YG_SYNTHESIZER && M >= 128 && (M & (M - 1)) == 0) return YG_OK;
+    // ... and so is an analyser at a power-of-two M whose tile holds fewer than 8 frames (taps and history are reloaded per
+    // tile; measured firpfbch M = 1024, p = 8, F = 3: 35 vs 47 Gsps)
+    if (q->type == YG_ANALYZER && (M & (M - 1)) == 0 && F < 8) return YG_OK;
+    t.F = (int)F;
+    t.smem = bytes(F);
+    if (q->type == YG_ANALYZER) YG_CUDA(cudaFuncSetAttribute(k_pfbch_analysis_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    else YG_CUDA(cudaFuncSetAttribute(k_pfbch_synth_ifft_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    t.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (t.smem + 1024)));
+    t.threads = std::min(1024, (2048 / t.ctas_per_sm) & ~31);
+    t.supported = true;
     return YG_OK;
 }
 
@@ -268,6 +431,7 @@ int32_t build(int32_t type, uint32_t M, uint32_t p, const float* h, size_t h_len
     CUDAQ(yg::memcpy_sync(q->d_tw.p, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
     // analyser: the last p-1 input frames; synthesiser: at least 16 (one warm-up batch of the fused kernel)
     q->state_len = (type == YG_ANALYZER) ? (size_t)(p - 1) * M : (size_t)std::max<uint32_t>(p - 1, 16) * M;
+    TRYQ(plan_tiled(q));
     TRYQ(firpfbch_fast_plan(q->fast, type, M, p, q->h.data()));
     TRYQ(firpfbch_tiny_plan(q->tiny, type, M, p, q->h.data()));
     for (int b = 0; b < 2; b++) {

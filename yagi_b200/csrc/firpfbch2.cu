@@ -259,102 +259,6 @@ __global__ void k_synth_wola(const float* __restrict__ h, const float2* __restri
 // butterflies in registers (other prime factors: one output per thread, r MACs each).  A pass of radix r maps
 // butterfly j = jh Ns + k of frame fl from in[fl M + j + i M/r] (times W_M^{i k M / (Ns r)}, no reduction needed:
 // i k M / (Ns r) < M) to out[fl M + (jh r + q) Ns + k].
-struct TiledPass { unsigned char radix[24]; int n_pass; };
-
-__device__ __forceinline__ float2 cmulj(float2 a) { return make_float2(-a.y, a.x); }        // j a
-
-template <int R>
-__device__ __forceinline__ void dft_small(float2 (&v)[R])                                     // backward, in place
-{
-    if (R == 2) {
-        const float2 a = v[0], b = v[1];
-        v[0] = cadd(a, b); v[1] = csub(a, b);
-    } else if (R == 3) {
-        constexpr float s3 = 0.86602540378443865f;
-        const float2 t1 = cadd(v[1], v[2]);
-        const float2 t2 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
-        const float2 d = csub(v[1], v[2]);
-        const float2 t3 = make_float2(-s3 * d.y, s3 * d.x);                                   // j s3 (v1 - v2)
-        v[0] = cadd(v[0], t1); v[1] = cadd(t2, t3); v[2] = csub(t2, t3);
-    } else if (R == 4) {
-        const float2 apc = cadd(v[0], v[2]), amc = csub(v[0], v[2]);
-        const float2 bpd = cadd(v[1], v[3]), jbmd = cmulj(csub(v[1], v[3]));
-        v[0] = cadd(apc, bpd); v[1] = cadd(amc, jbmd); v[2] = csub(apc, bpd); v[3] = csub(amc, jbmd);
-    } else if (R == 5) {
-        constexpr float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
-        constexpr float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
-        const float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]), t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
-        const float2 a1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
-        const float2 a2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
-        const float2 b1 = cmulj(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
-        const float2 b2 = cmulj(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
-        v[0] = cadd(v[0], cadd(t1, t2));
-        v[1] = cadd(a1, b1); v[4] = csub(a1, b1); v[2] = cadd(a2, b2); v[3] = csub(a2, b2);
-    }
-}
-
-template <int R>
-__device__ __forceinline__ void tiled_pass(const float2* in, float2* out, const float2* T, uint32_t M, uint32_t Ns, uint32_t nf)
-{
-    const uint32_t L = M / R, step = M / (Ns * R);
-    const uint32_t items = nf * L;
-    for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
-        const uint32_t fl = it / L, j = it - fl * L;
-        const uint32_t jh = j / Ns, k = j - jh * Ns;
-        const float2* xi = in + fl * M + j;
-        float2 v[R];
-        v[0] = xi[0];
-#pragma unroll
-        for (int i = 1; i < R; i++) v[i] = cmul(xi[i * L], T[i * k * step]);
-        dft_small<R>(v);
-        float2* yo = out + fl * M + jh * R * Ns + k;
-#pragma unroll
-        for (int q = 0; q < R; q++) yo[q * Ns] = v[q];
-    }
-}
-
-// any other (prime) radix: one output per thread, r MACs each (block_dft's form)
-__device__ __forceinline__ void tiled_pass_any(const float2* in, float2* out, const float2* T, uint32_t M, uint32_t Ns, uint32_t r,
-                                               uint32_t nf)
-{
-    const uint32_t L = M / r, step = M / (Ns * r);
-    const uint32_t items = nf * M;
-    for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
-        const uint32_t fl = it / M, o = it - fl * M;
-        const uint32_t t = o / Ns, k = o - t * Ns, jh = t / r, q = t - jh * r;
-        const float2* xi = in + fl * M + jh * Ns + k;
-        const uint32_t e = (k + q * Ns) * step;
-        float2 acc = xi[0];
-        uint32_t idx = 0;
-        for (uint32_t i = 1; i < r; i++) {
-            idx += e;
-            if (idx >= M) idx -= M;
-            acc = cadd(acc, cmul(xi[i * L], T[idx]));
-        }
-        out[it] = acc;
-    }
-}
-
-// all passes over nf frames held in A (result: returned pointer, A or B); barriers inside, every thread must call it
-__device__ __forceinline__ float2* tiled_dft(float2* A, float2* B, const float2* T, uint32_t M, const TiledPass& tp, uint32_t nf)
-{
-    uint32_t Ns = 1;
-    for (int p = 0; p < tp.n_pass; p++) {
-        const uint32_t r = tp.radix[p];
-        switch (r) {
-            case 2: tiled_pass<2>(A, B, T, M, Ns, nf); break;
-            case 3: tiled_pass<3>(A, B, T, M, Ns, nf); break;
-            case 4: tiled_pass<4>(A, B, T, M, Ns, nf); break;
-            case 5: tiled_pass<5>(A, B, T, M, Ns, nf); break;
-            default: tiled_pass_any(A, B, T, M, Ns, r, nf); break;
-        }
-        __syncthreads();
-        float2* t = A; A = B; B = t;
-        Ns *= r;
-    }
-    return A;
-}
-
 // Shared: T[M] | taps[P M] floats | Xin[(F-1) M/2 + P M] | A[F M] | B[F M]
 __global__ void __launch_bounds__(1024) k_analysis_tiled(const float* __restrict__ h, const float2* __restrict__ tw,
                                                         const float2* __restrict__ hist, long long Hlen,
@@ -762,6 +666,9 @@ int32_t plan_tiled(yg_firpfbch2_crcf q)
     // the synthesiser's stage 1 at a large power-of-two M is served better by the one-frame-per-block radix-4 kernel
     // (16 independent blocks per SM; measured M = 256: 19.4 vs 16.8 Gsps, M = 1024: 23.6 vs 16.4)
     if (q->type == YG_SYNTHESIZER && M >= 128 && (M & (M - 1)) == 0) return YG_OK;
+    // ... and so is an analyser at a power-of-two M whose tile holds fewer than 8 frames (taps and history are reloaded per
+    // tile; measured firpfbch M = 1024, p = 8, F = 3: 35 vs 47 Gsps)
+    if (q->type == YG_ANALYZER && (M & (M - 1)) == 0 && F < 8) return YG_OK;
     t.F = (int)F;
     t.smem = bytes(F);
     if (q->type == YG_ANALYZER) YG_CUDA(cudaFuncSetAttribute(k_analysis_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
