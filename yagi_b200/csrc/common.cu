@@ -159,6 +159,23 @@ int32_t fir_design_kaiser(uint32_t n, float fc, float as, float mu, float* h)
     return YG_OK;
 }
 
+bool plan_radices(uint32_t M, TiledPass& tp)
+{
+    tp = TiledPass{};
+    for (uint32_t rem = M; rem > 1;) {
+        uint32_t r = rem;
+        if ((rem & 3) == 0) r = 4;
+        else if ((rem & 1) == 0) r = 2;
+        else
+            for (uint32_t f = 3; f * f <= rem; f += 2)
+                if (rem % f == 0) { r = f; break; }
+        if (r > 255 || tp.n_pass >= 24) return false;
+        tp.radix[tp.n_pass++] = (unsigned char)r;
+        rem /= r;
+    }
+    return true;
+}
+
 void make_twiddles(uint32_t M, std::vector<float2>& tw)
 {
     tw.resize(M);

@@ -74,6 +74,11 @@ int32_t fir_design_kaiser(uint32_t n, float fc, float as, float mu, float* h);
 // twiddle table tw[k] = exp(+j 2 pi k / M), computed in f64 and rounded once
 void make_twiddles(uint32_t M, std::vector<float2>& tw);
 
+// Radices of the mixed-radix transform of length M, in pass order: 4 before 2, then the odd prime factors ascending.
+struct TiledPass { unsigned char radix[24]; int n_pass; };
+// false when M has a prime factor > 255 (or more than 24 factors): the tiled kernels do not take such an M
+bool plan_radices(uint32_t M, TiledPass& tp);
+
 // ---------------------------------------------------------------- device buffers
 template <typename T>
 struct DevBuf {
@@ -349,7 +354,6 @@ __device__ inline float2* slot_dft(float2* x, float2* y, uint32_t M, const float
 // ------------------------------------------------------------------ tiled generic kernels: mixed-radix passes over F frames
 // (firpfbch2.cu, firpfbch.cu) -- F frames of M points side by side in shared memory (in, out: ping-pong buffers), the
 // radices chosen on the host, radix-2/3/4/5 butterflies in registers, any other prime factor one output per thread.
-struct TiledPass { unsigned char radix[24]; int n_pass; };
 
 __device__ __forceinline__ float2 cmulj(float2 a) { return make_float2(-a.y, a.x); }        // j a
 

@@ -368,19 +368,7 @@ int32_t plan_tiled(yg_firpfbch_crcf q)
     if (e && e[0] == '0') return YG_OK;
     const size_t M = q->M, P = q->p;
     if (M < 2) return YG_OK;
-    uint32_t rem = q->M;
-    t.tp.n_pass = 0;
-    while (rem > 1) {
-        uint32_t r = rem;
-        if ((rem & 3) == 0) r = 4;
-        else if ((rem & 1) == 0) r = 2;
-        else
-            for (uint32_t f = 3; f * f <= rem; f += 2)
-                if (rem % f == 0) { r = f; break; }
-        if (r > 255 || t.tp.n_pass >= 24) return YG_OK;
-        t.tp.radix[t.tp.n_pass++] = (unsigned char)r;
-        rem /= r;
-    }
+    if (!plan_radices(q->M, t.tp)) return YG_OK;          // a large prime factor: the one-frame-per-block kernel takes it
     auto bytes = [&](size_t F) {
         return q->type == YG_ANALYZER ? 8 * (M + (P * M + 1) / 2 + (F + P - 1) * M + 2 * F * M) : 8 * (M + 2 * F * M);
     };

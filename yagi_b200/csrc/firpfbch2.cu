@@ -51,8 +51,7 @@ struct yg_firpfbch2_crcf_s {
     struct Tiled {
         bool supported = false;
         int F = 0;                 // frames per tile
-        int n_pass = 0;
-        unsigned char radix[24] = {};
+        TiledPass tp = {};
         size_t smem = 0;
         int ctas_per_sm = 1;
         int threads = 256;         // 2048 threads per SM whatever the tile's footprint allows resident
@@ -426,9 +425,7 @@ int32_t launch_generic_analysis(yg_firpfbch2_crcf q, const float2* hist, const f
 {
     if (f_end <= f_begin) return YG_OK;
     if (q->tiled.supported) {                // F frames per CTA pass out of shared memory
-        TiledPass tp;
-        memcpy(tp.radix, q->tiled.radix, sizeof(tp.radix));
-        tp.n_pass = q->tiled.n_pass;
+        const TiledPass tp = q->tiled.tp;
         const long long tiles = ((long long)(f_end - f_begin) + q->tiled.F - 1) / q->tiled.F;
         const int grid_t = (int)std::min<long long>(tiles, (long long)q->n_sm * q->tiled.ctas_per_sm);
         k_analysis_tiled<<<grid_t, q->tiled.threads, q->tiled.smem, st>>>(q->d_h.p, q->d_tw.p, hist, (long long)q->hist_len, x, y, q->M, 2 * q->m,
@@ -517,9 +514,7 @@ int32_t launch_generic_synthesis(yg_firpfbch2_crcf q, const float2* hist, const 
     for (long long f0 = (long long)f_begin; f0 < (long long)f_end; f0 += chunk) {
         const long long nf = std::min<long long>(chunk, (long long)f_end - f0);
         if (q->tiled.supported) {
-            TiledPass tp;
-            memcpy(tp.radix, q->tiled.radix, sizeof(tp.radix));
-            tp.n_pass = q->tiled.n_pass;
+            const TiledPass tp = q->tiled.tp;
             const long long tiles = (nh + nf + q->tiled.F - 1) / q->tiled.F;
             const int grid_t = (int)std::min<long long>(tiles, (long long)q->n_sm * q->tiled.ctas_per_sm);
             k_synth_ifft_tiled<<<grid_t, q->tiled.threads, q->tiled.smem, st>>>(q->d_tw.p, hist, (long long)(q->hist_len / M), x, U, M, f0 - nh, f0 + nf,
@@ -641,19 +636,7 @@ int32_t plan_tiled(yg_firpfbch2_crcf q)
             t.wthreads = std::min(1024, (2048 / t.wctas) & ~31);
         }
     }
-    uint32_t rem = q->M;
-    t.n_pass = 0;
-    while (rem > 1) {
-        uint32_t r = rem;
-        if ((rem & 3) == 0) r = 4;
-        else if ((rem & 1) == 0) r = 2;
-        else
-            for (uint32_t p = 3; p * p <= rem; p += 2)
-                if (rem % p == 0) { r = p; break; }
-        if (r > 255 || t.n_pass >= 24) return YG_OK;      // a large prime factor: the one-frame-per-block kernel takes it
-        t.radix[t.n_pass++] = (unsigned char)r;
-        rem /= r;
-    }
+    if (!plan_radices(q->M, t.tp)) return YG_OK;          // a large prime factor: the one-frame-per-block kernel takes it
     auto bytes = [&](size_t F) {
         return q->type == YG_ANALYZER ? 8 * (M + (P * M + 1) / 2 + (F - 1) * (M / 2) + P * M + 2 * F * M) : 8 * (M + 2 * F * M);
     };
