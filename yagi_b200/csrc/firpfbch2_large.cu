@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
@@ -673,6 +674,15 @@ int32_t launch_fused(const FusedParams& fp, cudaStream_t st)
 //   * DFT role (warps 8-15): one warp per frame, the 32 x 32 warp transform of the two-stage path (radix 32 in
 //     registers, ONE XOR-swizzled exchange, done in place in the frame's V region), 256-byte coalesced stores.
 // HBM and L2 see the algorithmic 24 B per sample; shared memory moves ~56 B per output sample (K1: 40).
+#ifndef YG_S1K_STAMPS
+#define YG_S1K_STAMPS 0        // debugging build (tools/build_variant.sh stamps firpfbch2_large.cu -DYG_S1K_STAMPS=1): the first,
+#endif                         // middle and last CTA of k_m1024_fused print globaltimer stamps of their pipeline
+#if YG_S1K_STAMPS
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define YG_STAMP(arr, i) do { (arr)[i] = gtime(); } while (0)
+#else
+#define YG_STAMP(arr, i) do { } while (0)
+#endif
 namespace s1k {
 constexpr int kM = 1024, kM2 = 512;
 constexpr int kBP = 2;                                   // frame pairs per batch
@@ -695,7 +705,7 @@ constexpr int kMaxTaps = 9;
 __host__ __device__ constexpr int pos_k(int k) { return k == 0 ? 511 : k == 1 ? 255 : k == 2 ? 1023 : 767; }
 
 template <int kTaps>
-__device__ __forceinline__ void fir_role(const LargeParams& p, uint32_t smem, long long b0, long long b1)
+__device__ __forceinline__ void fir_role(const LargeParams& p, uint32_t smem, long long b0, long long b1, volatile unsigned long long* stamps)
 {
     constexpr int kHist = kTaps - 1;                     // pairs of history a window reaches back
     const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
@@ -717,6 +727,7 @@ __device__ __forceinline__ void fir_role(const LargeParams& p, uint32_t smem, lo
     const int n_head = ta0 >= 0 ? 0 : (int)min(-ta0, (long long)(8 * kM));
     if (t == 0) {                                        // first of all: get the copies going
         pdl_wait();                                      // x and the history may come from the previous kernel
+        YG_STAMP(stamps, 0);                             // the clock of the stamps starts when the previous kernel is done
         if (n_head < 8 * kM) {
             const uint32_t bytes = (uint32_t)(8 * kM - n_head) * 8;
             mbar_expect_tx(bar + 8 * kBarHist, bytes);
@@ -750,7 +761,9 @@ __device__ __forceinline__ void fir_role(const LargeParams& p, uint32_t smem, lo
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // these rows are overwritten by bulk copies later
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (t == 0) YG_STAMP(stamps, 1);                    // taps loaded, head rows stored
     if (n_head < 8 * kM) mbar_wait(bar + 8 * kBarHist, 0);
+    if (t == 0) YG_STAMP(stamps, 2);                    // history rows landed
 
     const uint32_t ring_t = smem - t * 8;
     const uint32_t v_t = smem + kOffV + t * 8;
@@ -760,6 +773,7 @@ __device__ __forceinline__ void fir_role(const LargeParams& p, uint32_t smem, lo
         constexpr int ST = (PH + 4) & 7;
         constexpr int BUF = PH & 1;
         mbar_wait(bar + 8 * (kBarInFull + ST), (uint32_t)((lb >> 3) & 1));       // the batch's own two pairs have landed
+        if (t == 0 && lb == 0) YG_STAMP(stamps, 3);     // first batch landed
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             float2 w[kTaps + 1];                         // u[q0 - kHist .. q0 + 1]
@@ -783,6 +797,8 @@ __device__ __forceinline__ void fir_role(const LargeParams& p, uint32_t smem, lo
             sts64(vo + 3 * kRowBytes, o1);
         }
         __syncwarp();
+        if (t == 0 && lb == 0) YG_STAMP(stamps, 4);     // first V batch written
+        if (t == 0 && lb == nb - 1) YG_STAMP(stamps, 6); // last V batch written
         if (lane == 0) {
             mbar_arrive(bar + 8 * (kBarVFull + BUF));
             mbar_arrive(bar + 8 * (kBarInFree + PH));    // rows 2 lb, 2 lb + 1 (stage lb mod 8) are out of every later window
@@ -804,7 +820,8 @@ __device__ __forceinline__ void fir_role(const LargeParams& p, uint32_t smem, lo
     }
 }
 
-__device__ __forceinline__ void dft_role(const LargeParams& p, const unsigned char* smem_raw, uint32_t smem, long long b0, long long b1)
+__device__ __forceinline__ void dft_role(const LargeParams& p, const unsigned char* smem_raw, uint32_t smem, long long b0, long long b1,
+                                         volatile unsigned long long* stamps)
 {
     const int dt = threadIdx.x - 256, lane = dt & 31, dw = dt >> 5;
     const int buf = dw >> 2, fi = dw & 3;                // this warp's V buffer and frame (pair 0 even, odd, pair 1 even, odd)
@@ -851,7 +868,15 @@ __device__ __forceinline__ void dft_role(const LargeParams& p, const unsigned ch
         float2* fr = p.y + (p.f0 + 2 * q + (fi & 1)) * (long long)kM + lane;
 #pragma unroll
         for (int k2 = 0; k2 < 32; k2++) __stcs(fr + 32 * k2, v[dr32(k2)]);
+        if (dt == 0 && lb == 0) YG_STAMP(stamps, 5);    // first frame stored
     }
+#if YG_S1K_STAMPS
+    if (dt == 128 * ((nb - 1) & 1) && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1)) {
+        const unsigned long long t7 = gtime(), t0 = stamps[0];
+        printf("cta %3d nb %3lld: taps %6llu hist %6llu batch0 %6llu V0 %6llu out0 %6llu lastV %6llu end %6llu ns\n", (int)blockIdx.x, nb,
+               stamps[1] - t0, stamps[2] - t0, stamps[3] - t0, stamps[4] - t0, stamps[5] - t0, stamps[6] - t0, t7 - t0);
+    }
+#endif
 }
 
 template <int kTaps>
@@ -859,6 +884,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_m1024_fused(const LargeParams p
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t smem = smem_u32(smem_raw);
+#if YG_S1K_STAMPS
+    __shared__ unsigned long long stamps_s[8];
+    volatile unsigned long long* stamps = stamps_s;
+#else
+    volatile unsigned long long* stamps = nullptr;
+#endif
     const long long n_batches = (p.pair_end - p.pair_begin) / kBP;
     const long long b0 = (n_batches * blockIdx.x) / gridDim.x, b1 = (n_batches * (blockIdx.x + 1)) / gridDim.x;
     if (threadIdx.x == 0) {
@@ -879,8 +910,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_m1024_fused(const LargeParams p
     __syncthreads();
     pdl_launch_dependents();
     if (b0 >= b1) return;                                // never taken: the grid has at most one CTA per batch
-    if (threadIdx.x < 256) fir_role<kTaps>(p, smem, b0, b1);
-    else dft_role(p, smem_raw, smem, b0, b1);
+    if (threadIdx.x < 256) fir_role<kTaps>(p, smem, b0, b1, stamps);
+    else dft_role(p, smem_raw, smem, b0, b1, stamps);
 }
 
 template <int kTaps>
