@@ -165,3 +165,56 @@ def test_rust_sys_crate_tracks_the_c_abi():
         text = open(os.path.join(ROOT, "rust", facade)).read()
         used = set(re.findall(r"sys::(yg_[A-Za-z0-9_]+)\s*\(", text))
         assert used and used <= set(declared), used - set(declared)
+
+
+def test_mixed_radix_stockham_index_formulas():
+    """The index arithmetic of the generic kernels' transform (common.cuh: block_dft / slot_dft / tiled_pass), restated
+    in numpy: one pass per prime factor (4 before 2, then odd primes ascending); a pass of radix r maps butterfly
+    j = jh Ns + k from x[j + i M/r] to y[(jh r + q) Ns + k] with the single table exponent i (k + q Ns) M / (Ns r),
+    which stays below M for the pass twiddle alone (i k M / (Ns r)).  Checked against numpy's FFT for composite, prime
+    and power-of-two lengths."""
+    import numpy as np
+
+    def radices(M):
+        out, rem = [], M
+        while rem > 1:
+            r = rem
+            if rem % 4 == 0:
+                r = 4
+            elif rem % 2 == 0:
+                r = 2
+            else:
+                p = 3
+                while p * p <= rem:
+                    if rem % p == 0:
+                        r = p
+                        break
+                    p += 2
+            out.append(r)
+            rem //= r
+        return out
+
+    def transform(xin):
+        M = len(xin)
+        tw = np.exp(2j * np.pi * np.arange(M) / M)
+        x, Ns = xin.astype(np.complex128), 1
+        for r in radices(M):
+            L, step = M // r, M // (Ns * r)
+            y = np.empty(M, dtype=np.complex128)
+            for o in range(M):
+                k, t = o % Ns, o // Ns
+                q, jh = t % r, t // r
+                j = jh * Ns + k
+                e = (k + q * Ns) * step
+                assert e < M and (r - 1) * k * step < M
+                idx = (np.arange(r) * e) % M
+                y[o] = np.sum(x[j + np.arange(r) * L] * tw[idx])
+            x, Ns = y, Ns * r
+        return x
+
+    rng = np.random.default_rng(3)
+    assert radices(1000) == [4, 2, 5, 5, 5] and radices(48) == [4, 4, 3] and radices(202) == [2, 101]
+    for M in (2, 6, 10, 12, 24, 48, 64, 66, 100, 126, 202, 240, 250, 384, 1000):
+        x = rng.standard_normal(M) + 1j * rng.standard_normal(M)
+        ref = np.fft.ifft(x) * M
+        assert np.abs(transform(x) - ref).max() <= 1e-11 * np.abs(ref).max(), M
