@@ -175,12 +175,9 @@ __global__ void __launch_bounds__(1024) k_pfbch_analysis_tiled(const float* __re
             const float2* xw = Xin + (fl + p) * M - 1 - b;
             const float* hw = taps + b;
             float2 acc = make_float2(0.f, 0.f);
-            for (int n = (int)p - 1; n >= 0; n--) {          // oldest sample first (src/dotprod/mod.rs:36-39)
-                const float c = hw[n * M];
-                const float2 v = xw[-(int)(n * M)];
-                acc.x = fmaf(c, v.x, acc.x);
-                acc.y = fmaf(c, v.y, acc.y);
-            }
+#pragma unroll 4
+            for (int n = (int)p - 1; n >= 0; n--)            // oldest sample first (src/dotprod/mod.rs:36-39); packed FFMA2
+                acc = __ffma2_rn(xw[-(int)(n * M)], make_float2(hw[n * M], hw[n * M]), acc);
             A[fl * M + (M - 1 - b)] = make_float2(acc.x, -acc.y);
         }
         __syncthreads();

@@ -299,12 +299,9 @@ __global__ void __launch_bounds__(1024) k_analysis_tiled(const float* __restrict
             const float2* xs = Xin + fl * M2 + P * M - 1 - b;
             const float* hs = taps + b;
             float2 acc = make_float2(0.f, 0.f);
-            for (int n = (int)P - 1; n >= 0; n--) {
-                const float c = hs[n * M];
-                const float2 v = xs[-(int)(n * M)];
-                acc.x = fmaf(c, v.x, acc.x);
-                acc.y = fmaf(c, v.y, acc.y);
-            }
+#pragma unroll 4
+            for (int n = (int)P - 1; n >= 0; n--)            // one packed FFMA2 per tap (complex sample x broadcast real tap)
+                acc = __ffma2_rn(xs[-(int)(n * M)], make_float2(hs[n * M], hs[n * M]), acc);
             const int par = (flag0 + (int)((f0 + fl) & 1)) & 1;
             uint32_t dst = b + (par ? M2 : 0);
             if (dst >= M) dst -= M;
@@ -383,11 +380,11 @@ __global__ void __launch_bounds__(1024) k_synth_wola_tiled(const float* __restri
             const float* hs = taps + i;
             // two banks (even / odd lag), each summed oldest first, then added (upstream y0 + y1)
             float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll 4
             for (int n = (int)(2 * m) - 1; n >= 0; n--) {
                 const float c0 = hs[(2 * n) * M2], c1 = hs[(2 * n + 1) * M2];
-                const float2 u0 = us[-(int)((2 * n) * M)], u1 = us[-(int)((2 * n + 1) * M)];
-                a0.x = fmaf(c0, u0.x, a0.x); a0.y = fmaf(c0, u0.y, a0.y);
-                a1.x = fmaf(c1, u1.x, a1.x); a1.y = fmaf(c1, u1.y, a1.y);
+                a0 = __ffma2_rn(us[-(int)((2 * n) * M)], make_float2(c0, c0), a0);
+                a1 = __ffma2_rn(us[-(int)((2 * n + 1) * M)], make_float2(c1, c1), a1);
             }
             y[f0 * (long long)M2 + it] = make_float2(a0.x + a1.x, a0.y + a1.y);
         }
